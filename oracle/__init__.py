@@ -1,0 +1,173 @@
+"""oracle -- CPU checker for the VLGAE structured-inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+package; nothing under ``vlgae_b200/`` does (the product path fails loudly
+when its CUDA library is missing instead of falling back to this).
+
+It wraps ``oracle/dmv_oracle.c`` (a plain-C restatement of the reference's
+chart DP, see that file's header for the file:line map) and restates in numpy
+the small tensor glue around it:
+
+* ``merge``                 -> /root/reference/src/model/torch_struct/distributions.py:253-265
+* ``gather_logit_simple``   -> /root/reference/src/model/joint.py:406-419
+* ``gather_logit_reduced``  -> /root/reference/src/model/joint.py:421-432
+
+Parity pin: the reference has no tests or golden vectors for this path, so
+the restatement is pinned against outputs of the reference itself (imported
+in the build container by ``tests/golden/gen_golden.py``; fixtures committed
+under ``tests/golden/``) and against ``oracle/bruteforce.py``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle_dmv.so")
+
+# /root/reference/src/model/torch_struct/dmv.py:7-15
+NOCHILD, HASCHILD, LEFT, RIGHT, GO, STOP = 1, 0, 0, 1, 0, 1
+# /root/reference/src/model/torch_struct/semirings/semirings.py:16 (import-time value)
+NEGINF = -1e12
+# /root/reference/src/__init__.py:110
+INF = 1e20
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (``make -C oracle``)."""
+    src = os.path.join(_HERE, "dmv_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "-s"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a, ct):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def merge(dec, attach, root, one=0.0, zero=NEGINF):
+    """Prepend ROOT as position 0 (distributions.py:253-265).  Always float32."""
+    dec, attach, root = _f32(dec), _f32(attach), _f32(root)
+    B, n = dec.shape[:2]
+    N = n + 1
+    attach_w = np.full((B, N, N, 2), zero, dtype=np.float32)
+    dec_w = np.full((B, N, 2, 2, 2), zero, dtype=np.float32)
+    attach_w[:, 0, 1:, NOCHILD] = root
+    attach_w[:, 1:, 1:, :] = attach
+    dec_w[:, 0, RIGHT, :, :] = one
+    dec_w[:, 1:] = dec
+    return dec_w, attach_w
+
+
+def dmv_log(dec, attach, lengths, *, mask_zero=NEGINF, trim=False, gZ=None, want_grad=True, f64=False):
+    """Inside pass in the log semiring + explicit reverse pass.
+
+    Returns ``(Z [B], gdec [B,N,2,2,2] | None, gattach [B,N,N,2] | None)``;
+    ``gattach`` is what ``DMV1o.marginals`` / ``autograd.grad(partition.sum(), attach)`` return.
+    """
+    dec, attach = _f32(dec), _f32(attach)
+    lengths = np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))
+    B, N = dec.shape[:2]
+    assert dec.shape == (B, N, 2, 2, 2) and attach.shape == (B, N, N, 2) and lengths.shape == (B,)
+    rt, ct = (np.float64, ctypes.c_double) if f64 else (np.float32, ctypes.c_float)
+    Z = np.zeros(B, dtype=rt)
+    gdec = np.zeros((B, N, 2, 2, 2), dtype=rt) if want_grad else None
+    gatt = np.zeros((B, N, N, 2), dtype=rt) if want_grad else None
+    gz = None if gZ is None else np.ascontiguousarray(np.asarray(gZ, dtype=rt).reshape(B))
+    fn = lib().vlgae_oracle_dmv_log_f64 if f64 else lib().vlgae_oracle_dmv_log_f32
+    fn.restype = ctypes.c_int
+    rc = fn(_p(dec, ctypes.c_float), _p(attach, ctypes.c_float), _p(lengths, ctypes.c_int64), ctypes.c_int(B),
+            ctypes.c_int(N), ctypes.c_float(mask_zero), ctypes.c_int(int(trim)), _p(gz, ct), _p(Z, ct), _p(gdec, ct),
+            _p(gatt, ct))
+    if rc:
+        raise ValueError(f"oracle dmv_log failed: rc={rc} (2 = length outside [1, N-1])")
+    return Z, gdec, gatt
+
+
+def dmv_viterbi(dec, attach, lengths, *, mask_zero=NEGINF, trim=False, f64=False):
+    """Max semiring + first-max back-pointer decode.
+
+    Returns ``(best [B], heads [B,N] int64, arcs [B,N,N,2], gdec [B,N,2,2,2])`` where ``arcs`` is
+    ``DMV1o.argmax`` and ``heads[b, c]`` is the head of word ``c`` (0 = ROOT; column 0 and padding are 0).
+    """
+    dec, attach = _f32(dec), _f32(attach)
+    lengths = np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))
+    B, N = dec.shape[:2]
+    rt, ct = (np.float64, ctypes.c_double) if f64 else (np.float32, ctypes.c_float)
+    best = np.zeros(B, dtype=rt)
+    heads = np.zeros((B, N), dtype=np.int64)
+    arcs = np.zeros((B, N, N, 2), dtype=rt)
+    gdec = np.zeros((B, N, 2, 2, 2), dtype=rt)
+    fn = lib().vlgae_oracle_dmv_viterbi_f64 if f64 else lib().vlgae_oracle_dmv_viterbi_f32
+    fn.restype = ctypes.c_int
+    rc = fn(_p(dec, ctypes.c_float), _p(attach, ctypes.c_float), _p(lengths, ctypes.c_int64), ctypes.c_int(B),
+            ctypes.c_int(N), ctypes.c_float(mask_zero), ctypes.c_int(int(trim)), _p(best, ct),
+            _p(heads, ctypes.c_int64), _p(arcs, ct), _p(gdec, ct))
+    if rc:
+        raise ValueError(f"oracle dmv_viterbi failed: rc={rc}")
+    return best, heads, arcs, gdec
+
+
+def deptree(arc, lengths=None, *, semiring="log", fill=NEGINF, mask_zero=NEGINF, f64=False):
+    """Arc-factored projective CRF (``DependencyCRF``), deptree.py:25-76.
+
+    Returns ``(value [B], marginals-or-indicator [B,N,N], heads [B,N])``.
+    """
+    arc = _f32(arc)
+    B, N = arc.shape[:2]
+    if lengths is None:
+        lengths = np.full(B, N - 1)
+    lengths = np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))
+    rt, ct = (np.float64, ctypes.c_double) if f64 else (np.float32, ctypes.c_float)
+    out = np.zeros(B, dtype=rt)
+    marg = np.zeros((B, N, N), dtype=rt)
+    heads = np.zeros((B, N), dtype=np.int64)
+    fn = lib().vlgae_oracle_deptree_f64 if f64 else lib().vlgae_oracle_deptree_f32
+    fn.restype = ctypes.c_int
+    rc = fn(_p(arc, ctypes.c_float), _p(lengths, ctypes.c_int64), ctypes.c_int(B), ctypes.c_int(N),
+            ctypes.c_float(fill), ctypes.c_float(mask_zero), ctypes.c_int(1 if semiring == "max" else 0), _p(out, ct),
+            _p(marg, ct), _p(heads, ctypes.c_int64))
+    if rc:
+        raise ValueError(f"oracle deptree failed: rc={rc}")
+    return out, marg, heads
+
+
+def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, neg=-INF):
+    """``attmap[b,a,q,v] = <txt[b,q,:], vis[a,v,:]>`` then the two masked fills (joint.py:406-419)."""
+    vis_feat, txt_feat = _f32(vis_feat), _f32(txt_feat)
+    A, V, D = vis_feat.shape
+    B, Q, _ = txt_feat.shape
+    att = (txt_feat.reshape(B * Q, D) @ vis_feat.reshape(A * V, D).T).reshape(B, Q, A, V).transpose(0, 2, 1, 3)
+    att = np.ascontiguousarray(att)
+    vm = np.asarray(vis_mask, dtype=bool)[None, :, None, :]  # align_as -> [1, A, 1, V]
+    tm = np.asarray(txt_mask, dtype=bool)[:, None, :, None]  # align_as -> [B, 1, Q, 1]
+    att[np.broadcast_to(~vm, att.shape)] = neg
+    att[np.broadcast_to(~tm, att.shape)] = neg
+    return att
+
+
+def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, neg=-INF):
+    """max over V, marginal-weighted mean over Q (joint.py:421-432) -> [B, A]."""
+    att = gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, neg)
+    maxatt = att.max(-1)
+    tm = _f32(txt_marginal)
+    return (maxatt * tm[:, None, :]).sum(-1) / tm.sum(1, keepdims=True)
