@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- sentences/sec of the DMV hot path (inside + outside + Viterbi, len <= 40) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one cfg2 batch per GPU (BASELINE.json configs[1]: 128 captions,
+ragged lengths 4..40 sorted descending, fp32 merged score tensors): log-semiring inside, the explicit outside
+sweep (arc + decision expected counts) and max-semiring Viterbi with head decode, all in ONE kernel launch
+(vlgae_dmv_parse).  Sentences shard across GPUs with no data-path collective (weak scaling: 128 per GPU).
+
+Prints ONE JSON line on rank 0 (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+BATCH_PER_GPU = 128
+MAX_LEN = 40
+MASK_ZERO = -1e12
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ----------------------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------------------
+def make_lengths(B, seed):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    L = torch.randint(4, MAX_LEN + 1, (B,), generator=g).sort(descending=True).values
+    L[0] = MAX_LEN
+    return L
+
+
+def make_batch_cpu(B, seed):
+    """Merged score tensors of one batch, built on the host with the oracle's merge."""
+    import torch
+
+    import oracle
+
+    g = torch.Generator().manual_seed(seed)
+    n = MAX_LEN
+    dec = torch.randn(B, n, 2, 2, 2, generator=g).log_softmax(-1)
+    attach = torch.randn(B, n, n, 2, generator=g).log_softmax(2)
+    root = torch.randn(B, n, generator=g).log_softmax(-1)
+    md, ma = oracle.merge(dec.numpy(), attach.numpy(), root.numpy())
+    return md, ma, make_lengths(B, seed).numpy().astype(np.int64)
+
+
+def work_counts(lengths):
+    """Algorithmic work of inside + outside + Viterbi: split-point terms T(N) = N^3 - N per
+    chart sweep; MUFU ops = 2 T + 3 N (N - 1); FP32-pipe ops ~ 10 T; HBM bytes = 16 N^2 + 64 N + 8 len + 16."""
+    N = np.asarray(lengths, dtype=np.float64) + 1
+    T = N ** 3 - N
+    return dict(mufu=float((2 * T + 3 * N * (N - 1)).sum()), fp32=float((10 * T).sum()),
+                hbm_bytes=float((16 * N * N + 64 * N + 8 * (N - 1) + 16).sum()))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.timed = False
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.timed, mhz))
+                if self.timed:
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        timed = [m for t, m in self.samples if t] or [m for _, m in self.samples[-3:]]
+        return {"sm_mhz": float(np.median(timed)) if timed else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len([1 for t, _ in self.samples if t])}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU legs (oracle = C port of the reference's algorithm; the Python reference cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------------
+def oracle_step(md, ma, L, threads):
+    """inside + outside + Viterbi with the oracle, sentences sharded over `threads` host threads
+    (ctypes releases the GIL, so the C sweeps run concurrently)."""
+    import oracle
+
+    B = len(L)
+    if threads <= 1 or B < 2:
+        oracle.dmv_log(md, ma, L, trim=True)
+        oracle.dmv_viterbi(md, ma, L, trim=True)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    # interleave so every shard gets the same mix of lengths
+    shards = [np.arange(k, B, threads) for k in range(min(threads, B))]
+
+    def run(idx):
+        a, b, c = np.ascontiguousarray(md[idx]), np.ascontiguousarray(ma[idx]), np.ascontiguousarray(L[idx])
+        oracle.dmv_log(a, b, c, trim=True)
+        oracle.dmv_viterbi(a, b, c, trim=True)
+
+    with ThreadPoolExecutor(len(shards)) as ex:
+        list(ex.map(run, shards))
+
+
+def cpu_baseline(md, ma, L, budget_s=10.0):
+    """Scalar oracle port on ONE host core over the whole cfg2 batch, repeated for ~budget_s seconds."""
+    import oracle
+
+    oracle.lib()
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        oracle_step(md, ma, L, 1)
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or reps >= 50:
+            break
+    return {"value": len(L) * reps / el, "unit": "sentences/s", "cores": 1, "kind": "port",
+            "sample": f"{reps} x the full cfg2 batch ({len(L)} sentences) in {el:.1f} s, oracle/dmv_oracle.c "
+                      f"(inside+outside+Viterbi, fp32)"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    oracle.lib()
+    threads = os.cpu_count() or 1
+    md, ma, L = make_batch_cpu(BATCH_PER_GPU, 2)
+    # calibrate, then bound each step so that the whole run ends within ~2 minutes
+    t0 = time.perf_counter()
+    oracle_step(md[:threads * 2], ma[:threads * 2], L[:threads * 2], threads)
+    rate = (threads * 2) / max(time.perf_counter() - t0, 1e-6)
+    budget = 90.0 / max(args.steps + args.warmup, 1)
+    S = int(max(min(BATCH_PER_GPU, rate * budget), min(threads, BATCH_PER_GPU)))
+    idx = np.linspace(0, BATCH_PER_GPU - 1, S).round().astype(int)  # same length mix as the full batch
+    smd, sma, sL = np.ascontiguousarray(md[idx]), np.ascontiguousarray(ma[idx]), np.ascontiguousarray(L[idx])
+    for _ in range(args.warmup):
+        oracle_step(smd, sma, sL, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(smd, sma, sL, threads)
+    el = time.perf_counter() - t0
+    value = S * args.steps / el
+    line = {
+        "impl": "reference", "metric": "sentences/sec (inside+outside+Viterbi, len<=40)", "value": value,
+        "unit": "sentences/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 128 captions, len 4..40 ragged sorted desc (BASELINE.json configs[1]), "
+                               "DMV inside+outside+Viterbi", "sample_sentences_per_step": S},
+        "cpu_baseline": {"value": value, "unit": "sentences/s", "cores": threads, "kind": "port",
+                         "sample": f"{S} of the 128 cfg2 sentences per step (same length mix), {threads} host threads; "
+                                   "the reference is pure Python/PyTorch and cannot travel to the GPU box, so this "
+                                   "is oracle/dmv_oracle.c, the C restatement pinned to it"},
+        "e2e": {"value": value, "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+
+    from vlgae_b200 import ops
+    from vlgae_b200._lib import check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    L_ = lib()
+    B, N = BATCH_PER_GPU, MAX_LEN + 1
+
+    # ---- inputs: a pool of distinct batches whose footprint exceeds L2, so every step reads cold data ----
+    md0, ma0, L0 = make_batch_cpu(B, 2 + 1000 * rank)
+    step_bytes = md0.nbytes + ma0.nbytes + L0.nbytes + md0.nbytes + ma0.nbytes + B * 4 * 2 + B * N * 8
+    pool_n = int(np.ceil(2.2 * L2_BYTES / step_bytes))
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = []
+    for k in range(pool_n):
+        if k == 0:
+            md, ma = torch.from_numpy(md0).to(dev), torch.from_numpy(ma0).to(dev)
+        else:  # same construction as make_batch_cpu, different draws, built on the device
+            from vlgae_b200.torch_struct import DMV1o
+
+            dec = torch.randn(B, MAX_LEN, 2, 2, 2, generator=gen, device=dev).log_softmax(-1)
+            att = torch.randn(B, MAX_LEN, MAX_LEN, 2, generator=gen, device=dev).log_softmax(2)
+            root = torch.randn(B, MAX_LEN, generator=gen, device=dev).log_softmax(-1)
+            md, ma = DMV1o.merge(dec, att, root)
+        pool.append((md, ma, torch.from_numpy(L0).to(dev), ops.ParseBuffers(B, N, dev)))
+    torch.cuda.synchronize()
+
+    def step(k):
+        md, ma, L, out = pool[k % pool_n]
+        ops.dmv_parse(md, ma, L, out=out, prepared=True)
+
+    # ---- parity gate on the timed configuration ----
+    import oracle
+
+    step(0)
+    torch.cuda.synchronize()
+    out0 = pool[0][3]
+    oZ, ogdec, ogatt = oracle.dmv_log(md0, ma0, L0, trim=True)
+    obest, oheads, _, _ = oracle.dmv_viterbi(md0, ma0, L0, trim=True)
+    parity = {
+        "heads_bit_exact": bool(np.array_equal(out0.heads.cpu().numpy(), oheads)),
+        "best_bit_exact": bool(np.array_equal(out0.best.cpu().numpy(), obest)),
+        "Z_max_rel": float(np.abs((out0.Z.cpu().numpy() - oZ) / oZ).max()),
+        "marginal_max_abs": float(np.abs(out0.gattach.cpu().numpy() - ogatt).max()),
+    }
+
+    # ---- roofline denominators measured live (MUFU / FP32 issue rate are not in MEASURED_PEAKS.json) ----
+    ms = ctypes.c_float()
+    nops = ctypes.c_double()
+    peaks = {}
+    for name, fn in (("mufu", L_.vlgae_microbench_mufu), ("fp32", L_.vlgae_microbench_fp32)):
+        best = 0.0
+        for _ in range(3):
+            check(fn(4000, ctypes.byref(ms), ctypes.byref(nops), None), "microbench")
+            best = max(best, nops.value / (ms.value * 1e-3))
+        peaks[name] = best
+
+    # ---- timed region ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.timed = True
+    ev0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.timed = False
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    elapsed_ms = ev0.elapsed_time(ev1)
+
+    # ---- end to end: host buffers -> H2D -> kernels -> D2H, through the C ABI's host entry point ----
+    pin = lambda a: torch.from_numpy(a).pin_memory()  # noqa: E731
+    h_md, h_ma, h_L = pin(md0), pin(ma0), pin(L0)
+    h_Z, h_best = torch.empty(B).pin_memory(), torch.empty(B).pin_memory()
+    h_gatt = torch.empty((B, N, N, 2)).pin_memory()
+    h_gdec = torch.empty((B, N, 2, 2, 2)).pin_memory()
+    h_heads = torch.empty((B, N), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def e2e_step():
+        check(L_.vlgae_dmv_parse_host(h_md.data_ptr(), h_ma.data_ptr(), h_L.data_ptr(), B, N, MASK_ZERO,
+                                      h_Z.data_ptr(), h_gdec.data_ptr(), h_gatt.data_ptr(), h_best.data_ptr(),
+                                      h_heads.data_ptr(), stream), "vlgae_dmv_parse_host")
+
+    e2e_steps = max(10, min(args.steps, 200))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronises the stream itself (results are in host memory on return)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop()
+    e2e_ok = bool(np.array_equal(h_heads.numpy(), oheads))
+    h2d = md0.nbytes + ma0.nbytes + L0.nbytes
+    d2h = h_Z.numel() * 4 + h_best.numel() * 4 + h_gatt.numel() * 4 + h_gdec.numel() * 4 + h_heads.numel() * 8
+
+    # ---- max over ranks ----
+    t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        wc = work_counts(L0)
+        per_launch_s = elapsed_ms * 1e-3 / args.steps
+        achieved = wc["mufu"] / per_launch_s
+        value = B * world * args.steps / (elapsed_ms * 1e-3)
+        cb = cpu_baseline(md0, ma0, L0) if world == 1 else None
+        line = {
+            "metric": "sentences/sec (inside+outside+Viterbi, len<=40)", "value": value, "unit": "sentences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: 128 captions per GPU, len 4..40 ragged sorted desc (BASELINE.json "
+                                   "configs[1]), DMV inside+outside+Viterbi in one launch",
+                       "batch_per_gpu": B, "max_len": MAX_LEN, "parallelism": f"sentence-sharded x{world}, no collective",
+                       "l2": f"inputs rotate through a pool of {pool_n} distinct batches "
+                             f"({pool_n * step_bytes / 2**20:.0f} MiB > L2), no flush needed"},
+            "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "api": "vlgae_dmv_parse_host (pinned host buffers; H2D + kernel + D2H + sync per step)",
+                    "heads_bit_exact": e2e_ok},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "sfu", "achieved": achieved / 1e9, "peak": peaks["mufu"] / 1e9, "unit": "Gop/s",
+                         "frac": achieved / peaks["mufu"], "traffic": None,
+                         "kernel": "dmv_kernel<128,true>", "algorithmic_mufu_ops_per_launch": wc["mufu"],
+                         "peak_source": "measured live: ex2.approx.f32 microbenchmark (vlgae_microbench_mufu)",
+                         "fp32_frac": (wc["fp32"] / per_launch_s) / peaks["fp32"],
+                         "fp32_peak_gops": peaks["fp32"] / 1e9,
+                         "hbm_gbs": wc["hbm_bytes"] / per_launch_s / 1e9},
+            "parity": parity,
+            "clocks": sampler.summary(),
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 20  # the CPU arm's default: 20 bounded steps
+            args.warmup = min(args.warmup, 2)
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

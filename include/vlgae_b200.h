@@ -1,0 +1,132 @@
+/*
+ * vlgae_b200.h -- C ABI of libvlgae_b200.so (sm_100a).
+ *
+ * The drop-in boundary for VLGAE's structured-inference hot path.  The
+ * reference (LouChao98/VLGAE) is pure Python: its "FFI" for this path is the
+ * operator API of src/model/torch_struct and the gather_logit implementation
+ * group of src/model/joint.py.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root).  The Python
+ * mirror of that API (vlgae_b200/torch_struct, vlgae_b200/alignment.py) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes; every data pointer is a DEVICE pointer unless
+ *     the name ends in _host; tensors are contiguous, row-major, float32
+ *     (lengths: int64) exactly as the reference holds them.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Calls only enqueue work; nothing synchronises the host.
+ *   - return 0 on success; nonzero = VLGAE_E_*; vlgae_last_error() gives the
+ *     text (thread-local).  There is no CPU fallback anywhere.
+ *
+ * Tensor layouts (reference: src/model/torch_struct/dmv.py:24-31)
+ *   dec     [B][N][2 dir][2 val][2 decision]   merged (ROOT at position 0)
+ *   attach  [B][N][N][2 val]   (head, child, valence)   merged
+ *   lengths [B]  int64, words without ROOT, 0 <= len <= N-1
+ *   constants: LEFT=0 RIGHT=1, HASCHILD=0 NOCHILD=1, GO=0 STOP=1 (dmv.py:7-15)
+ */
+#ifndef VLGAE_B200_H_
+#define VLGAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLGAE_OK 0
+#define VLGAE_E_INVALID 1   /* bad argument (null pointer, N out of range, ...) */
+#define VLGAE_E_CUDA 2      /* a CUDA runtime call failed                        */
+#define VLGAE_E_WORKSPACE 3 /* workspace too small                               */
+#define VLGAE_E_ARCH 4      /* device is not sm_100                              */
+
+#define VLGAE_DMV_MAX_N 256 /* chart positions incl. ROOT (reference data: <= 51) */
+
+/* ABI version (bumped on any signature change). */
+int vlgae_version(void);
+/* Text of the last error on this thread. */
+const char *vlgae_last_error(void);
+
+/*
+ * Bytes of device scratch the DMV entry points need for a batch of B sentences
+ * padded to N positions.  Charts live in shared memory when they fit (N <= ~80);
+ * otherwise each resident CTA keeps its chart in this workspace (L2-resident).
+ * May return 0.
+ */
+size_t vlgae_dmv_workspace_bytes(int B, int N);
+
+/*
+ * Log semiring: Z and the expected counts.
+ * Replaces  DMV1o(...).partition              src/model/torch_struct/distributions.py:190-193
+ *           -> _Struct.sum -> DMV1oStruct._dp  helpers.py:101-116, dmv.py:19-66
+ *     and   torch.autograd.grad(partition.sum(), [dec, attach]) / DMV1o(...).marginals
+ *           src/model/torch_struct/helpers.py:118-154 (autograd through the chart),
+ *           here an explicit reverse sweep in the same kernel.
+ *   gZ      [B] upstream gradient of Z (NULL = ones)
+ *   Z       [B]                       (the reference returns [B,1]; same memory)
+ *   gdec    [B][N][2][2][2] or NULL   d(sum_b gZ[b] Z[b]) / d dec
+ *   gattach [B][N][N][2]    or NULL   d(...) / d attach  (= arc marginals when gZ = 1)
+ * Padded positions receive exact zeros.  If both gdec and gattach are NULL only
+ * the inside pass runs.
+ * mask_zero: value written by the single-root mask (dmv.py:63; class attr zero = -1e12).
+ */
+int vlgae_dmv_inside_outside(const float *dec, const float *attach, const int64_t *lengths, int B, int N,
+                             float mask_zero, const float *gZ, float *Z, float *gdec, float *gattach, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+/*
+ * Max semiring: best score, heads, dense arc indicator, decision counts.
+ * Replaces  DMV1o(...).max     distributions.py:116-123
+ *           DMV1o(...).argmax  distributions.py:125-133 -> helpers.py:118-154 with MaxSemiring
+ *                              (semirings.py:187-207; torch.max first-index tie rule)
+ *   best   [B]
+ *   heads  [B][N] int64 or NULL: heads[b][c] = head of word c (1..len), 0 elsewhere
+ *                                (what callers build from argmax.sum(-1).nonzero(),
+ *                                 ldndmv.py:301-303, joint.py:256-258)
+ *   arcs   [B][N][N][2] or NULL: the dense 0/1 tensor `argmax` returns (= d max / d attach)
+ *   gdec   [B][N][2][2][2] or NULL: d max / d dec (decision counts of the best tree)
+ */
+int vlgae_dmv_viterbi(const float *dec, const float *attach, const int64_t *lengths, int B, int N, float mask_zero,
+                      float *best, int64_t *heads, float *arcs, float *gdec, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
+/*
+ * Both of the above in ONE launch (log-semiring CTAs and max-semiring CTAs run side by side):
+ * the "inside + outside + Viterbi" step BASELINE.json's metric is quoted on
+ * (src/model/joint.py:251-256 runs exactly this pair per training step).
+ */
+int vlgae_dmv_parse(const float *dec, const float *attach, const int64_t *lengths, int B, int N, float mask_zero,
+                    const float *gZ, float *Z, float *gdec, float *gattach, float *best, int64_t *heads, float *arcs,
+                    float *vgdec, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Same as vlgae_dmv_parse but with HOST buffers: copies inputs to the device, runs, copies the
+ * results back and synchronises `stream` before returning (the end-to-end call a non-torch
+ * embedder would make).  Any output pointer may be NULL.
+ */
+int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                         float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                         int64_t *heads_host, void *stream);
+
+/*
+ * DMV1o.merge  (distributions.py:253-265): prepend ROOT.
+ *   dec [B][n][2][2][2], attach [B][n][n][2], root [B][n]  ->  dec_w [B][n+1][2][2][2], attach_w [B][n+1][n+1][2]
+ */
+int vlgae_dmv_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
+                    float *dec_w, float *attach_w, void *stream);
+
+/* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
+int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);
+
+/*
+ * Microbenchmarks used by bench.py to measure the roofline denominators on the box:
+ * MUFU (ex2.approx.f32) ops/s and FP32-pipe (FADD) ops/s over the whole chip.
+ * Each writes elapsed milliseconds and the number of operations issued.
+ */
+int vlgae_microbench_mufu(int iters, float *ms_host, double *ops_host, void *stream);
+int vlgae_microbench_fp32(int iters, float *ms_host, double *ops_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLGAE_B200_H_ */

@@ -174,7 +174,7 @@ int FN(vlgae_oracle_dmv_log)(const float *dec_all, const float *attach_all, cons
         const float *dec = dec_all + (size_t)b * N * 8;
         const float *attach = attach_all + (size_t)b * N * N * 2;
         int len = (int)lengths[b];
-        if (len < 1 || len > N - 1) { chart_free(&c); chart_free(&g); free(scratch); return 2; }
+        if (len < 0 || len > N - 1) { chart_free(&c); chart_free(&g); free(scratch); return 2; }
         int Nb = trim ? len + 1 : N;
         /* run on a compact [Nb][Nb] chart; inputs keep stride N */
         forward_one(dec, attach, N, Nb, len, (REAL)mask_zero, 0, &c, 0, 0, 0, 0, scratch);
@@ -290,7 +290,7 @@ int FN(vlgae_oracle_dmv_viterbi)(const float *dec_all, const float *attach_all, 
         const float *dec = dec_all + (size_t)b * N * 8;
         const float *attach = attach_all + (size_t)b * N * N * 2;
         int len = (int)lengths[b];
-        if (len < 1 || len > N - 1) return 2;
+        if (len < 0 || len > N - 1) return 2;
         int Nb = trim ? len + 1 : N;
         forward_one(dec, attach, N, Nb, len, (REAL)mask_zero, 1, &c, bpXL, bpXR, bpCL, bpCR, scratch);
         int64_t *heads = heads_all ? heads_all + (size_t)b * N : 0;
@@ -359,7 +359,7 @@ int FN(vlgae_oracle_deptree)(const float *arc_all, const int64_t *lengths, int B
 #define M(Q, a, b) Q[(size_t)(a) * N + (b)]
     for (int b = 0; b < B; ++b) {
         int len = (int)lengths[b];
-        if (len < 1 || len > N - 1) return 2;
+        if (len < 0 || len > N - 1) return 2;
         const float *arc = arc_all + (size_t)b * n2;
         for (int h = 0; h < N; ++h)
             for (int cc = 0; cc < N; ++cc) M(A, h, cc) = (h > len || cc > len) ? (REAL)fill : (REAL)M(arc, h, cc);

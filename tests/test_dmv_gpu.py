@@ -1,0 +1,248 @@
+"""Parity of the CUDA DMV path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances are BASELINE.json's: Viterbi heads / scores bit-exact, log-partition 1e-4 relative,
+arc marginals 1e-5 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+Z_RTOL, MARG_ATOL, DEC_ATOL = 1e-4, 1e-5, 4e-5
+DMV_CASES = ["dmv_tiny_ragged", "dmv_cfg1", "dmv_cfg1_ragged", "dmv_ties_q025", "dmv_ties_q1", "dmv_ties_zero",
+             "dmv_len40"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from vlgae_b200._lib import lib
+
+    lib()
+    return torch.device("cuda:0")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def synth(B, n, seed, lengths=None, quant=None):
+    g = torch.Generator().manual_seed(seed)
+    dec = torch.randn(B, n, 2, 2, 2, generator=g).log_softmax(-1)
+    attach = torch.randn(B, n, n, 2, generator=g).log_softmax(2)
+    root = torch.randn(B, n, generator=g).log_softmax(-1)
+    if quant:
+        dec, attach, root = [(t / quant).round() * quant for t in (dec, attach, root)]
+    if lengths is None:
+        lengths = torch.full((B,), n, dtype=torch.long)
+    md, ma = oracle.merge(dec.numpy(), attach.numpy(), root.numpy())
+    return md, ma, np.asarray(lengths, dtype=np.int64)
+
+
+def check_all(md, ma, L, dev, marg_atol=MARG_ATOL):
+    from vlgae_b200 import ops
+
+    out = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev), want_arcs=True, want_vgdec=True)
+    torch.cuda.synchronize()
+    Z, gdec, gatt = oracle.dmv_log(md, ma, L, trim=True)
+    best, heads, arcs, vgdec = oracle.dmv_viterbi(md, ma, L, trim=True)
+    np.testing.assert_allclose(out.Z.cpu().numpy(), Z, rtol=Z_RTOL)
+    np.testing.assert_allclose(out.gattach.cpu().numpy(), gatt, atol=marg_atol, rtol=0)
+    np.testing.assert_allclose(out.gdec.cpu().numpy(), gdec, atol=4 * marg_atol, rtol=0)
+    np.testing.assert_array_equal(out.best.cpu().numpy(), best)
+    np.testing.assert_array_equal(out.heads.cpu().numpy(), heads)
+    np.testing.assert_array_equal(out.arcs.cpu().numpy(), arcs)
+    np.testing.assert_array_equal(out.vgdec.cpu().numpy(), vgdec)
+    return out
+
+
+@pytest.mark.parametrize("name", DMV_CASES)
+def test_golden_reference_vectors(golden, dev, name):
+    from vlgae_b200 import ops
+
+    g = golden(name)
+    md, ma, L = _t(g["merged_dec"], dev), _t(g["merged_attach"], dev), _t(g["lengths"], dev)
+    Z, gdec, gatt = ops.dmv_inside_outside(md, ma, L)
+    best, heads, arcs, vgdec = ops.dmv_viterbi(md, ma, L, want_gdec=True)
+    np.testing.assert_allclose(Z.cpu().numpy(), g["partition"][:, 0], rtol=Z_RTOL)
+    np.testing.assert_allclose(gatt.cpu().numpy(), g["grad_attach"], atol=MARG_ATOL, rtol=0)
+    np.testing.assert_allclose(gdec.cpu().numpy(), g["grad_dec"], atol=DEC_ATOL, rtol=0)
+    np.testing.assert_array_equal(best.cpu().numpy(), g["max"][:, 0])
+    np.testing.assert_array_equal(heads.cpu().numpy(), g["heads"])
+    np.testing.assert_array_equal(vgdec.cpu().numpy(), g["vgrad_dec"])
+    a = arcs.cpu().numpy()
+    B, N = g["heads"].shape
+    val = np.full((B, N), -1, dtype=np.int8)
+    for b, h, c, v in np.argwhere(a > 0):
+        val[b, c] = v
+    np.testing.assert_array_equal(val, g["arc_valence"])
+    assert set(np.unique(a)) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("name", ["dmv_tiny_ragged", "dmv_cfg1_ragged"])
+def test_merge_matches_reference(golden, dev, name):
+    from vlgae_b200.torch_struct import DMV1o
+
+    g = golden(name)
+    md, ma = DMV1o.merge(_t(g["dec"], dev), _t(g["attach"], dev), _t(g["root"], dev))
+    assert md.dtype == torch.float32 and ma.dtype == torch.float32
+    np.testing.assert_array_equal(md.cpu().numpy(), g["merged_dec"])
+    np.testing.assert_array_equal(ma.cpu().numpy(), g["merged_attach"])
+    md64, _ = DMV1o.merge(_t(g["dec"], dev).double(), _t(g["attach"], dev).double(), _t(g["root"], dev).double())
+    assert md64.dtype == torch.float32  # reference quirk Q3
+
+
+def test_operator_api_like_the_callers(golden, dev):
+    """The call patterns of ldndmv.py:268-281,293-303 and joint.py:251-258 on the mirror API."""
+    from vlgae_b200.torch_struct import DMV1o
+
+    g = golden("dmv_cfg1_ragged")
+    L = _t(g["lengths"], dev)
+    mdec = _t(g["merged_dec"], dev).requires_grad_()
+    mattach = _t(g["merged_attach"], dev).requires_grad_()
+    dist = DMV1o([mdec, mattach], L)
+    Z = dist.partition
+    assert Z.shape == (len(L), 1) and dist.partition is Z  # [B,1] (quirk Q2), lazily cached
+    gd, ga = torch.autograd.grad(Z.sum(), [mdec, mattach])
+    np.testing.assert_allclose(ga.cpu().numpy(), g["grad_attach"], atol=MARG_ATOL)
+    np.testing.assert_allclose(gd.cpu().numpy(), g["grad_dec"], atol=DEC_ATOL)
+    arc_margin = torch.autograd.grad(DMV1o([mdec, mattach], L).partition.sum(), mattach)[0].sum(-1)
+    assert arc_margin.shape == g["grad_attach"].shape[:3]
+    arc = dist.argmax.sum(-1).nonzero()
+    predicted = L.new_zeros(len(L), g["heads"].shape[1])
+    predicted[arc[:, 0], arc[:, 2]] = arc[:, 1]
+    np.testing.assert_array_equal(predicted.cpu().numpy(), g["heads"])
+    np.testing.assert_array_equal(dist.heads.cpu().numpy(), g["heads"])
+    # viterbi training: loss = -max.sum(), gradients to both inputs, scaled upstream grad
+    mx = DMV1o([mdec, mattach], L).max
+    assert mx.shape == (len(L), 1)
+    np.testing.assert_array_equal(mx.detach().cpu().numpy(), g["max"])
+    vgd, vga = torch.autograd.grad((-2.0 * mx).sum(), [mdec, mattach])
+    np.testing.assert_array_equal(vgd.cpu().numpy(), -2.0 * g["vgrad_dec"])
+    np.testing.assert_array_equal((vga != 0).sum(-1).nonzero().cpu().numpy(), arc.cpu().numpy())
+    # marginals property, no-grad partition
+    np.testing.assert_allclose(dist.marginals.cpu().numpy(), g["grad_attach"], atol=MARG_ATOL)
+    with torch.no_grad():
+        Z2 = DMV1o([mdec, mattach], L).partition
+    assert not Z2.requires_grad
+    np.testing.assert_allclose(Z2.cpu().numpy(), g["partition"], rtol=Z_RTOL)
+
+
+def test_gradient_flows_through_merge(golden, dev):
+    from vlgae_b200.torch_struct import DMV1o
+
+    g = golden("dmv_tiny_ragged")
+    dec = _t(g["dec"], dev).requires_grad_()
+    attach = _t(g["attach"], dev).requires_grad_()
+    root = _t(g["root"], dev).requires_grad_()
+    md, ma = DMV1o.merge(dec, attach, root)
+    loss = -DMV1o([md, ma], _t(g["lengths"], dev)).partition.sum()
+    loss.backward()
+    np.testing.assert_allclose(dec.grad.cpu().numpy(), -g["grad_dec"][:, 1:], atol=DEC_ATOL)
+    np.testing.assert_allclose(attach.grad.cpu().numpy(), -g["grad_attach"][:, 1:, 1:], atol=MARG_ATOL)
+    np.testing.assert_allclose(root.grad.cpu().numpy(), -g["grad_attach"][:, 0, 1:, 1], atol=MARG_ATOL)
+
+
+@pytest.mark.parametrize("B,n,seed", [(64, 16, 1), (37, 5, 3), (16, 33, 4), (5, 1, 5), (9, 2, 6)])
+def test_full_length_batches(dev, B, n, seed):
+    check_all(*synth(B, n, seed), dev)
+
+
+def test_cfg2_shape_ragged_sorted(dev):
+    g = torch.Generator().manual_seed(2)
+    L = torch.randint(4, 41, (128,), generator=g).sort(descending=True).values
+    L[0] = 40
+    md, ma, L = synth(128, 40, 2, L)
+    out = check_all(md, ma, L, dev, marg_atol=2e-5)  # fp32 noise floor at len 40 (see test_noise_floor_vs_f64)
+    m = out.gattach.cpu().numpy().sum(-1)
+    for b in range(128):
+        np.testing.assert_allclose(m[b, :, 1:L[b] + 1].sum(0), 1.0, atol=1e-4)
+        assert m[b, :, L[b] + 1:].sum() == 0 and m[b, L[b] + 1:].sum() == 0
+    np.testing.assert_allclose(out.gdec.cpu().numpy().sum((1, 2, 3, 4)), 3 * L + 1, rtol=1e-5)
+
+
+def test_noise_floor_vs_f64(dev):
+    """The CUDA path is no farther from an fp64 evaluation than the fp32 oracle (= the reference's arithmetic)."""
+    from vlgae_b200 import ops
+
+    md, ma, L = synth(32, 40, 21)
+    _, _, g64 = oracle.dmv_log(md, ma, L, f64=True, trim=True)
+    _, _, g32 = oracle.dmv_log(md, ma, L, trim=True)
+    _, _, gpu = ops.dmv_inside_outside(_t(md, dev), _t(ma, dev), _t(L, dev))
+    e_gpu = np.abs(gpu.cpu().numpy() - g64).max()
+    e_ref = np.abs(g32 - g64).max()
+    assert e_gpu < max(2.0 * e_ref, 1e-5), (e_gpu, e_ref)
+
+
+@pytest.mark.parametrize("quant", [1.0, 0.5, 0.25])
+def test_tie_stress(dev, quant):
+    g = torch.Generator().manual_seed(int(quant * 100))
+    L = torch.randint(1, 25, (96,), generator=g)
+    L[0] = 24
+    check_all(*synth(96, 24, 31, L, quant=quant), dev)
+
+
+def test_all_zero_scores_chain(dev):
+    from vlgae_b200 import ops
+
+    B, N = 3, 9
+    md, ma = oracle.merge(np.zeros((B, N - 1, 2, 2, 2)), np.zeros((B, N - 1, N - 1, 2)), np.zeros((B, N - 1)))
+    L = np.array([8, 5, 1])
+    best, heads, arcs, _ = ops.dmv_viterbi(_t(md, dev), _t(ma, dev), _t(L, dev))
+    for b in range(B):
+        assert heads[b, 1:L[b] + 1].tolist() == list(range(0, L[b]))
+    assert arcs[..., 0].sum().item() == 0  # every arc is NOCHILD
+
+
+def test_empty_and_single_word(dev):
+    md, ma, _ = synth(4, 6, 9)
+    check_all(md, ma, np.array([0, 1, 0, 6]), dev)
+
+
+@pytest.mark.parametrize("B,n", [(12, 64), (6, 100), (4, 128)])
+def test_long_sentences(dev, B, n):
+    """n = 64 stays in shared memory (256 threads); n >= 100 uses the global-workspace charts."""
+    g = torch.Generator().manual_seed(n)
+    L = torch.randint(n // 2, n + 1, (B,), generator=g)
+    L[0] = n
+    check_all(*synth(B, n, 40 + n, L), dev, marg_atol=5e-5)
+
+
+def test_cfg3_sweep_small(dev):
+    for n in (8, 16, 32):
+        check_all(*synth(512, n, 3), dev, marg_atol=2e-5)
+
+
+def test_upstream_gradient_scaling(dev):
+    from vlgae_b200 import ops
+
+    md, ma, L = synth(7, 9, 77)
+    gZ = np.linspace(-2, 3, 7).astype(np.float32)
+    Z, gdec, gatt = ops.dmv_inside_outside(_t(md, dev), _t(ma, dev), _t(L, dev), gZ=_t(gZ, dev))
+    _, ogdec, ogatt = oracle.dmv_log(md, ma, L, gZ=gZ)
+    np.testing.assert_allclose(gatt.cpu().numpy(), ogatt, atol=3e-5)
+    np.testing.assert_allclose(gdec.cpu().numpy(), ogdec, atol=1e-4)
+
+
+def test_host_buffer_entry_point(dev):
+    """vlgae_dmv_parse_host: the end-to-end call with host pointers (what bench.py's e2e leg times)."""
+    import ctypes
+
+    from vlgae_b200._lib import check, lib
+
+    md, ma, L = synth(16, 12, 5)
+    B, N = md.shape[:2]
+    Z = np.zeros(B, np.float32); best = np.zeros(B, np.float32)
+    gdec = np.zeros_like(md); gatt = np.zeros_like(ma); heads = np.zeros((B, N), np.int64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    check(lib().vlgae_dmv_parse_host(p(md), p(ma), p(L), B, N, -1e12, p(Z), p(gdec), p(gatt), p(best), p(heads),
+                                     None), "parse_host")
+    oZ, ogdec, ogatt = oracle.dmv_log(md, ma, L)
+    obest, oheads, _, _ = oracle.dmv_viterbi(md, ma, L)
+    np.testing.assert_allclose(Z, oZ, rtol=Z_RTOL)
+    np.testing.assert_allclose(gatt, ogatt, atol=MARG_ATOL)
+    np.testing.assert_array_equal(best, obest)
+    np.testing.assert_array_equal(heads, oheads)

@@ -1,0 +1,177 @@
+// c_api.cu -- the extern "C" boundary declared in include/vlgae_b200.h.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vlgae_b200.h"
+#include "dmv_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return VLGAE_E_CUDA;
+}
+
+int check_dmv(const float *dec, const float *attach, const int64_t *lengths, int B, int N) {
+    if (!dec || !attach || !lengths) return fail(VLGAE_E_INVALID, "%s", "dec, attach and lengths must be non-null");
+    if (B < 0) return fail(VLGAE_E_INVALID, "%s", "B must be >= 0");
+    if (N < 1 || N > VLGAE_DMV_MAX_N) return fail(VLGAE_E_INVALID, "%s", "N must be in [1, 256]");
+    return VLGAE_OK;
+}
+
+int run_dmv(vlgae::DmvArgs &a, int passes, void *workspace, size_t workspace_bytes, void *stream) {
+    if (a.B == 0) return VLGAE_OK;
+    if (!vlgae::dmv_fits_smem(a.N, passes)) {
+        const size_t need = vlgae_dmv_workspace_bytes(a.B, a.N);
+        if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "workspace too small for this N");
+        a.workspace = workspace;
+    }
+    a.npass = passes == 3 ? 2 : 1;
+    a.first_pass = passes == 2 ? 1 : 0;
+    cudaError_t e = vlgae::launch_dmv(a, passes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dmv launch");
+    return VLGAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vlgae_version(void) { return 1; }
+const char *vlgae_last_error(void) { return g_err; }
+
+size_t vlgae_dmv_workspace_bytes(int B, int N) {
+    if (B <= 0 || N < 1 || N > VLGAE_DMV_MAX_N) return 0;
+    if (vlgae::dmv_fits_smem(N, 3)) return 0;
+    return (size_t)vlgae::dmv_grid_for_workspace(B) * vlgae::dmv_chart_bytes(N, 3);
+}
+
+int vlgae_dmv_inside_outside(const float *dec, const float *attach, const int64_t *lengths, int B, int N,
+                             float mask_zero, const float *gZ, float *Z, float *gdec, float *gattach, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    int rc = check_dmv(dec, attach, lengths, B, N);
+    if (rc) return rc;
+    if (!Z) return fail(VLGAE_E_INVALID, "%s", "Z must be non-null");
+    vlgae::DmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dec = dec; a.attach = attach; a.lengths = lengths; a.B = B; a.N = N; a.mask_zero = mask_zero;
+    a.gZ = gZ; a.Z = Z; a.gdec = gdec; a.gattach = gattach;
+    return run_dmv(a, 1, workspace, workspace_bytes, stream);
+}
+
+int vlgae_dmv_viterbi(const float *dec, const float *attach, const int64_t *lengths, int B, int N, float mask_zero,
+                      float *best, int64_t *heads, float *arcs, float *gdec, void *workspace, size_t workspace_bytes,
+                      void *stream) {
+    int rc = check_dmv(dec, attach, lengths, B, N);
+    if (rc) return rc;
+    if (!best) return fail(VLGAE_E_INVALID, "%s", "best must be non-null");
+    vlgae::DmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dec = dec; a.attach = attach; a.lengths = lengths; a.B = B; a.N = N; a.mask_zero = mask_zero;
+    a.best = best; a.heads = heads; a.arcs = arcs; a.vgdec = gdec;
+    return run_dmv(a, 2, workspace, workspace_bytes, stream);
+}
+
+int vlgae_dmv_parse(const float *dec, const float *attach, const int64_t *lengths, int B, int N, float mask_zero,
+                    const float *gZ, float *Z, float *gdec, float *gattach, float *best, int64_t *heads, float *arcs,
+                    float *vgdec, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = check_dmv(dec, attach, lengths, B, N);
+    if (rc) return rc;
+    if (!Z || !best) return fail(VLGAE_E_INVALID, "%s", "Z and best must be non-null");
+    vlgae::DmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dec = dec; a.attach = attach; a.lengths = lengths; a.B = B; a.N = N; a.mask_zero = mask_zero;
+    a.gZ = gZ; a.Z = Z; a.gdec = gdec; a.gattach = gattach;
+    a.best = best; a.heads = heads; a.arcs = arcs; a.vgdec = vgdec;
+    return run_dmv(a, 3, workspace, workspace_bytes, stream);
+}
+
+int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                         float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                         int64_t *heads_host, void *stream) {
+    int rc = check_dmv(dec_host, attach_host, lengths_host, B, N);
+    if (rc) return rc;
+    if (B == 0) return VLGAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nd = (size_t)B * N * 8, na = (size_t)B * N * N * 2;
+    const size_t ws = vlgae_dmv_workspace_bytes(B, N);
+    // one device arena: dec | attach | gdec | gattach | Z | best | lengths | heads | workspace
+    const size_t fl = nd + na + nd + na + 2 * (size_t)B;
+    const size_t bytes = ((fl * 4 + 15) & ~(size_t)15) + (size_t)B * 8 + (size_t)B * N * 8 + 256 + ws;
+    unsigned char *arena = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&arena, bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+    float *d_dec = (float *)arena, *d_att = d_dec + nd, *d_gdec = d_att + na, *d_gatt = d_gdec + nd;
+    float *d_Z = d_gatt + na, *d_best = d_Z + B;
+    int64_t *d_len = (int64_t *)(arena + ((fl * 4 + 15) & ~(size_t)15));
+    int64_t *d_heads = d_len + B;
+    void *d_ws = (void *)(((uintptr_t)(d_heads + (size_t)B * N) + 255) & ~(uintptr_t)255);
+#define CK(x, w) do { e = (x); if (e != cudaSuccess) { cudaFreeAsync(arena, st); return cuda_fail(e, w); } } while (0)
+    CK(cudaMemcpyAsync(d_dec, dec_host, nd * 4, cudaMemcpyHostToDevice, st), "H2D dec");
+    CK(cudaMemcpyAsync(d_att, attach_host, na * 4, cudaMemcpyHostToDevice, st), "H2D attach");
+    CK(cudaMemcpyAsync(d_len, lengths_host, (size_t)B * 8, cudaMemcpyHostToDevice, st), "H2D lengths");
+    const bool want_grad = gdec_host || gattach_host;
+    rc = vlgae_dmv_parse(d_dec, d_att, d_len, B, N, mask_zero, nullptr, d_Z, want_grad ? d_gdec : nullptr,
+                         want_grad ? d_gatt : nullptr, d_best, d_heads, nullptr, nullptr, d_ws, ws, stream);
+    if (rc) { cudaFreeAsync(arena, st); return rc; }
+    if (Z_host) CK(cudaMemcpyAsync(Z_host, d_Z, (size_t)B * 4, cudaMemcpyDeviceToHost, st), "D2H Z");
+    if (best_host) CK(cudaMemcpyAsync(best_host, d_best, (size_t)B * 4, cudaMemcpyDeviceToHost, st), "D2H best");
+    if (gdec_host) CK(cudaMemcpyAsync(gdec_host, d_gdec, nd * 4, cudaMemcpyDeviceToHost, st), "D2H gdec");
+    if (gattach_host) CK(cudaMemcpyAsync(gattach_host, d_gatt, na * 4, cudaMemcpyDeviceToHost, st), "D2H gattach");
+    if (heads_host) CK(cudaMemcpyAsync(heads_host, d_heads, (size_t)B * N * 8, cudaMemcpyDeviceToHost, st), "D2H heads");
+    CK(cudaFreeAsync(arena, st), "cudaFreeAsync");
+    CK(cudaStreamSynchronize(st), "sync");
+#undef CK
+    return VLGAE_OK;
+}
+
+int vlgae_dmv_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
+                    float *dec_w, float *attach_w, void *stream) {
+    if (!dec || !attach || !root || !dec_w || !attach_w) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B < 0 || n < 0 || n + 1 > VLGAE_DMV_MAX_N) return fail(VLGAE_E_INVALID, "%s", "bad B or n");
+    if (B == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_merge(dec, attach, root, B, n, one, zero, dec_w, attach_w, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "merge launch");
+}
+
+int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream) {
+    if (!in || !g || !out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B <= 0 || inner == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_scale_rows(in, g, B, inner, out, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "scale_rows launch");
+}
+
+static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
+    if (!ms_host || !ops_host || iters < 1) return fail(VLGAE_E_INVALID, "%s", "bad microbench arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *sink = nullptr;
+    cudaError_t e = cudaMalloc((void **)&sink, 4);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    int grid = 0, block = 0;
+    vlgae::launch_microbench(which, 16, sink, &grid, &block, st);  // warm-up
+    cudaEventRecord(a, st);
+    e = vlgae::launch_microbench(which, iters, sink, &grid, &block, st);
+    cudaEventRecord(b, st);
+    cudaError_t e2 = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(e, "microbench launch");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "microbench sync");
+    *ms_host = ms;
+    *ops_host = (double)grid * block * (double)iters * 64.0;
+    return VLGAE_OK;
+}
+int vlgae_microbench_mufu(int iters, float *ms_host, double *ops_host, void *stream) { return microbench(0, iters, ms_host, ops_host, stream); }
+int vlgae_microbench_fp32(int iters, float *ms_host, double *ops_host, void *stream) { return microbench(1, iters, ms_host, ops_host, stream); }
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// dmv_kernels.cuh -- internal interface between the C ABI (c_api.cu) and the DMV kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vlgae {
+
+struct DmvArgs {
+    // inputs (device)
+    const float *dec;        // [B][N][2][2][2]
+    const float *attach;     // [B][N][N][2]
+    const int64_t *lengths;  // [B]
+    int B, N;
+    float mask_zero;
+    // log semiring
+    const float *gZ;  // [B] or null
+    float *Z;         // [B]
+    float *gdec;      // [B][N][2][2][2] or null
+    float *gattach;   // [B][N][N][2] or null
+    // max semiring
+    float *best;     // [B]
+    int64_t *heads;  // [B][N] or null
+    float *arcs;     // [B][N][N][2] or null
+    float *vgdec;    // [B][N][2][2][2] or null
+    // scheduling
+    void *workspace;   // per-CTA chart storage when the chart does not fit in shared memory
+    size_t ws_stride;  // bytes per CTA in `workspace`
+    int npass;         // 1: only `first_pass`; 2: log and max CTAs interleaved
+    int first_pass;    // 0 = log, 1 = max
+};
+
+// passes bitmask: 1 = log semiring, 2 = max semiring
+size_t dmv_chart_bytes(int N, int passes);
+bool dmv_fits_smem(int N, int passes);
+int dmv_grid_for_workspace(int B);
+cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st);
+cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
+                         float *dec_w, float *attach_w, cudaStream_t st);
+cudaError_t launch_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, cudaStream_t st);
+cudaError_t launch_microbench(int which, int iters, float *sink, int *grid_out, int *block_out, cudaStream_t st);
+
+}  // namespace vlgae
