@@ -48,6 +48,12 @@ int vlgae_version(void);
 const char *vlgae_last_error(void);
 
 /*
+ * Launch tuning of the DMV kernels (process-wide; 0 = automatic): gmax = most lanes that share one span
+ * (1, 2, 4, 8), threads = CTA size (64, 128, 256).  Results do not depend on it.  Used by bench sweeps.
+ */
+int vlgae_dmv_set_tuning(int gmax, int threads);
+
+/*
  * Bytes of device scratch the DMV entry points need for a batch of B sentences
  * padded to N positions.  Charts live in shared memory when they fit (N <= ~80);
  * otherwise each resident CTA keeps its chart in this workspace (L2-resident).

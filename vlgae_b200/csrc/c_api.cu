@@ -45,6 +45,13 @@ int run_dmv(vlgae::DmvArgs &a, int passes, void *workspace, size_t workspace_byt
 extern "C" {
 
 int vlgae_version(void) { return 1; }
+int vlgae_dmv_set_tuning(int gmax, int threads) {
+    if ((gmax != 0 && gmax != 1 && gmax != 2 && gmax != 4 && gmax != 8) ||
+        (threads != 0 && threads != 64 && threads != 128 && threads != 256))
+        return fail(VLGAE_E_INVALID, "%s", "gmax must be 0/1/2/4/8 and threads 0/64/128/256");
+    vlgae::dmv_set_tuning(gmax, threads);
+    return VLGAE_OK;
+}
 const char *vlgae_last_error(void) { return g_err; }
 
 size_t vlgae_dmv_workspace_bytes(int B, int N) {

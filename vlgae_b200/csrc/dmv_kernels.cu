@@ -25,6 +25,7 @@
 // which makes every read-modify-write target unique within a width: no atomics, one barrier.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dmv_kernels.cuh"
 
@@ -33,75 +34,199 @@ namespace vlgae {
 namespace {
 
 constexpr float NEG_BIG = -3.0e38f;  // finite stand-in for -inf (no NaN from (-inf) - (-inf))
-constexpr int KCH = 4;               // split points per lane per chunk of the streaming logsumexp
+constexpr int KCH = 8;               // split points per lane per chunk of the streaming logsumexp
+
+#ifdef VLGAE_ACCURATE_MATH
+#define VEXP(x) expf(x)
+#define VLOG(x) logf(x)
+#else
+#define VEXP(x) __expf(x)
+#define VLOG(x) __logf(x)
+#endif
 
 __device__ __forceinline__ int cidx(int lo, int d, int Nb) { return d * Nb - ((d * (d - 1)) >> 1) + lo; }
 
-__device__ __forceinline__ unsigned group_mask(int g) {
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    if (G >= 32) return 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    return g >= 32 ? 0xffffffffu : (((1u << g) - 1u) << (lane & ~(g - 1)));
+    return ((1u << G) - 1u) << (lane & ~(G - 1));
 }
 
 // lanes per cell for width w with ncell cells: fill the CTA, never more lanes than split points (rounded up)
-__device__ __forceinline__ int lanes_per_cell(int ncell, int w, int nthreads) {
+__device__ __forceinline__ int lanes_per_cell(int ncell, int w, int nthreads, int gmax) {
     int g = 1;
-    while (g < 32 && g < w && ncell * (g << 1) <= nthreads) g <<= 1;
+    while (g < gmax && g < w && ncell * (g << 1) <= nthreads) g <<= 1;
     return g;
 }
 
-// streaming logsumexp state: value = m + log(s)
-struct Lse {
-    float m, s;
-    __device__ __forceinline__ void init() { m = NEG_BIG; s = 0.f; }
-    __device__ __forceinline__ void add_chunk(const float (&t)[KCH]) {
-        float cm = t[0];
-#pragma unroll
-        for (int k = 1; k < KCH; ++k) cm = fmaxf(cm, t[k]);
-        const float nm = fmaxf(m, cm);
-        s *= __expf(m - nm);
-        m = nm;
-#pragma unroll
-        for (int k = 0; k < KCH; ++k) s += __expf(t[k] - nm);
-    }
-    // combine across the g lanes of a group (all lanes end with the same value)
-    __device__ __forceinline__ float finish(int g, unsigned mask) {
-        float gm = m;
-        for (int o = g >> 1; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(mask, gm, o));
-        float gs = s * __expf(m - gm);
-        for (int o = g >> 1; o > 0; o >>= 1) gs += __shfl_xor_sync(mask, gs, o);
-        return gm + __logf(gs);
+__host__ __device__ inline int ncells(int Nb) { return Nb * (Nb + 1) / 2; }
+
+// Log-pass chart, 80 B per cell:
+//   C4  = (CL[HAS], CL[NO], CR[HAS], CR[NO])                         complete items, both directions
+//   IL, IR = incomplete items (both valences); before width d is processed they hold attach + dec[GO]
+//   GA  = (gCR[HAS], gCR[NO] from I-parents, gCL[NO] from C-parents, XL)   updated by the cell's row owner
+//   GB  = (gCL[HAS], gCL[NO] from I-parents, gCR[NO] from C-parents, XR)   updated by the cell's column owner
+//   gIL, gIR = gradients of the incomplete items (= d Z / d attach)
+struct LogChart {
+    float4 *C4, *GA, *GB;
+    float2 *IL, *IR, *gIL, *gIR;
+    __device__ __forceinline__ void carve(void *mem, int nc) {
+        C4 = reinterpret_cast<float4 *>(mem); GA = C4 + nc; GB = GA + nc;
+        IL = reinterpret_cast<float2 *>(GB + nc); IR = IL + nc; gIL = IR + nc; gIR = gIL + nc;
     }
 };
 
-// first-max state: value and smallest split index attaining it (torch.max tie rule)
-struct ArgMax {
-    float v;
-    int a;
-    __device__ __forceinline__ void init() { v = NEG_BIG; a = 0x7fffffff; }
-    __device__ __forceinline__ void add(float t, int r) {
-        if (t > v) { v = t; a = r; }  // r increases within a lane: strict > keeps the first
-    }
-    __device__ __forceinline__ void finish(int g, unsigned mask) {
-        for (int o = g >> 1; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(mask, v, o);
-            const int oa = __shfl_xor_sync(mask, a, o);
-            if (ov > v || (ov == v && oa < a)) { v = ov; a = oa; }
+// ---------------------------------------------------------------------------------------------
+// log semiring, one width of the inside sweep (dmv.py:47-63), G lanes per span
+// ---------------------------------------------------------------------------------------------
+template <int G, int NT>
+__device__ __forceinline__ void inside_width(const LogChart &c, int w, int Nb, int len, float mask_zero, bool keep_x) {
+    const int tid = threadIdx.x;
+    const int ncell = Nb - w;
+    const int sub = tid & (G - 1);
+    const unsigned mask = group_mask<G>();
+    for (int i = tid / G; i < ncell; i += NT / G) {
+        const int j = i + w;
+        const int own = cidx(i, w, Nb);
+        // six reductions over the split point: XL, XR, CL[HAS], CL[NO], CR[HAS], CR[NO]; the width-w operand of
+        // the complete items (the span's own incomplete item) is merged at the end, so one pass serves all six
+        float m[6], s[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { m[q] = NEG_BIG; s[q] = 0.f; }
+        for (int r0 = sub; r0 < w; r0 += G * KCH) {
+            float t[6][KCH];
+#pragma unroll
+            for (int k = 0; k < KCH; ++k) {
+                const int rp = r0 + k * G;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) t[q][k] = NEG_BIG;
+                if (rp < w) {
+                    const float4 ca = c.C4[cidx(i, rp, Nb)];                  // CL[i+rp][i], CR[i][i+rp]
+                    const float4 cb = c.C4[cidx(i + rp + 1, w - 1 - rp, Nb)];  // CL[j][i+rp+1], CR[i+rp+1][j]
+                    t[0][k] = ca.w + cb.x;  // step 1 (dmv.py:50): CR[i][r][NO] + CL[j][r+1][HAS]
+                    t[1][k] = ca.z + cb.y;  // step 2 (dmv.py:54): CR[i][r][HAS] + CL[j][r+1][NO]
+                    if (rp > 0) {           // step 3 (dmv.py:58): CL[r][i][NO] + IL[j][r][v], r = i + rp
+                        const float2 e = c.IL[cidx(i + rp, w - rp, Nb)];
+                        t[2][k] = ca.y + e.x; t[3][k] = ca.y + e.y;
+                    }
+                    if (rp < w - 1) {       // step 4 (dmv.py:61): IR[i][r][v] + CR[r][j][NO], r = i + 1 + rp
+                        const float2 f = c.IR[cidx(i, rp + 1, Nb)];
+                        t[4][k] = f.x + cb.w; t[5][k] = f.y + cb.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                float cm = t[q][0];
+#pragma unroll
+                for (int k = 1; k < KCH; ++k) cm = fmaxf(cm, t[q][k]);
+                const float nm = fmaxf(m[q], cm);
+                float acc = s[q] * VEXP(m[q] - nm);
+#pragma unroll
+                for (int k = 0; k < KCH; ++k) acc += VEXP(t[q][k] - nm);
+                s[q] = acc; m[q] = nm;
+            }
+        }
+        if (G > 1) {  // combine the G lanes' partial (max, sum) pairs; every lane ends with the total
+            float gm[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) gm[q] = m[q];
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) gm[q] = fmaxf(gm[q], __shfl_xor_sync(mask, gm[q], o));
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { s[q] *= VEXP(m[q] - gm[q]); m[q] = gm[q]; }
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s[q] += __shfl_xor_sync(mask, s[q], o);
+            }
+        }
+        const float XL = m[0] + VLOG(s[0]), XR = m[1] + VLOG(s[1]);
+        const float2 arcL = c.IL[own], arcR = c.IR[own];  // attach + dec[GO], pre-added (dmv.py:36-37)
+        const float2 il = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
+        const float2 ir = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
+        const float cii = c.C4[i].y;  // CL[i][i][NO]
+        const float cjj = c.C4[j].w;  // CR[j][j][NO]
+        float res[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float ownt = q == 0 ? cii + il.x : q == 1 ? cii + il.y : q == 2 ? ir.x + cjj : ir.y + cjj;
+            const float M = fmaxf(m[2 + q], ownt);
+            const float S = s[2 + q] * VEXP(m[2 + q] - M) + VEXP(ownt - M);
+            res[q] = M + VLOG(S);
+        }
+        if (i == 0 && w != len) { res[2] = mask_zero; res[3] = mask_zero; }  // single root (dmv.py:63)
+        if (G > 1) __syncwarp(mask);  // every lane has read the pre-added arc scores of `own`
+        if (sub == 0) {
+            c.IL[own] = il; c.IR[own] = ir;
+            c.C4[own] = make_float4(res[0], res[1], res[2], res[3]);
+            if (keep_x) { c.GA[own].w = XL; c.GB[own].w = XR; }
         }
     }
-};
+}
 
-struct LogChart {
-    float2 *CL, *CR, *IL, *IR, *X;     // inside values; X = (XL, XR) pre-arc reductions
-    float2 *gCL, *gCR, *gCa, *gIL, *gIR;  // reverse sweep; gCa = (A-part of gCL[NO], A-part of gCR[NO])
-};
-
-__host__ __device__ inline int ncells(int Nb) { return Nb * (Nb + 1) / 2; }
+// ---------------------------------------------------------------------------------------------
+// log semiring, one width of the reverse sweep (replaces autograd through the chart, helpers.py:150-154)
+// ---------------------------------------------------------------------------------------------
+template <int G, int NT>
+__device__ __forceinline__ void outside_width(const LogChart &c, int w, int Nb, int len) {
+    const int tid = threadIdx.x;
+    const int ncell = Nb - w;
+    const int sub = tid & (G - 1);
+    const unsigned mask = group_mask<G>();
+    for (int i = tid / G; i < ncell; i += NT / G) {
+        const int j = i + w;
+        const int own = cidx(i, w, Nb);
+        const float4 ga = c.GA[own], gb = c.GB[own];
+        float2 gcr = make_float2(ga.x, ga.y + gb.z);
+        const float2 gcl = make_float2(gb.x, gb.y + ga.z);
+        const float XL = ga.w, XR = gb.w;
+        const float4 co = c.C4[own];
+        const float2 outL = make_float2(co.x, co.y);
+        float2 outR = make_float2(co.z, co.w);
+        if (i == 0 && w != len) {  // masked cell (dmv.py:63) passes nothing back: p = 0 * exp(-big) = 0
+            gcr = make_float2(0.f, 0.f);
+            outR = make_float2(-NEG_BIG, -NEG_BIG);
+        }
+        // the span's own incomplete items receive their last contribution from the span's own complete items
+        const float2 il = c.IL[own], ir = c.IR[own];
+        const float cii = c.C4[i].y, cjj = c.C4[j].w;
+        float2 giR = c.gIR[own], giL = c.gIL[own];
+        giR.x += gcr.x * VEXP(ir.x + cjj - outR.x); giR.y += gcr.y * VEXP(ir.y + cjj - outR.y);
+        giL.x += gcl.x * VEXP(cii + il.x - outL.x); giL.y += gcl.y * VEXP(cii + il.y - outL.y);
+        const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
+        if (G > 1) __syncwarp(mask);  // all lanes hold gI[own] before the lane owning rp = 0 / w-1 updates it
+        for (int rp = sub; rp < w; rp += G) {
+            const int ia = cidx(i, rp, Nb), ib = cidx(i + rp + 1, w - 1 - rp, Nb);
+            const int ie = cidx(i + rp, w - rp, Nb), jf = cidx(i, rp + 1, Nb);
+            const float4 ca = c.C4[ia], cb = c.C4[ib];
+            const float2 e = c.IL[ie], f = c.IR[jf];
+            // step 4 transposed: parent CR[i][j][v] -> IR[i][r][v], CR[r][j][NO]
+            const float p0 = gcr.x * VEXP(f.x + cb.w - outR.x);
+            const float p1 = gcr.y * VEXP(f.y + cb.w - outR.y);
+            // step 3 transposed: parent CL[j][i][v] -> CL[r][i][NO], IL[j][r][v]
+            const float q0 = gcl.x * VEXP(ca.y + e.x - outL.x);
+            const float q1 = gcl.y * VEXP(ca.y + e.y - outL.y);
+            // steps 1, 2 transposed: parents IL[j][i], IR[i][j] -> CR[i][r][.], CL[j][r+1][.]
+            const float pL = gxL * VEXP(ca.w + cb.x - XL);
+            const float pR = gxR * VEXP(ca.z + cb.y - XR);
+            float2 t = c.gIR[jf]; t.x += p0; t.y += p1; c.gIR[jf] = t;
+            float2 u = c.gIL[ie]; u.x += q0; u.y += q1; c.gIL[ie] = u;
+            float4 A = c.GA[ia]; A.x += pR; A.y += pL; A.z += q0 + q1; c.GA[ia] = A;
+            float4 B = c.GB[ib]; B.x += pL; B.y += pR; B.z += p0 + p1; c.GB[ib] = B;
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // log semiring: inside + outside for one sentence
 // ---------------------------------------------------------------------------------------------
 template <int NT>
-__device__ void log_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
+__device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     const int tid = threadIdx.x;
     const int N = p.N;
     int len = (int)p.lengths[b];
@@ -109,147 +234,49 @@ __device__ void log_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
     const int Nb = len + 1;
     const int nc = ncells(Nb);
     LogChart c;
-    c.CL = mem; c.CR = mem + nc; c.IL = mem + 2 * nc; c.IR = mem + 3 * nc; c.X = mem + 4 * nc;
-    c.gCL = mem + 5 * nc; c.gCR = mem + 6 * nc; c.gCa = mem + 7 * nc; c.gIL = mem + 8 * nc; c.gIR = mem + 9 * nc;
+    c.carve(mem, nc);
     const bool want_grad = (p.gdec != nullptr) || (p.gattach != nullptr);
 
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
     for (int t = tid; t < Nb * 8; t += NT) sdec[t] = dec[t];
-    if (want_grad)
-        for (int t = tid; t < 5 * nc; t += NT) c.gCL[t] = make_float2(0.f, 0.f);
+    if (want_grad) {
+        for (int t = tid; t < 2 * nc; t += NT) c.GA[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tid; t < 2 * nc; t += NT) c.gIL[t] = make_float2(0.f, 0.f);
+    }
     __syncthreads();
     // width-0 complete items = STOP decisions (dmv.py:39-40); arc scores pre-added into the I cells
-    // (attach + dec[GO] is formed first, exactly as dmv.py:36-37 does)
-    for (int i = tid; i < Nb; i += NT) {
-        c.CL[i] = make_float2(sdec[i * 8 + 0 * 4 + 0 * 2 + 1], sdec[i * 8 + 0 * 4 + 1 * 2 + 1]);
-        c.CR[i] = make_float2(sdec[i * 8 + 1 * 4 + 0 * 2 + 1], sdec[i * 8 + 1 * 4 + 1 * 2 + 1]);
-    }
+    // (attach + dec[GO] is formed first, exactly as dmv.py:36-37 does).  dec index = dir*4 + val*2 + decision.
+    for (int i = tid; i < Nb; i += NT) c.C4[i] = make_float4(sdec[i * 8 + 1], sdec[i * 8 + 3], sdec[i * 8 + 5], sdec[i * 8 + 7]);
     for (int t = tid; t < Nb * Nb; t += NT) {
         const int h = t / Nb, ch = t - h * Nb;
         if (h == ch) continue;
         const float2 a = *reinterpret_cast<const float2 *>(attach + ((size_t)h * N + ch) * 2);
-        if (ch < h)
-            c.IL[cidx(ch, h - ch, Nb)] = make_float2(a.x + sdec[h * 8 + 0 * 4 + 0 * 2 + 0], a.y + sdec[h * 8 + 0 * 4 + 1 * 2 + 0]);
-        else
-            c.IR[cidx(h, ch - h, Nb)] = make_float2(a.x + sdec[h * 8 + 1 * 4 + 0 * 2 + 0], a.y + sdec[h * 8 + 1 * 4 + 1 * 2 + 0]);
+        if (ch < h) c.IL[cidx(ch, h - ch, Nb)] = make_float2(a.x + sdec[h * 8 + 0], a.y + sdec[h * 8 + 2]);
+        else c.IR[cidx(h, ch - h, Nb)] = make_float2(a.x + sdec[h * 8 + 4], a.y + sdec[h * 8 + 6]);
     }
     __syncthreads();
 
-    // ---------------- inside ----------------
     for (int w = 1; w < Nb; ++w) {
-        const int ncell = Nb - w;
-        const int g = lanes_per_cell(ncell, w, NT);
-        const unsigned mask = group_mask(g);
-        const int sub = tid & (g - 1);
-        for (int i = tid / g; i < ncell; i += NT / g) {
-            const int own = cidx(i, w, Nb);
-            Lse xl, xr;
-            xl.init(); xr.init();
-            for (int r0 = sub; r0 < w; r0 += g * KCH) {
-                float tl[KCH], tr[KCH];
-#pragma unroll
-                for (int k = 0; k < KCH; ++k) {
-                    const int rp = r0 + k * g;
-                    if (rp < w) {
-                        const float2 a = c.CR[cidx(i, rp, Nb)];                   // CR[i][i+rp]
-                        const float2 bb = c.CL[cidx(i + rp + 1, w - 1 - rp, Nb)];  // CL[j][i+rp+1]
-                        tl[k] = a.y + bb.x;                                        // step 1 (dmv.py:50)
-                        tr[k] = a.x + bb.y;                                        // step 2 (dmv.py:54)
-                    } else {
-                        tl[k] = NEG_BIG; tr[k] = NEG_BIG;
-                    }
-                }
-                xl.add_chunk(tl); xr.add_chunk(tr);
-            }
-            const float XL = xl.finish(g, mask), XR = xr.finish(g, mask);
-            const float2 arcL = c.IL[own], arcR = c.IR[own];
-            const float2 il = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
-            const float2 ir = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
-            Lse l0, l1, q0, q1;
-            l0.init(); l1.init(); q0.init(); q1.init();
-            for (int r0 = sub; r0 < w; r0 += g * KCH) {
-                float t0[KCH], t1[KCH], u0[KCH], u1[KCH];
-#pragma unroll
-                for (int k = 0; k < KCH; ++k) {
-                    const int rp = r0 + k * g;
-                    if (rp < w) {
-                        const float cl = c.CL[cidx(i, rp, Nb)].y;                                // CL[i+rp][i][NO]
-                        const float2 e = rp == 0 ? il : c.IL[cidx(i + rp, w - rp, Nb)];           // IL[j][i+rp]
-                        t0[k] = cl + e.x; t1[k] = cl + e.y;                                       // step 3 (dmv.py:58)
-                        const float2 f = rp == w - 1 ? ir : c.IR[cidx(i, rp + 1, Nb)];            // IR[i][i+1+rp]
-                        const float cr = c.CR[cidx(i + 1 + rp, w - 1 - rp, Nb)].y;                // CR[i+1+rp][j][NO]
-                        u0[k] = f.x + cr; u1[k] = f.y + cr;                                       // step 4 (dmv.py:61)
-                    } else {
-                        t0[k] = NEG_BIG; t1[k] = NEG_BIG; u0[k] = NEG_BIG; u1[k] = NEG_BIG;
-                    }
-                }
-                l0.add_chunk(t0); l1.add_chunk(t1); q0.add_chunk(u0); q1.add_chunk(u1);
-            }
-            float2 cl2 = make_float2(l0.finish(g, mask), l1.finish(g, mask));
-            float2 cr2 = make_float2(q0.finish(g, mask), q1.finish(g, mask));
-            if (i == 0 && w != len) cr2 = make_float2(p.mask_zero, p.mask_zero);  // single root (dmv.py:63)
-            __syncwarp(mask);  // every lane has read the pre-added arc scores of `own`
-            if (sub == 0) {
-                c.IL[own] = il; c.IR[own] = ir; c.X[own] = make_float2(XL, XR);
-                c.CL[own] = cl2; c.CR[own] = cr2;
-            }
+        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
+            case 1: inside_width<1, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
+            case 2: inside_width<2, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
+            case 4: inside_width<4, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
+            default: inside_width<8, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
         }
         __syncthreads();
     }
-    if (tid == 0) p.Z[b] = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65
+    if (tid == 0) p.Z[b] = c.C4[cidx(0, len, Nb)].w;  // dmv.py:65
     if (!want_grad) { __syncthreads(); return; }
 
-    // ---------------- outside (reverse sweep; replaces helpers.py:150-154) ----------------
-    if (tid == 0) c.gCa[cidx(0, len, Nb)].y = p.gZ ? p.gZ[b] : 1.f;
+    if (tid == 0) c.GB[cidx(0, len, Nb)].z = p.gZ ? p.gZ[b] : 1.f;
     __syncthreads();
     for (int w = Nb - 1; w >= 1; --w) {
-        const int ncell = Nb - w;
-        const int g = lanes_per_cell(ncell, w, NT);
-        const unsigned mask = group_mask(g);
-        const int sub = tid & (g - 1);
-        for (int i = tid / g; i < ncell; i += NT / g) {
-            const int own = cidx(i, w, Nb);
-            // A: complete-item parents (steps 4 and 3 transposed)
-            float2 gcr = c.gCR[own], gcl = c.gCL[own];
-            const float2 ga = c.gCa[own];
-            gcr.y += ga.y; gcl.y += ga.x;
-            if (i == 0 && w != len) gcr = make_float2(0.f, 0.f);  // masked cell passes nothing back
-            const float2 outR = c.CR[own], outL = c.CL[own];
-            for (int rp = sub; rp < w; rp += g) {
-                {
-                    const int ci = cidx(i, rp + 1, Nb), cc = cidx(i + 1 + rp, w - 1 - rp, Nb);
-                    const float2 f = c.IR[ci];
-                    const float h = c.CR[cc].y;
-                    const float p0 = gcr.x * __expf(f.x + h - outR.x);
-                    const float p1 = gcr.y * __expf(f.y + h - outR.y);
-                    float2 t = c.gIR[ci]; t.x += p0; t.y += p1; c.gIR[ci] = t;
-                    c.gCa[cc].y += p0 + p1;
-                }
-                {
-                    const int cc = cidx(i, rp, Nb), ci = cidx(i + rp, w - rp, Nb);
-                    const float cl = c.CL[cc].y;
-                    const float2 e = c.IL[ci];
-                    const float p0 = gcl.x * __expf(cl + e.x - outL.x);
-                    const float p1 = gcl.y * __expf(cl + e.y - outL.y);
-                    c.gCa[cc].x += p0 + p1;
-                    float2 t = c.gIL[ci]; t.x += p0; t.y += p1; c.gIL[ci] = t;
-                }
-            }
-            __syncwarp(mask);
-            // B: incomplete-item parents (steps 2 and 1 transposed)
-            const float2 giR = c.gIR[own], giL = c.gIL[own];
-            const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
-            const float2 X = c.X[own];
-            for (int rp = sub; rp < w; rp += g) {
-                const int ca = cidx(i, rp, Nb), cb = cidx(i + rp + 1, w - 1 - rp, Nb);
-                const float2 a = c.CR[ca];
-                const float2 bb = c.CL[cb];
-                const float pL = gxL * __expf(a.y + bb.x - X.x);
-                const float pR = gxR * __expf(a.x + bb.y - X.y);
-                float2 t = c.gCR[ca]; t.x += pR; t.y += pL; c.gCR[ca] = t;
-                float2 u = c.gCL[cb]; u.x += pL; u.y += pR; c.gCL[cb] = u;
-            }
+        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
+            case 1: outside_width<1, NT>(c, w, Nb, len); break;
+            case 2: outside_width<2, NT>(c, w, Nb, len); break;
+            case 4: outside_width<4, NT>(c, w, Nb, len); break;
+            default: outside_width<8, NT>(c, w, Nb, len); break;
         }
         __syncthreads();
     }
@@ -269,12 +296,13 @@ __device__ void log_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
             const int i = t >> 1, dir = t & 1;
             float2 go = make_float2(0.f, 0.f), stop = make_float2(0.f, 0.f);
             if (i < Nb) {
+                const float4 ga = c.GA[i], gb = c.GB[i];
                 if (dir == 0) {
                     for (int ch = 0; ch < i; ++ch) { const float2 v = c.gIL[cidx(ch, i - ch, Nb)]; go.x += v.x; go.y += v.y; }
-                    stop = c.gCL[i]; stop.y += c.gCa[i].x;
+                    stop = make_float2(gb.x, gb.y + ga.z);
                 } else {
                     for (int d = 1; d < Nb - i; ++d) { const float2 v = c.gIR[cidx(i, d, Nb)]; go.x += v.x; go.y += v.y; }
-                    stop = c.gCR[i]; stop.y += c.gCa[i].y;
+                    stop = make_float2(ga.x, ga.y + gb.z);
                 }
             }
             // [dir][val][decision]
@@ -288,7 +316,8 @@ __device__ void log_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
 // max semiring: Viterbi chart with first-max back-pointers + parallel back-trace
 // ---------------------------------------------------------------------------------------------
 struct MaxChart {
-    float2 *CL, *CR, *IL, *IR;
+    float4 *C4;
+    float2 *IL, *IR;
     uint32_t *bpA;  // XL | XR << 8 | CL[HAS] << 16 | CL[NO] << 24
     uint16_t *bpB;  // CR[HAS] | CR[NO] << 8
 };
@@ -296,8 +325,79 @@ struct MaxChart {
 // items of the back-trace: kind (0 CR, 1 CL, 2 IR, 3 IL) | v << 2 | lo << 3 | hi << 12
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
+template <int G, int NT>
+__device__ __forceinline__ void viterbi_width(const MaxChart &c, int w, int Nb, int len, float mask_zero) {
+    const int tid = threadIdx.x;
+    const int ncell = Nb - w;
+    const int sub = tid & (G - 1);
+    const unsigned mask = group_mask<G>();
+    for (int i = tid / G; i < ncell; i += NT / G) {
+        const int j = i + w;
+        const int own = cidx(i, w, Nb);
+        float bv[6];
+        int ba[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { bv[q] = NEG_BIG; ba[q] = 0x7fffffff; }
+        // rp increases within a lane and the update is strict (>), so each lane keeps its FIRST maximum
+        for (int rp = sub; rp < w; rp += G) {
+            const float4 ca = c.C4[cidx(i, rp, Nb)];
+            const float4 cb = c.C4[cidx(i + rp + 1, w - 1 - rp, Nb)];
+            float t = __fadd_rn(ca.w, cb.x);
+            if (t > bv[0]) { bv[0] = t; ba[0] = rp; }
+            t = __fadd_rn(ca.z, cb.y);
+            if (t > bv[1]) { bv[1] = t; ba[1] = rp; }
+            if (rp > 0) {
+                const float2 e = c.IL[cidx(i + rp, w - rp, Nb)];
+                t = __fadd_rn(ca.y, e.x);
+                if (t > bv[2]) { bv[2] = t; ba[2] = rp; }
+                t = __fadd_rn(ca.y, e.y);
+                if (t > bv[3]) { bv[3] = t; ba[3] = rp; }
+            }
+            if (rp < w - 1) {
+                const float2 f = c.IR[cidx(i, rp + 1, Nb)];
+                t = __fadd_rn(f.x, cb.w);
+                if (t > bv[4]) { bv[4] = t; ba[4] = rp; }
+                t = __fadd_rn(f.y, cb.w);
+                if (t > bv[5]) { bv[5] = t; ba[5] = rp; }
+            }
+        }
+        if (G > 1) {  // across lanes: larger value wins, equal values -> smaller split (torch.max tie rule)
+#pragma unroll
+            for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float ov = __shfl_xor_sync(mask, bv[q], o);
+                    const int oa = __shfl_xor_sync(mask, ba[q], o);
+                    if (ov > bv[q] || (ov == bv[q] && oa < ba[q])) { bv[q] = ov; ba[q] = oa; }
+                }
+            }
+        }
+        const float2 arcL = c.IL[own], arcR = c.IR[own];
+        const float2 il = make_float2(__fadd_rn(bv[0], arcL.x), __fadd_rn(bv[0], arcL.y));
+        const float2 ir = make_float2(__fadd_rn(bv[1], arcR.x), __fadd_rn(bv[1], arcR.y));
+        const float cii = c.C4[i].y, cjj = c.C4[j].w;
+        // the span's own incomplete items: split 0 for CL (wins ties), split w-1 for CR (loses ties)
+        float t = __fadd_rn(cii, il.x);
+        if (t >= bv[2]) { bv[2] = t; ba[2] = 0; }
+        t = __fadd_rn(cii, il.y);
+        if (t >= bv[3]) { bv[3] = t; ba[3] = 0; }
+        t = __fadd_rn(ir.x, cjj);
+        if (t > bv[4]) { bv[4] = t; ba[4] = w - 1; }
+        t = __fadd_rn(ir.y, cjj);
+        if (t > bv[5]) { bv[5] = t; ba[5] = w - 1; }
+        if (i == 0 && w != len) { bv[4] = mask_zero; bv[5] = mask_zero; }
+        if (G > 1) __syncwarp(mask);
+        if (sub == 0) {
+            c.IL[own] = il; c.IR[own] = ir;
+            c.C4[own] = make_float4(bv[2], bv[3], bv[4], bv[5]);
+            c.bpA[own] = (uint32_t)ba[0] | ((uint32_t)ba[1] << 8) | ((uint32_t)ba[2] << 16) | ((uint32_t)ba[3] << 24);
+            c.bpB[own] = (uint16_t)((uint32_t)ba[4] | ((uint32_t)ba[5] << 8));
+        }
+    }
+}
+
 template <int NT>
-__device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
+__device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     const int tid = threadIdx.x;
     const int N = p.N;
     int len = (int)p.lengths[b];
@@ -305,8 +405,9 @@ __device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
     const int Nb = len + 1;
     const int nc = ncells(Nb);
     MaxChart c;
-    c.CL = mem; c.CR = mem + nc; c.IL = mem + 2 * nc; c.IR = mem + 3 * nc;
-    c.bpA = reinterpret_cast<uint32_t *>(mem + 4 * nc);
+    c.C4 = reinterpret_cast<float4 *>(mem);
+    c.IL = reinterpret_cast<float2 *>(c.C4 + nc); c.IR = c.IL + nc;
+    c.bpA = reinterpret_cast<uint32_t *>(c.IR + nc);
     c.bpB = reinterpret_cast<uint16_t *>(c.bpA + nc);
     int *queue = reinterpret_cast<int *>(c.bpB + ((nc + 1) & ~1));  // 2 x (2 Nb + 2) ints
 
@@ -314,10 +415,7 @@ __device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
     const float *attach = p.attach + (size_t)b * N * N * 2;
     for (int t = tid; t < Nb * 8; t += NT) sdec[t] = dec[t];
     __syncthreads();
-    for (int i = tid; i < Nb; i += NT) {
-        c.CL[i] = make_float2(sdec[i * 8 + 0 * 4 + 0 * 2 + 1], sdec[i * 8 + 0 * 4 + 1 * 2 + 1]);
-        c.CR[i] = make_float2(sdec[i * 8 + 1 * 4 + 0 * 2 + 1], sdec[i * 8 + 1 * 4 + 1 * 2 + 1]);
-    }
+    for (int i = tid; i < Nb; i += NT) c.C4[i] = make_float4(sdec[i * 8 + 1], sdec[i * 8 + 3], sdec[i * 8 + 5], sdec[i * 8 + 7]);
     for (int t = tid; t < Nb * Nb; t += NT) {
         const int h = t / Nb, ch = t - h * Nb;
         if (h == ch) continue;
@@ -337,48 +435,15 @@ __device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
     __syncthreads();
 
     for (int w = 1; w < Nb; ++w) {
-        const int ncell = Nb - w;
-        const int g = lanes_per_cell(ncell, w, NT);
-        const unsigned mask = group_mask(g);
-        const int sub = tid & (g - 1);
-        for (int i = tid / g; i < ncell; i += NT / g) {
-            const int own = cidx(i, w, Nb);
-            ArgMax xl, xr;
-            xl.init(); xr.init();
-            for (int rp = sub; rp < w; rp += g) {
-                const float2 a = c.CR[cidx(i, rp, Nb)];
-                const float2 bb = c.CL[cidx(i + rp + 1, w - 1 - rp, Nb)];
-                xl.add(__fadd_rn(a.y, bb.x), rp);
-                xr.add(__fadd_rn(a.x, bb.y), rp);
-            }
-            xl.finish(g, mask); xr.finish(g, mask);
-            const float2 arcL = c.IL[own], arcR = c.IR[own];
-            const float2 il = make_float2(__fadd_rn(xl.v, arcL.x), __fadd_rn(xl.v, arcL.y));
-            const float2 ir = make_float2(__fadd_rn(xr.v, arcR.x), __fadd_rn(xr.v, arcR.y));
-            ArgMax l0, l1, q0, q1;
-            l0.init(); l1.init(); q0.init(); q1.init();
-            for (int rp = sub; rp < w; rp += g) {
-                const float cl = c.CL[cidx(i, rp, Nb)].y;
-                const float2 e = rp == 0 ? il : c.IL[cidx(i + rp, w - rp, Nb)];
-                l0.add(__fadd_rn(cl, e.x), rp); l1.add(__fadd_rn(cl, e.y), rp);
-                const float2 f = rp == w - 1 ? ir : c.IR[cidx(i, rp + 1, Nb)];
-                const float cr = c.CR[cidx(i + 1 + rp, w - 1 - rp, Nb)].y;
-                q0.add(__fadd_rn(f.x, cr), rp); q1.add(__fadd_rn(f.y, cr), rp);
-            }
-            l0.finish(g, mask); l1.finish(g, mask); q0.finish(g, mask); q1.finish(g, mask);
-            float2 cr2 = make_float2(q0.v, q1.v);
-            if (i == 0 && w != len) cr2 = make_float2(p.mask_zero, p.mask_zero);
-            __syncwarp(mask);
-            if (sub == 0) {
-                c.IL[own] = il; c.IR[own] = ir;
-                c.CL[own] = make_float2(l0.v, l1.v); c.CR[own] = cr2;
-                c.bpA[own] = (uint32_t)xl.a | ((uint32_t)xr.a << 8) | ((uint32_t)l0.a << 16) | ((uint32_t)l1.a << 24);
-                c.bpB[own] = (uint16_t)((uint32_t)q0.a | ((uint32_t)q1.a << 8));
-            }
+        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
+            case 1: viterbi_width<1, NT>(c, w, Nb, len, p.mask_zero); break;
+            case 2: viterbi_width<2, NT>(c, w, Nb, len, p.mask_zero); break;
+            case 4: viterbi_width<4, NT>(c, w, Nb, len, p.mask_zero); break;
+            default: viterbi_width<8, NT>(c, w, Nb, len, p.mask_zero); break;
         }
         __syncthreads();
     }
-    if (tid == 0) p.best[b] = c.CR[cidx(0, len, Nb)].y;
+    if (tid == 0) p.best[b] = c.C4[cidx(0, len, Nb)].w;
 
     // back-trace: breadth-first over the derivation, one warp, two children per expanded item
     if (tid < 32 && (p.heads || p.arcs || p.vgdec)) {
@@ -398,7 +463,7 @@ __device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
                     const int kind = it & 3, v = (it >> 2) & 1, lo = (it >> 3) & 511, hi = it >> 12;
                     const int d = hi - lo;
                     if (kind < 2 && d == 0) {  // STOP decision of position lo; kind 0 = right side
-                        if (p.vgdec) p.vgdec[(size_t)b * N * 8 + lo * 8 + (kind == 0 ? 4 : 0) + v * 2 + 1] = 1.f;
+                        if (p.vgdec) atomicAdd(&p.vgdec[(size_t)b * N * 8 + lo * 8 + (kind == 0 ? 4 : 0) + v * 2 + 1], 1.f);
                     } else {
                         const int own = cidx(lo, d, Nb);
                         const uint32_t ba = c.bpA[own];
@@ -414,13 +479,13 @@ __device__ void max_pass(const DmvArgs &p, int b, float2 *mem, float *sdec) {
                             c1 = mk_item(0, 0, lo, r); c2 = mk_item(1, 1, r + 1, hi);
                             if (p.heads) p.heads[(size_t)b * N + hi] = lo;
                             if (p.arcs) p.arcs[(((size_t)b * N + lo) * N + hi) * 2 + v] = 1.f;
-                            if (p.vgdec) p.vgdec[(size_t)b * N * 8 + lo * 8 + 4 + v * 2 + 0] = 1.f;
+                            if (p.vgdec) atomicAdd(&p.vgdec[(size_t)b * N * 8 + lo * 8 + 4 + v * 2 + 0], 1.f);
                         } else {  // IL: arc hi -> lo; XL -> CR(lo,r,NO) + CL(hi,r+1,HAS)
                             const int r = lo + (int)(ba & 255);
                             c1 = mk_item(0, 1, lo, r); c2 = mk_item(1, 0, r + 1, hi);
                             if (p.heads) p.heads[(size_t)b * N + lo] = hi;
                             if (p.arcs) p.arcs[(((size_t)b * N + hi) * N + lo) * 2 + v] = 1.f;
-                            if (p.vgdec) p.vgdec[(size_t)b * N * 8 + hi * 8 + 0 + v * 2 + 0] = 1.f;
+                            if (p.vgdec) atomicAdd(&p.vgdec[(size_t)b * N * 8 + hi * 8 + 0 + v * 2 + 0], 1.f);
                         }
                     }
                 }
@@ -446,11 +511,11 @@ template <int NT, bool SMEM>
 __global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sdec = reinterpret_cast<float *>(smem_raw);
-    float2 *mem;
+    void *mem;
     if (SMEM)
-        mem = reinterpret_cast<float2 *>(smem_raw + (((size_t)p.N * 8 * sizeof(float) + 15) & ~(size_t)15));
+        mem = smem_raw + (((size_t)p.N * 8 * sizeof(float) + 15) & ~(size_t)15);
     else
-        mem = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride);
+        mem = reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride;
     const int total = p.B * p.npass;
     // static round-robin over (sentence, semiring) work items; batches arrive sorted by length
     // (reference sampler.py:135-136), so consecutive items cost about the same
@@ -534,10 +599,10 @@ __global__ void fp32_bench_kernel(int iters, float *sink) {
 // ---------------------------------------------------------------------------------------------
 // host-side launch logic
 // ---------------------------------------------------------------------------------------------
-size_t log_chart_bytes(int N) { return (size_t)ncells(N) * 10 * sizeof(float2); }
+size_t log_chart_bytes(int N) { return (size_t)ncells(N) * 80; }
 size_t max_chart_bytes(int N) {
     const size_t nc = ncells(N);
-    return nc * 4 * sizeof(float2) + nc * 4 + ((nc + 1) & ~(size_t)1) * 2 + (size_t)(2 * (2 * N + 2)) * 4 + 16;
+    return nc * 32 + nc * 4 + ((nc + 1) & ~(size_t)1) * 2 + (size_t)(2 * (2 * N + 2)) * 4 + 16;
 }
 static size_t dec_bytes(int N) { return ((size_t)N * 8 * sizeof(float) + 15) & ~(size_t)15; }
 
@@ -598,9 +663,30 @@ static cudaError_t launch_nt(DmvArgs a, int passes, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st) {
-    // short charts: 128 threads (more CTAs per SM); long charts: 256
-    if (a.N <= 48) return launch_nt<128>(a, passes, st);
+static int g_tune_gmax = 0, g_tune_threads = 0;
+void dmv_set_tuning(int gmax, int threads) { g_tune_gmax = gmax; g_tune_threads = threads; }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
+    DmvArgs a = a_in;
+    cudaError_t e = device_info();
+    if (e != cudaSuccess) return e;
+    // Tunables (experiments: VLGAE_DMV_GMAX / VLGAE_DMV_THREADS).  Few sentences per SM = latency-bound: spread
+    // each span over several lanes.  Many sentences per SM = throughput-bound: one lane per span (no shuffles,
+    // conflict-free shared-memory access) and small CTAs so that more sentences are resident.
+    static const int env_gmax0 = env_int("VLGAE_DMV_GMAX", 0), env_threads0 = env_int("VLGAE_DMV_THREADS", 0);
+    const int env_gmax = g_tune_gmax > 0 ? g_tune_gmax : env_gmax0;
+    const int env_threads = g_tune_threads > 0 ? g_tune_threads : env_threads0;
+    const int items = a.B * a.npass;
+    const bool bulk = items > 6 * g_sm_count;
+    if (a.gmax <= 0) a.gmax = env_gmax > 0 ? env_gmax : (bulk ? 1 : 4);
+    if (a.threads <= 0) a.threads = env_threads > 0 ? env_threads : (a.N <= 48 ? (bulk ? 64 : 128) : 256);
+    if (a.threads <= 64) return launch_nt<64>(a, passes, st);
+    if (a.threads <= 128) return launch_nt<128>(a, passes, st);
     return launch_nt<256>(a, passes, st);
 }
 
