@@ -49,9 +49,18 @@ const char *vlgae_last_error(void);
 
 /*
  * Launch tuning of the DMV kernels (process-wide; 0 = automatic): gmax = most lanes that share one span
- * (1, 2, 4, 8), threads = CTA size (64, 128, 256).  Results do not depend on it.  Used by bench sweeps.
+ * (1, 2, 4, 8, 16, 32), threads = CTA size (96, 192, 384 = 3 roles x lanes), tpl = split points one lane takes
+ * before a span is shared between lanes (power of two <= 32).  Results do not depend on it beyond fp32
+ * summation order.  Used by bench sweeps.
  */
-int vlgae_dmv_set_tuning(int gmax, int threads);
+int vlgae_dmv_set_tuning(int gmax, int threads, int tpl);
+
+/*
+ * Debug aid: a device buffer of 8 int64; the CTAs of sentence 0 write cumulative SM cycle counts after each phase
+ * ([0..3] log pass: staged, inside done, outside done, outputs written; [4..6] max pass: staged, chart done,
+ * back-trace done).  NULL disables it (default).
+ */
+int vlgae_dmv_set_profile_buffer(void *device_buf);
 
 /*
  * Bytes of device scratch the DMV entry points need for a batch of B sentences

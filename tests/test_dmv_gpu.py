@@ -216,18 +216,19 @@ def test_cfg3_sweep_small(dev):
         check_all(*synth(512, n, 3), dev, marg_atol=2e-5)
 
 
-@pytest.mark.parametrize("gmax,threads", [(1, 64), (1, 128), (2, 128), (8, 128), (4, 256), (8, 64)])
-def test_launch_tuning_does_not_change_results(dev, gmax, threads):
+@pytest.mark.parametrize("gmax,threads,tpl", [(1, 96, 8), (1, 192, 1), (2, 192, 4), (8, 192, 2), (32, 192, 1),
+                                              (4, 384, 8), (32, 96, 2), (32, 192, 32)])
+def test_launch_tuning_does_not_change_results(dev, gmax, threads, tpl):
     from vlgae_b200._lib import check, lib
 
-    check(lib().vlgae_dmv_set_tuning(gmax, threads), "set_tuning")
+    check(lib().vlgae_dmv_set_tuning(gmax, threads, tpl), "set_tuning")
     try:
         g = torch.Generator().manual_seed(5)
         L = torch.randint(1, 41, (48,), generator=g)
         L[0] = 40
         check_all(*synth(48, 40, 50 + gmax, L, quant=0.5 if gmax == 2 else None), dev, marg_atol=2e-5)
     finally:
-        check(lib().vlgae_dmv_set_tuning(0, 0), "set_tuning")
+        check(lib().vlgae_dmv_set_tuning(0, 0, 0), "set_tuning")
 
 
 def test_upstream_gradient_scaling(dev):

@@ -71,8 +71,8 @@ def main():
             _, _, g64 = oracle.dmv_log(md[:nb], ma[:nb], L[:nb], f64=True, trim=True)
             _, _, g32 = oracle.dmv_log(md[:nb], ma[:nb], L[:nb], trim=True)
         for tn in args.tunings.split(","):
-            gmax, threads = (0, 0) if tn == "auto" else tuple(int(x) for x in tn.split("x"))
-            check(L_.vlgae_dmv_set_tuning(gmax, threads), "tuning")
+            gmax, threads, tpl = (0, 0, 0) if tn == "auto" else tuple(int(x) for x in tn.split("x"))
+            check(L_.vlgae_dmv_set_tuning(gmax, threads, tpl), "tuning")
             for _ in range(3):
                 ops.dmv_parse(tmd, tma, tL, out=out, prepared=True)
             torch.cuda.synchronize()
@@ -83,13 +83,13 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / args.iters
-            line = (f"{cname:8s} B={B:6d} n={n:3d} tuning={tn:6s} {us:10.1f} us/launch  {B / us:8.3f} Msent/s  "
+            line = (f"{cname:8s} B={B:6d} n={n:3d} tuning={tn:9s} {us:10.1f} us/launch  {B / us:8.3f} Msent/s  "
                     f"mufu_frac={mufu / (us * 1e-6) / peak:.3f}")
             if args.errors:
                 gpu = out.gattach[:nb].cpu().numpy()
                 line += f"  |gpu-f64|={np.abs(gpu - g64).max():.2e} |gpu-f32|={np.abs(gpu - g32).max():.2e} |f32-f64|={np.abs(g32 - g64).max():.2e}"
             print(line, flush=True)
-    check(L_.vlgae_dmv_set_tuning(0, 0), "tuning")
+    check(L_.vlgae_dmv_set_tuning(0, 0, 0), "tuning")
 
 
 if __name__ == "__main__":

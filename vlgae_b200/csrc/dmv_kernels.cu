@@ -16,13 +16,15 @@
 // 4 float2 + 6 back-pointer bytes.  For Nb <= ~80 everything is in shared memory; longer
 // sentences use the same code with the chart in a per-CTA global workspace (L2-resident).
 //
-// Work decomposition for width w: cell (i, j = i + w) is owned by a group of g lanes (g a power
-// of two <= 32 chosen per width so that (Nb - w) * g fills the CTA); lane `sub` handles the split
-// points r' = sub, sub + g, ...  A group computes the two incomplete items of its span and then,
-// without a block barrier, its two complete items (the only width-w operands those need are the
-// group's own), so there is ONE __syncthreads per width.  The reverse sweep keeps the
-// contributions of complete-item parents and incomplete-item parents in separate accumulators,
-// which makes every read-modify-write target unique within a width: no atomics, one barrier.
+// Work decomposition for width w (v3, "role split"): the CTA has NT = 3 * LPR threads; warps [0, LPR/32) reduce the
+// two incomplete items of every span (role X), the next LPR/32 warps the left complete items (role CL), the last the
+// right complete items (role CR).  Inside a role, span (i, j = i + w) is owned by a group of g lanes (g = power of
+// two <= 32 chosen per width so that (Nb - w) * g fills the role's lanes); lane `sub` handles split points
+// r' = sub, sub + g, ...  The complete items need the span's own incomplete items only for ONE of their w terms, so
+// all three roles reduce concurrently; role X publishes its result through a named barrier (bar.arrive / bar.sync)
+// and roles CL / CR merge that last term.  One __syncthreads per width.  The reverse sweep splits the same way
+// (parents XL/XR, parents CL, parents CR); every read-modify-write target word is unique within a width (row owner /
+// column owner / role), so there are no atomics and again one barrier per width.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -34,33 +36,122 @@ namespace vlgae {
 namespace {
 
 constexpr float NEG_BIG = -3.0e38f;  // finite stand-in for -inf (no NaN from (-inf) - (-inf))
-constexpr int KCH = 8;               // split points per lane per chunk of the streaming logsumexp
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int KCH = 4;  // split points per lane per chunk of the streaming logsumexp
 
+// exp / log on the MUFU pipe: one FMUL + MUFU.EX2 / MUFU.LG2 + FMUL (flush-to-zero variants: no denormal fix-up code)
+__device__ __forceinline__ float fexp(float x) {
 #ifdef VLGAE_ACCURATE_MATH
-#define VEXP(x) expf(x)
-#define VLOG(x) logf(x)
+    return expf(x);
 #else
-#define VEXP(x) __expf(x)
-#define VLOG(x) __logf(x)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * LOG2E));
+    return y;
 #endif
-
-__device__ __forceinline__ int cidx(int lo, int d, int Nb) { return d * Nb - ((d * (d - 1)) >> 1) + lo; }
-
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    if (G >= 32) return 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    return ((1u << G) - 1u) << (lane & ~(G - 1));
 }
-
-// lanes per cell for width w with ncell cells: fill the CTA, never more lanes than split points (rounded up)
-__device__ __forceinline__ int lanes_per_cell(int ncell, int w, int nthreads, int gmax) {
-    int g = 1;
-    while (g < gmax && g < w && ncell * (g << 1) <= nthreads) g <<= 1;
-    return g;
+__device__ __forceinline__ float flog(float x) {
+#ifdef VLGAE_ACCURATE_MATH
+    return logf(x);
+#else
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * LN2;
+#endif
 }
 
 __host__ __device__ inline int ncells(int Nb) { return Nb * (Nb + 1) / 2; }
+__device__ __forceinline__ int dbase(int d, int Nb) { return d * Nb - ((d * (d - 1)) >> 1); }
+__device__ __forceinline__ int cidx(int lo, int d, int Nb) { return dbase(d, Nb) + lo; }
+
+// Index streams over the split point.  fwd: cell (lo, d0 + k g); bwd: cell (lo0 + k g, d0 - k g).
+// Successive differences of the diagonal-major index are linear in k, so each step is two integer adds.
+struct Stream {
+    int idx, step, dec;
+    __device__ __forceinline__ void fwd(int lo, int d, int g, int Nb) {
+        idx = cidx(lo, d, Nb); step = g * Nb - g * d - ((g * (g - 1)) >> 1); dec = g * g;
+    }
+    __device__ __forceinline__ void bwd(int lo, int d, int g, int Nb) {
+        idx = cidx(lo, d, Nb); step = -g * Nb + g * d - ((g * (g + 1)) >> 1) + g; dec = g * g;
+    }
+    __device__ __forceinline__ void next() { idx += step; step -= dec; }
+};
+
+__device__ __forceinline__ int ceil_log2(int x) { return x <= 1 ? 0 : 32 - __clz(x - 1); }
+
+// log2 of the lanes per span for width w: the smallest power of two that leaves every lane at most 2^tpl_log2 split
+// points, capped by gmax and by the lanes a role has for the ncell spans of this width
+__device__ __forceinline__ int lanes_log2(int ncell, int w, int lpr_log2, int gmax_log2, int tpl_log2) {
+    int lg = ceil_log2((w + (1 << tpl_log2) - 1) >> tpl_log2);
+    const int room = lpr_log2 - ceil_log2(ncell);
+    lg = min(lg, min(gmax_log2, room));
+    return max(lg, 0);
+}
+
+__device__ __forceinline__ void named_arrive(int nthreads) { asm volatile("bar.arrive 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+// streaming logsumexp of two interleaved reductions: value_q = m[q] + log(s[q])
+struct Lse2 {
+    float m0, s0, m1, s1;
+    __device__ __forceinline__ void init() { m0 = m1 = NEG_BIG; s0 = s1 = 0.f; }
+    // n = number of valid slots (slots >= n hold NEG_BIG and are skipped)
+    __device__ __forceinline__ void add_chunk(const float (&t0)[KCH], const float (&t1)[KCH], int n) {
+        float c0 = t0[0], c1 = t1[0];
+#pragma unroll
+        for (int k = 1; k < KCH; ++k) { c0 = fmaxf(c0, t0[k]); c1 = fmaxf(c1, t1[k]); }
+        const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);
+        float a0 = s0 * fexp(m0 - n0), a1 = s1 * fexp(m1 - n1);
+#pragma unroll
+        for (int k = 0; k < KCH; ++k)
+            if (k < n) { a0 += fexp(t0[k] - n0); a1 += fexp(t1[k] - n1); }
+        s0 = a0; s1 = a1; m0 = n0; m1 = n1;
+    }
+    // combine the g lanes of a group; every lane ends with the group total
+    // (g is warp-uniform and every lane of the warp calls this: full-mask shuffles, partners stay inside the group)
+    __device__ __forceinline__ void combine(int g) {
+        if (g == 1) return;
+        float g0 = m0, g1 = m1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < g) {
+                g0 = fmaxf(g0, __shfl_xor_sync(0xffffffffu, g0, o));
+                g1 = fmaxf(g1, __shfl_xor_sync(0xffffffffu, g1, o));
+            }
+        s0 *= fexp(m0 - g0); s1 *= fexp(m1 - g1);
+        m0 = g0; m1 = g1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < g) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    }
+    // merge one more term into each reduction and finish
+    __device__ __forceinline__ float2 finish_with(float o0, float o1) const {
+        const float M0 = fmaxf(m0, o0), M1 = fmaxf(m1, o1);
+        const float S0 = s0 * fexp(m0 - M0) + fexp(o0 - M0), S1 = s1 * fexp(m1 - M1) + fexp(o1 - M1);
+        return make_float2(M0 + flog(S0), M1 + flog(S1));
+    }
+};
+
+// two interleaved first-max reductions (value, smallest split attaining it): torch.max's tie rule
+struct Max2 {
+    float v0, v1;
+    int a0, a1;
+    __device__ __forceinline__ void init() { v0 = v1 = NEG_BIG; a0 = a1 = 0x7fffffff; }
+    __device__ __forceinline__ void add(float t0, float t1, int rp) {  // rp increases within a lane: strict >
+        if (t0 > v0) { v0 = t0; a0 = rp; }
+        if (t1 > v1) { v1 = t1; a1 = rp; }
+    }
+    __device__ __forceinline__ void combine(int g) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o < g) {
+                const float w0 = __shfl_xor_sync(0xffffffffu, v0, o), w1 = __shfl_xor_sync(0xffffffffu, v1, o);
+                const int b0 = __shfl_xor_sync(0xffffffffu, a0, o), b1 = __shfl_xor_sync(0xffffffffu, a1, o);
+                if (w0 > v0 || (w0 == v0 && b0 < a0)) { v0 = w0; a0 = b0; }
+                if (w1 > v1 || (w1 == v1 && b1 < a1)) { v1 = w1; a1 = b1; }
+            }
+    }
+};
 
 // Log-pass chart, 80 B per cell:
 //   C4  = (CL[HAS], CL[NO], CR[HAS], CR[NO])                         complete items, both directions
@@ -76,95 +167,124 @@ struct LogChart {
         IL = reinterpret_cast<float2 *>(GB + nc); IR = IL + nc; gIL = IR + nc; gIR = gIL + nc;
     }
 };
+__device__ __forceinline__ float2 &lo2(float4 &v) { return *reinterpret_cast<float2 *>(&v.x); }
+__device__ __forceinline__ float2 &hi2(float4 &v) { return *reinterpret_cast<float2 *>(&v.z); }
+
+// per-width geometry of one thread inside its role (t = lane index inside the role, LPR = lanes per role)
+struct Geo {
+    int g, lg, sub, ncell, cpr_log2, nrounds, first_cell;
+    __device__ __forceinline__ Geo(int w, int Nb, int t, int lpr_log2, int gmax_log2, int tpl_log2) {
+        ncell = Nb - w;
+        lg = lanes_log2(ncell, w, lpr_log2, gmax_log2, tpl_log2);
+        g = 1 << lg;
+        sub = t & (g - 1);
+        first_cell = t >> lg;
+        cpr_log2 = lpr_log2 - lg;
+        nrounds = (ncell + (1 << cpr_log2) - 1) >> cpr_log2;
+    }
+};
+
+// per-kernel constants of one thread
+struct Lane {
+    int role, t, lpr_log2, gmax_log2, tpl_log2;
+    template <int NT>
+    __device__ __forceinline__ void init(const DmvArgs &p) {
+        constexpr int LPR = NT / 3;
+        lpr_log2 = LPR == 32 ? 5 : (LPR == 64 ? 6 : 7);
+        role = threadIdx.x >> lpr_log2;
+        t = threadIdx.x & (LPR - 1);
+        gmax_log2 = 31 - __clz(p.gmax);
+        tpl_log2 = 31 - __clz(p.tpl);
+    }
+};
+
+// Operand streams of a role over the split point rp = rbeg, rbeg + g, ... < rend of span (i, j = i + w):
+//   role X  (steps 1, 2, dmv.py:50,54): CR[i][i+rp] (.zw of C4) with CL[j][i+rp+1] (.xy of C4)
+//   role CL (step 3, dmv.py:58):        CL[i+rp][i][NO] (.y of C4) with IL[j][i+rp];        rp = 0 merged separately
+//   role CR (step 4, dmv.py:61):        IR[i][i+1+rp] with CR[i+1+rp][j][NO] (.w of C4);    rp = w-1 merged separately
+template <int ROLE>
+__device__ __forceinline__ void role_range(int i, int w, int g, int sub, int Nb, bool has, int &rbeg, int &rend,
+                                           Stream &s1, Stream &s2) {
+    rbeg = (ROLE == 1 && sub == 0) ? g : sub;
+    rend = has ? (ROLE == 2 ? w - 1 : w) : 0;
+    if (ROLE == 0) { s1.fwd(i, rbeg, g, Nb); s2.bwd(i + rbeg + 1, w - 1 - rbeg, g, Nb); }
+    else if (ROLE == 1) { s1.fwd(i, rbeg, g, Nb); s2.bwd(i + rbeg, w - rbeg, g, Nb); }
+    else { s1.fwd(i, rbeg + 1, g, Nb); s2.bwd(i + rbeg + 1, w - 1 - rbeg, g, Nb); }
+}
+// the two terms of one split point
+template <int ROLE, typename Chart>
+__device__ __forceinline__ void role_terms(const Chart &c, int i1, int i2, float &t0, float &t1) {
+    if (ROLE == 0) {
+        const float2 a = hi2(c.C4[i1]), b = lo2(c.C4[i2]);
+        t0 = a.y + b.x; t1 = a.x + b.y;
+    } else if (ROLE == 1) {
+        const float cl = c.C4[i1].y;
+        const float2 e = c.IL[i2];
+        t0 = cl + e.x; t1 = cl + e.y;
+    } else {
+        const float2 f = c.IR[i1];
+        const float cr = c.C4[i2].w;
+        t0 = f.x + cr; t1 = f.y + cr;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
-// log semiring, one width of the inside sweep (dmv.py:47-63), G lanes per span
+// log semiring, one width of the inside sweep (dmv.py:47-63)
 // ---------------------------------------------------------------------------------------------
-template <int G, int NT>
-__device__ __forceinline__ void inside_width(const LogChart &c, int w, int Nb, int len, float mask_zero, bool keep_x) {
-    const int tid = threadIdx.x;
-    const int ncell = Nb - w;
-    const int sub = tid & (G - 1);
-    const unsigned mask = group_mask<G>();
-    for (int i = tid / G; i < ncell; i += NT / G) {
+template <int NT, int ROLE>
+__device__ __forceinline__ void inside_role(const LogChart &c, const Lane &ln, int w, int Nb, int len, float mask_zero,
+                                            bool keep_x) {
+    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
+    const int g = q.g, sub = q.sub, lg = q.lg;
+    for (int round = 0; round < q.nrounds; ++round) {
+        const int i = q.first_cell + (round << q.cpr_log2);
+        const bool has = i < q.ncell;
         const int j = i + w;
         const int own = cidx(i, w, Nb);
-        // six reductions over the split point: XL, XR, CL[HAS], CL[NO], CR[HAS], CR[NO]; the width-w operand of
-        // the complete items (the span's own incomplete item) is merged at the end, so one pass serves all six
-        float m[6], s[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) { m[q] = NEG_BIG; s[q] = 0.f; }
-        for (int r0 = sub; r0 < w; r0 += G * KCH) {
-            float t[6][KCH];
+        Lse2 acc;
+        acc.init();
+        int rbeg, rend;
+        Stream s1, s2;
+        role_range<ROLE>(i, w, g, sub, Nb, has, rbeg, rend, s1, s2);
+        for (int r0 = rbeg; r0 < rend; r0 += g * KCH) {
+            const int n = min(KCH, (rend - r0 + g - 1) >> lg);
+            float t0[KCH], t1[KCH];
 #pragma unroll
             for (int k = 0; k < KCH; ++k) {
-                const int rp = r0 + k * G;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) t[q][k] = NEG_BIG;
-                if (rp < w) {
-                    const float4 ca = c.C4[cidx(i, rp, Nb)];                  // CL[i+rp][i], CR[i][i+rp]
-                    const float4 cb = c.C4[cidx(i + rp + 1, w - 1 - rp, Nb)];  // CL[j][i+rp+1], CR[i+rp+1][j]
-                    t[0][k] = ca.w + cb.x;  // step 1 (dmv.py:50): CR[i][r][NO] + CL[j][r+1][HAS]
-                    t[1][k] = ca.z + cb.y;  // step 2 (dmv.py:54): CR[i][r][HAS] + CL[j][r+1][NO]
-                    if (rp > 0) {           // step 3 (dmv.py:58): CL[r][i][NO] + IL[j][r][v], r = i + rp
-                        const float2 e = c.IL[cidx(i + rp, w - rp, Nb)];
-                        t[2][k] = ca.y + e.x; t[3][k] = ca.y + e.y;
-                    }
-                    if (rp < w - 1) {       // step 4 (dmv.py:61): IR[i][r][v] + CR[r][j][NO], r = i + 1 + rp
-                        const float2 f = c.IR[cidx(i, rp + 1, Nb)];
-                        t[4][k] = f.x + cb.w; t[5][k] = f.y + cb.w;
-                    }
+                t0[k] = NEG_BIG; t1[k] = NEG_BIG;
+                if (k < n) role_terms<ROLE>(c, s1.idx, s2.idx, t0[k], t1[k]);
+                s1.next(); s2.next();
+            }
+            acc.add_chunk(t0, t1, n);
+        }
+        acc.combine(g);
+        if (ROLE == 0) {
+            float2 arcL, arcR;
+            if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }  // attach + dec[GO], pre-added (dmv.py:36-37)
+            __syncwarp();
+            if (has && sub == 0) {
+                const float XL = acc.m0 + flog(acc.s0), XR = acc.m1 + flog(acc.s1);
+                c.IL[own] = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
+                c.IR[own] = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
+                if (keep_x) { c.GA[own].w = XL; c.GB[own].w = XR; }
+            }
+            // role X publishes IL / IR of this width; roles CL, CR wait for it once per width
+            if (round == q.nrounds - 1) named_arrive(NT);
+        } else {
+            if (round == 0) named_sync(NT);
+            if (has && sub == 0) {
+                if (ROLE == 1) {
+                    const float2 il = c.IL[own];
+                    const float cii = c.C4[i].y;  // CL[i][i][NO]
+                    lo2(c.C4[own]) = acc.finish_with(cii + il.x, cii + il.y);
+                } else {
+                    const float2 ir = c.IR[own];
+                    const float cjj = c.C4[j].w;  // CR[j][j][NO]
+                    float2 r = acc.finish_with(ir.x + cjj, ir.y + cjj);
+                    if (i == 0 && w != len) r = make_float2(mask_zero, mask_zero);  // single root (dmv.py:63)
+                    hi2(c.C4[own]) = r;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                float cm = t[q][0];
-#pragma unroll
-                for (int k = 1; k < KCH; ++k) cm = fmaxf(cm, t[q][k]);
-                const float nm = fmaxf(m[q], cm);
-                float acc = s[q] * VEXP(m[q] - nm);
-#pragma unroll
-                for (int k = 0; k < KCH; ++k) acc += VEXP(t[q][k] - nm);
-                s[q] = acc; m[q] = nm;
-            }
-        }
-        if (G > 1) {  // combine the G lanes' partial (max, sum) pairs; every lane ends with the total
-            float gm[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) gm[q] = m[q];
-#pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) gm[q] = fmaxf(gm[q], __shfl_xor_sync(mask, gm[q], o));
-            }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { s[q] *= VEXP(m[q] - gm[q]); m[q] = gm[q]; }
-#pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) s[q] += __shfl_xor_sync(mask, s[q], o);
-            }
-        }
-        const float XL = m[0] + VLOG(s[0]), XR = m[1] + VLOG(s[1]);
-        const float2 arcL = c.IL[own], arcR = c.IR[own];  // attach + dec[GO], pre-added (dmv.py:36-37)
-        const float2 il = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
-        const float2 ir = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
-        const float cii = c.C4[i].y;  // CL[i][i][NO]
-        const float cjj = c.C4[j].w;  // CR[j][j][NO]
-        float res[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float ownt = q == 0 ? cii + il.x : q == 1 ? cii + il.y : q == 2 ? ir.x + cjj : ir.y + cjj;
-            const float M = fmaxf(m[2 + q], ownt);
-            const float S = s[2 + q] * VEXP(m[2 + q] - M) + VEXP(ownt - M);
-            res[q] = M + VLOG(S);
-        }
-        if (i == 0 && w != len) { res[2] = mask_zero; res[3] = mask_zero; }  // single root (dmv.py:63)
-        if (G > 1) __syncwarp(mask);  // every lane has read the pre-added arc scores of `own`
-        if (sub == 0) {
-            c.IL[own] = il; c.IR[own] = ir;
-            c.C4[own] = make_float4(res[0], res[1], res[2], res[3]);
-            if (keep_x) { c.GA[own].w = XL; c.GB[own].w = XR; }
         }
     }
 }
@@ -172,52 +292,88 @@ __device__ __forceinline__ void inside_width(const LogChart &c, int w, int Nb, i
 // ---------------------------------------------------------------------------------------------
 // log semiring, one width of the reverse sweep (replaces autograd through the chart, helpers.py:150-154)
 // ---------------------------------------------------------------------------------------------
-template <int G, int NT>
-__device__ __forceinline__ void outside_width(const LogChart &c, int w, int Nb, int len) {
-    const int tid = threadIdx.x;
-    const int ncell = Nb - w;
-    const int sub = tid & (G - 1);
-    const unsigned mask = group_mask<G>();
-    for (int i = tid / G; i < ncell; i += NT / G) {
+template <int NT, int ROLE>
+__device__ __forceinline__ void outside_role(const LogChart &c, const Lane &ln, int w, int Nb, int len) {
+    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
+    const int g = q.g, sub = q.sub;
+    for (int round = 0; round < q.nrounds; ++round) {
+        const int i = q.first_cell + (round << q.cpr_log2);
+        const bool has = i < q.ncell;
         const int j = i + w;
         const int own = cidx(i, w, Nb);
-        const float4 ga = c.GA[own], gb = c.GB[own];
-        float2 gcr = make_float2(ga.x, ga.y + gb.z);
-        const float2 gcl = make_float2(gb.x, gb.y + ga.z);
-        const float XL = ga.w, XR = gb.w;
-        const float4 co = c.C4[own];
-        const float2 outL = make_float2(co.x, co.y);
-        float2 outR = make_float2(co.z, co.w);
-        if (i == 0 && w != len) {  // masked cell (dmv.py:63) passes nothing back: p = 0 * exp(-big) = 0
-            gcr = make_float2(0.f, 0.f);
-            outR = make_float2(-NEG_BIG, -NEG_BIG);
+        float2 gcr = make_float2(0.f, 0.f), gcl = gcr, outR = gcr, outL = gcr;
+        float XL = 0.f, XR = 0.f;
+        if (has) {
+            const float4 ga = c.GA[own], gb = c.GB[own];
+            const float4 co = c.C4[own];
+            gcr = make_float2(ga.x, ga.y + gb.z);
+            gcl = make_float2(gb.x, gb.y + ga.z);
+            outR = make_float2(co.z, co.w);
+            outL = make_float2(co.x, co.y);
+            XL = ga.w; XR = gb.w;
+            if (i == 0 && w != len) {  // masked cell (dmv.py:63) passes nothing back: p = 0 * exp(-big) = 0
+                gcr = make_float2(0.f, 0.f);
+                outR = make_float2(-NEG_BIG, -NEG_BIG);
+            }
         }
-        // the span's own incomplete items receive their last contribution from the span's own complete items
-        const float2 il = c.IL[own], ir = c.IR[own];
-        const float cii = c.C4[i].y, cjj = c.C4[j].w;
-        float2 giR = c.gIR[own], giL = c.gIL[own];
-        giR.x += gcr.x * VEXP(ir.x + cjj - outR.x); giR.y += gcr.y * VEXP(ir.y + cjj - outR.y);
-        giL.x += gcl.x * VEXP(cii + il.x - outL.x); giL.y += gcl.y * VEXP(cii + il.y - outL.y);
-        const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
-        if (G > 1) __syncwarp(mask);  // all lanes hold gI[own] before the lane owning rp = 0 / w-1 updates it
-        for (int rp = sub; rp < w; rp += G) {
-            const int ia = cidx(i, rp, Nb), ib = cidx(i + rp + 1, w - 1 - rp, Nb);
-            const int ie = cidx(i + rp, w - rp, Nb), jf = cidx(i, rp + 1, Nb);
-            const float4 ca = c.C4[ia], cb = c.C4[ib];
-            const float2 e = c.IL[ie], f = c.IR[jf];
-            // step 4 transposed: parent CR[i][j][v] -> IR[i][r][v], CR[r][j][NO]
-            const float p0 = gcr.x * VEXP(f.x + cb.w - outR.x);
-            const float p1 = gcr.y * VEXP(f.y + cb.w - outR.y);
-            // step 3 transposed: parent CL[j][i][v] -> CL[r][i][NO], IL[j][r][v]
-            const float q0 = gcl.x * VEXP(ca.y + e.x - outL.x);
-            const float q1 = gcl.y * VEXP(ca.y + e.y - outL.y);
-            // steps 1, 2 transposed: parents IL[j][i], IR[i][j] -> CR[i][r][.], CL[j][r+1][.]
-            const float pL = gxL * VEXP(ca.w + cb.x - XL);
-            const float pR = gxR * VEXP(ca.z + cb.y - XR);
-            float2 t = c.gIR[jf]; t.x += p0; t.y += p1; c.gIR[jf] = t;
-            float2 u = c.gIL[ie]; u.x += q0; u.y += q1; c.gIL[ie] = u;
-            float4 A = c.GA[ia]; A.x += pR; A.y += pL; A.z += q0 + q1; c.GA[ia] = A;
-            float4 B = c.GB[ib]; B.x += pL; B.y += pR; B.z += p0 + p1; c.GB[ib] = B;
+        const int rend = has ? w : 0;
+        if (ROLE == 0) {
+            // parents IL[j][i], IR[i][j] (steps 1, 2 transposed) -> CR[i][r][.], CL[j][r+1][.]
+            // their gradient is complete once the span's own complete items have contributed (r = j resp. r = i)
+            float2 giR = make_float2(0.f, 0.f), giL = giR;
+            if (has) {
+                const float2 il = c.IL[own], ir = c.IR[own];
+                const float cii = c.C4[i].y, cjj = c.C4[j].w;
+                giR = c.gIR[own]; giL = c.gIL[own];
+                giR.x += gcr.x * fexp(ir.x + cjj - outR.x); giR.y += gcr.y * fexp(ir.y + cjj - outR.y);
+                giL.x += gcl.x * fexp(cii + il.x - outL.x); giL.y += gcl.y * fexp(cii + il.y - outL.y);
+            }
+            __syncwarp();
+            if (has && sub == 0) { c.gIR[own] = giR; c.gIL[own] = giL; }  // final: d Z / d attach of this span
+            const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
+            Stream sa, sb;
+            sa.fwd(i, sub, g, Nb);
+            sb.bwd(i + sub + 1, w - 1 - sub, g, Nb);
+#pragma unroll 2
+            for (int rp = sub; rp < rend; rp += g) {
+                const float2 a = hi2(c.C4[sa.idx]);
+                const float2 b = lo2(c.C4[sb.idx]);
+                const float pL = gxL * fexp(a.y + b.x - XL);
+                const float pR = gxR * fexp(a.x + b.y - XR);
+                float2 A = lo2(c.GA[sa.idx]); A.x += pR; A.y += pL; lo2(c.GA[sa.idx]) = A;
+                float2 B = lo2(c.GB[sb.idx]); B.x += pL; B.y += pR; lo2(c.GB[sb.idx]) = B;
+                sa.next(); sb.next();
+            }
+        } else if (ROLE == 1) {
+            // parent CL[j][i][v] (step 3 transposed) -> CL[r][i][NO], IL[j][r][v]; IL[j][i] itself is role X's
+            Stream sa, se;
+            sa.fwd(i, sub, g, Nb);
+            se.bwd(i + sub, w - sub, g, Nb);
+#pragma unroll 2
+            for (int rp = sub; rp < rend; rp += g) {
+                const float cl = c.C4[sa.idx].y;
+                const float2 e = c.IL[se.idx];
+                const float q0 = gcl.x * fexp(cl + e.x - outL.x);
+                const float q1 = gcl.y * fexp(cl + e.y - outL.y);
+                c.GA[sa.idx].z += q0 + q1;
+                if (rp > 0) { float2 u = c.gIL[se.idx]; u.x += q0; u.y += q1; c.gIL[se.idx] = u; }
+                sa.next(); se.next();
+            }
+        } else {
+            // parent CR[i][j][v] (step 4 transposed) -> IR[i][r][v], CR[r][j][NO]; IR[i][j] itself is role X's
+            Stream sf, sb;
+            sf.fwd(i, sub + 1, g, Nb);
+            sb.bwd(i + sub + 1, w - 1 - sub, g, Nb);
+#pragma unroll 2
+            for (int rp = sub; rp < rend; rp += g) {
+                const float2 f = c.IR[sf.idx];
+                const float cr = c.C4[sb.idx].w;
+                const float p0 = gcr.x * fexp(f.x + cr - outR.x);
+                const float p1 = gcr.y * fexp(f.y + cr - outR.y);
+                c.GB[sb.idx].z += p0 + p1;
+                if (rp < w - 1) { float2 t = c.gIR[sf.idx]; t.x += p0; t.y += p1; c.gIR[sf.idx] = t; }
+                sf.next(); sb.next();
+            }
         }
     }
 }
@@ -237,6 +393,9 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     c.carve(mem, nc);
     const bool want_grad = (p.gdec != nullptr) || (p.gattach != nullptr);
 
+    const bool prof = p.prof && b == 0 && tid == 0;
+    long long t0c = 0;
+    if (prof) t0c = clock64();
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
     for (int t = tid; t < Nb * 8; t += NT) sdec[t] = dec[t];
@@ -257,29 +416,28 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     }
     __syncthreads();
 
+    if (prof) p.prof[0] = clock64() - t0c;
+    Lane ln;
+    ln.init<NT>(p);
     for (int w = 1; w < Nb; ++w) {
-        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
-            case 1: inside_width<1, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
-            case 2: inside_width<2, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
-            case 4: inside_width<4, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
-            default: inside_width<8, NT>(c, w, Nb, len, p.mask_zero, want_grad); break;
-        }
+        if (ln.role == 0) inside_role<NT, 0>(c, ln, w, Nb, len, p.mask_zero, want_grad);
+        else if (ln.role == 1) inside_role<NT, 1>(c, ln, w, Nb, len, p.mask_zero, want_grad);
+        else inside_role<NT, 2>(c, ln, w, Nb, len, p.mask_zero, want_grad);
         __syncthreads();
     }
+    if (prof) p.prof[1] = clock64() - t0c;
     if (tid == 0) p.Z[b] = c.C4[cidx(0, len, Nb)].w;  // dmv.py:65
     if (!want_grad) { __syncthreads(); return; }
 
     if (tid == 0) c.GB[cidx(0, len, Nb)].z = p.gZ ? p.gZ[b] : 1.f;
     __syncthreads();
     for (int w = Nb - 1; w >= 1; --w) {
-        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
-            case 1: outside_width<1, NT>(c, w, Nb, len); break;
-            case 2: outside_width<2, NT>(c, w, Nb, len); break;
-            case 4: outside_width<4, NT>(c, w, Nb, len); break;
-            default: outside_width<8, NT>(c, w, Nb, len); break;
-        }
+        if (ln.role == 0) outside_role<NT, 0>(c, ln, w, Nb, len);
+        else if (ln.role == 1) outside_role<NT, 1>(c, ln, w, Nb, len);
+        else outside_role<NT, 2>(c, ln, w, Nb, len);
         __syncthreads();
     }
+    if (prof) p.prof[2] = clock64() - t0c;
     // ---------------- outputs ----------------
     if (p.gattach) {
         float2 *ga = reinterpret_cast<float2 *>(p.gattach + (size_t)b * N * N * 2);
@@ -310,6 +468,7 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
         }
     }
     __syncthreads();
+    if (prof) p.prof[3] = clock64() - t0c;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,80 +477,88 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
 struct MaxChart {
     float4 *C4;
     float2 *IL, *IR;
-    uint32_t *bpA;  // XL | XR << 8 | CL[HAS] << 16 | CL[NO] << 24
-    uint16_t *bpB;  // CR[HAS] | CR[NO] << 8
+    uint8_t *bp;  // 6 bytes per cell: XL, XR, CL[HAS], CL[NO], CR[HAS], CR[NO]  (first maximal split)
 };
 
 // items of the back-trace: kind (0 CR, 1 CL, 2 IR, 3 IL) | v << 2 | lo << 3 | hi << 12
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
-template <int G, int NT>
-__device__ __forceinline__ void viterbi_width(const MaxChart &c, int w, int Nb, int len, float mask_zero) {
-    const int tid = threadIdx.x;
-    const int ncell = Nb - w;
-    const int sub = tid & (G - 1);
-    const unsigned mask = group_mask<G>();
-    for (int i = tid / G; i < ncell; i += NT / G) {
+#ifdef VLGAE_PROF_DETAIL
+struct ProfAcc { long long v[8]; long long last; };
+#define PROF_MARK(slot) do { long long now_ = clock64(); pa.v[slot] += now_ - pa.last; pa.last = now_; } while (0)
+#else
+struct ProfAcc { };
+#define PROF_MARK(slot) do { } while (0)
+#endif
+template <int NT, int ROLE>
+__device__ __forceinline__ void viterbi_role(const MaxChart &c, const Lane &ln, int w, int Nb, int len,
+                                             float mask_zero, ProfAcc &pa) {
+    PROF_MARK(0);
+    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
+    const int g = q.g, sub = q.sub;
+    for (int round = 0; round < q.nrounds; ++round) {
+        const int i = q.first_cell + (round << q.cpr_log2);
+        const bool has = i < q.ncell;
         const int j = i + w;
         const int own = cidx(i, w, Nb);
-        float bv[6];
-        int ba[6];
+        Max2 acc;
+        acc.init();
+        int rbeg, rend;
+        Stream s1, s2;
+        role_range<ROLE>(i, w, g, sub, Nb, has, rbeg, rend, s1, s2);
+        PROF_MARK(1);
+        for (int r0 = rbeg; r0 < rend; r0 += 4 * g) {
+            float t0[4], t1[4];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) { bv[q] = NEG_BIG; ba[q] = 0x7fffffff; }
-        // rp increases within a lane and the update is strict (>), so each lane keeps its FIRST maximum
-        for (int rp = sub; rp < w; rp += G) {
-            const float4 ca = c.C4[cidx(i, rp, Nb)];
-            const float4 cb = c.C4[cidx(i + rp + 1, w - 1 - rp, Nb)];
-            float t = __fadd_rn(ca.w, cb.x);
-            if (t > bv[0]) { bv[0] = t; ba[0] = rp; }
-            t = __fadd_rn(ca.z, cb.y);
-            if (t > bv[1]) { bv[1] = t; ba[1] = rp; }
-            if (rp > 0) {
-                const float2 e = c.IL[cidx(i + rp, w - rp, Nb)];
-                t = __fadd_rn(ca.y, e.x);
-                if (t > bv[2]) { bv[2] = t; ba[2] = rp; }
-                t = __fadd_rn(ca.y, e.y);
-                if (t > bv[3]) { bv[3] = t; ba[3] = rp; }
+            for (int k = 0; k < 4; ++k) {
+                t0[k] = NEG_BIG; t1[k] = NEG_BIG;
+                if (r0 + k * g < rend) {
+                    role_terms<ROLE>(c, s1.idx, s2.idx, t0[k], t1[k]);  // plain fp32 adds: nothing to contract
+                }
+                s1.next(); s2.next();
             }
-            if (rp < w - 1) {
-                const float2 f = c.IR[cidx(i, rp + 1, Nb)];
-                t = __fadd_rn(f.x, cb.w);
-                if (t > bv[4]) { bv[4] = t; ba[4] = rp; }
-                t = __fadd_rn(f.y, cb.w);
-                if (t > bv[5]) { bv[5] = t; ba[5] = rp; }
-            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc.add(t0[k], t1[k], r0 + k * g);  // NEG_BIG never beats a real term
         }
-        if (G > 1) {  // across lanes: larger value wins, equal values -> smaller split (torch.max tie rule)
-#pragma unroll
-            for (int o = G >> 1; o > 0; o >>= 1) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const float ov = __shfl_xor_sync(mask, bv[q], o);
-                    const int oa = __shfl_xor_sync(mask, ba[q], o);
-                    if (ov > bv[q] || (ov == bv[q] && oa < ba[q])) { bv[q] = ov; ba[q] = oa; }
+        PROF_MARK(2);
+        acc.combine(g);
+        PROF_MARK(3);
+        if (ROLE == 0) {
+            float2 arcL, arcR;
+            if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }
+            __syncwarp();
+            if (has && sub == 0) {
+                c.IL[own] = make_float2(__fadd_rn(acc.v0, arcL.x), __fadd_rn(acc.v0, arcL.y));
+                c.IR[own] = make_float2(__fadd_rn(acc.v1, arcR.x), __fadd_rn(acc.v1, arcR.y));
+                c.bp[own * 6 + 0] = (uint8_t)acc.a0; c.bp[own * 6 + 1] = (uint8_t)acc.a1;
+            }
+            PROF_MARK(4);
+            if (round == q.nrounds - 1) named_arrive(NT);
+            PROF_MARK(5);
+        } else {
+            if (round == 0) named_sync(NT);
+            PROF_MARK(5);
+            if (has && sub == 0) {
+                if (ROLE == 1) {  // the span's own incomplete item is split 0: it wins ties
+                    const float2 il = c.IL[own];
+                    const float cii = c.C4[i].y;
+                    const float t0 = __fadd_rn(cii, il.x), t1 = __fadd_rn(cii, il.y);
+                    if (t0 >= acc.v0) { acc.v0 = t0; acc.a0 = 0; }
+                    if (t1 >= acc.v1) { acc.v1 = t1; acc.a1 = 0; }
+                    lo2(c.C4[own]) = make_float2(acc.v0, acc.v1);
+                    c.bp[own * 6 + 2] = (uint8_t)acc.a0; c.bp[own * 6 + 3] = (uint8_t)acc.a1;
+                } else {  // the span's own incomplete item is split w-1: it loses ties
+                    const float2 ir = c.IR[own];
+                    const float cjj = c.C4[j].w;
+                    const float t0 = __fadd_rn(ir.x, cjj), t1 = __fadd_rn(ir.y, cjj);
+                    if (t0 > acc.v0) { acc.v0 = t0; acc.a0 = w - 1; }
+                    if (t1 > acc.v1) { acc.v1 = t1; acc.a1 = w - 1; }
+                    if (i == 0 && w != len) { acc.v0 = mask_zero; acc.v1 = mask_zero; }
+                    hi2(c.C4[own]) = make_float2(acc.v0, acc.v1);
+                    c.bp[own * 6 + 4] = (uint8_t)acc.a0; c.bp[own * 6 + 5] = (uint8_t)acc.a1;
                 }
             }
-        }
-        const float2 arcL = c.IL[own], arcR = c.IR[own];
-        const float2 il = make_float2(__fadd_rn(bv[0], arcL.x), __fadd_rn(bv[0], arcL.y));
-        const float2 ir = make_float2(__fadd_rn(bv[1], arcR.x), __fadd_rn(bv[1], arcR.y));
-        const float cii = c.C4[i].y, cjj = c.C4[j].w;
-        // the span's own incomplete items: split 0 for CL (wins ties), split w-1 for CR (loses ties)
-        float t = __fadd_rn(cii, il.x);
-        if (t >= bv[2]) { bv[2] = t; ba[2] = 0; }
-        t = __fadd_rn(cii, il.y);
-        if (t >= bv[3]) { bv[3] = t; ba[3] = 0; }
-        t = __fadd_rn(ir.x, cjj);
-        if (t > bv[4]) { bv[4] = t; ba[4] = w - 1; }
-        t = __fadd_rn(ir.y, cjj);
-        if (t > bv[5]) { bv[5] = t; ba[5] = w - 1; }
-        if (i == 0 && w != len) { bv[4] = mask_zero; bv[5] = mask_zero; }
-        if (G > 1) __syncwarp(mask);
-        if (sub == 0) {
-            c.IL[own] = il; c.IR[own] = ir;
-            c.C4[own] = make_float4(bv[2], bv[3], bv[4], bv[5]);
-            c.bpA[own] = (uint32_t)ba[0] | ((uint32_t)ba[1] << 8) | ((uint32_t)ba[2] << 16) | ((uint32_t)ba[3] << 24);
-            c.bpB[own] = (uint16_t)((uint32_t)ba[4] | ((uint32_t)ba[5] << 8));
+            PROF_MARK(4);
         }
     }
 }
@@ -407,9 +574,11 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     MaxChart c;
     c.C4 = reinterpret_cast<float4 *>(mem);
     c.IL = reinterpret_cast<float2 *>(c.C4 + nc); c.IR = c.IL + nc;
-    c.bpA = reinterpret_cast<uint32_t *>(c.IR + nc);
-    c.bpB = reinterpret_cast<uint16_t *>(c.bpA + nc);
-    int *queue = reinterpret_cast<int *>(c.bpB + ((nc + 1) & ~1));  // 2 x (2 Nb + 2) ints
+    int *queue = reinterpret_cast<int *>(c.IR + nc);  // 2 x (2 Nb + 2) ints
+    c.bp = reinterpret_cast<uint8_t *>(queue + 2 * (2 * Nb + 2));
+    const bool prof = p.prof && b == 0 && tid == 0;
+    long long t0c = 0;
+    if (prof) t0c = clock64();
 
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
@@ -434,15 +603,27 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
     if (p.heads) for (int t = tid; t < N; t += NT) p.heads[(size_t)b * N + t] = 0;
     __syncthreads();
 
+    if (prof) p.prof[4] = clock64() - t0c;
+    Lane ln;
+    ln.init<NT>(p);
+    ProfAcc pa;
+#ifdef VLGAE_PROF_DETAIL
+    for (int k = 0; k < 8; ++k) pa.v[k] = 0;
+    pa.last = clock64();
+#endif
     for (int w = 1; w < Nb; ++w) {
-        switch (lanes_per_cell(Nb - w, w, NT, p.gmax)) {
-            case 1: viterbi_width<1, NT>(c, w, Nb, len, p.mask_zero); break;
-            case 2: viterbi_width<2, NT>(c, w, Nb, len, p.mask_zero); break;
-            case 4: viterbi_width<4, NT>(c, w, Nb, len, p.mask_zero); break;
-            default: viterbi_width<8, NT>(c, w, Nb, len, p.mask_zero); break;
-        }
+        if (ln.role == 0) viterbi_role<NT, 0>(c, ln, w, Nb, len, p.mask_zero, pa);
+        else if (ln.role == 1) viterbi_role<NT, 1>(c, ln, w, Nb, len, p.mask_zero, pa);
+        else viterbi_role<NT, 2>(c, ln, w, Nb, len, p.mask_zero, pa);
+        PROF_MARK(6);
         __syncthreads();
+        PROF_MARK(7);
     }
+#ifdef VLGAE_PROF_DETAIL
+    if (p.prof && b == 0 && (tid == 0 || tid == NT / 3 || tid == 2 * NT / 3))
+        for (int k = 0; k < 8; ++k) p.prof[8 + (tid / (NT / 3)) * 8 + k] = pa.v[k];
+#endif
+    if (prof) p.prof[5] = clock64() - t0c;
     if (tid == 0) p.best[b] = c.C4[cidx(0, len, Nb)].w;
 
     // back-trace: breadth-first over the derivation, one warp, two children per expanded item
@@ -465,23 +646,21 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
                     if (kind < 2 && d == 0) {  // STOP decision of position lo; kind 0 = right side
                         if (p.vgdec) atomicAdd(&p.vgdec[(size_t)b * N * 8 + lo * 8 + (kind == 0 ? 4 : 0) + v * 2 + 1], 1.f);
                     } else {
-                        const int own = cidx(lo, d, Nb);
-                        const uint32_t ba = c.bpA[own];
-                        const uint32_t bb = c.bpB[own];
+                        const uint8_t *bp = c.bp + cidx(lo, d, Nb) * 6;
                         if (kind == 0) {  // CR(lo,hi,v) -> IR(lo,r,v) + CR(r,hi,NO), r = lo+1+bp
-                            const int r = lo + 1 + (int)((bb >> (8 * v)) & 255);
+                            const int r = lo + 1 + (int)bp[4 + v];
                             c1 = mk_item(2, v, lo, r); c2 = mk_item(0, 1, r, hi);
                         } else if (kind == 1) {  // CL(hi,lo,v) -> CL(r,lo,NO) + IL(hi,r,v), r = lo+bp
-                            const int r = lo + (int)((ba >> (16 + 8 * v)) & 255);
+                            const int r = lo + (int)bp[2 + v];
                             c1 = mk_item(1, 1, lo, r); c2 = mk_item(3, v, r, hi);
                         } else if (kind == 2) {  // IR: arc lo -> hi; XR -> CR(lo,r,HAS) + CL(hi,r+1,NO)
-                            const int r = lo + (int)((ba >> 8) & 255);
+                            const int r = lo + (int)bp[1];
                             c1 = mk_item(0, 0, lo, r); c2 = mk_item(1, 1, r + 1, hi);
                             if (p.heads) p.heads[(size_t)b * N + hi] = lo;
                             if (p.arcs) p.arcs[(((size_t)b * N + lo) * N + hi) * 2 + v] = 1.f;
                             if (p.vgdec) atomicAdd(&p.vgdec[(size_t)b * N * 8 + lo * 8 + 4 + v * 2 + 0], 1.f);
                         } else {  // IL: arc hi -> lo; XL -> CR(lo,r,NO) + CL(hi,r+1,HAS)
-                            const int r = lo + (int)(ba & 255);
+                            const int r = lo + (int)bp[0];
                             c1 = mk_item(0, 1, lo, r); c2 = mk_item(1, 0, r + 1, hi);
                             if (p.heads) p.heads[(size_t)b * N + lo] = hi;
                             if (p.arcs) p.arcs[(((size_t)b * N + hi) * N + lo) * 2 + v] = 1.f;
@@ -502,6 +681,7 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
         }
     }
     __syncthreads();
+    if (prof) p.prof[6] = clock64() - t0c;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,7 +782,7 @@ __global__ void fp32_bench_kernel(int iters, float *sink) {
 size_t log_chart_bytes(int N) { return (size_t)ncells(N) * 80; }
 size_t max_chart_bytes(int N) {
     const size_t nc = ncells(N);
-    return nc * 32 + nc * 4 + ((nc + 1) & ~(size_t)1) * 2 + (size_t)(2 * (2 * N + 2)) * 4 + 16;
+    return nc * 32 + (size_t)(2 * (2 * N + 2)) * 4 + nc * 6 + 16;
 }
 static size_t dec_bytes(int N) { return ((size_t)N * 8 * sizeof(float) + 15) & ~(size_t)15; }
 
@@ -663,8 +843,10 @@ static cudaError_t launch_nt(DmvArgs a, int passes, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static int g_tune_gmax = 0, g_tune_threads = 0;
-void dmv_set_tuning(int gmax, int threads) { g_tune_gmax = gmax; g_tune_threads = threads; }
+static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
+static long long *g_prof = nullptr;
+void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
+void dmv_set_tuning(int gmax, int threads, int tpl) { g_tune_gmax = gmax; g_tune_threads = threads; g_tune_tpl = tpl; }
 
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -673,6 +855,7 @@ static int env_int(const char *name, int dflt) {
 
 cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     DmvArgs a = a_in;
+    a.prof = g_prof;
     cudaError_t e = device_info();
     if (e != cudaSuccess) return e;
     // Tunables (experiments: VLGAE_DMV_GMAX / VLGAE_DMV_THREADS).  Few sentences per SM = latency-bound: spread
@@ -683,11 +866,14 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     const int env_threads = g_tune_threads > 0 ? g_tune_threads : env_threads0;
     const int items = a.B * a.npass;
     const bool bulk = items > 6 * g_sm_count;
-    if (a.gmax <= 0) a.gmax = env_gmax > 0 ? env_gmax : (bulk ? 1 : 4);
-    if (a.threads <= 0) a.threads = env_threads > 0 ? env_threads : (a.N <= 48 ? (bulk ? 64 : 128) : 256);
-    if (a.threads <= 64) return launch_nt<64>(a, passes, st);
-    if (a.threads <= 128) return launch_nt<128>(a, passes, st);
-    return launch_nt<256>(a, passes, st);
+    if (a.gmax <= 0) a.gmax = env_gmax > 0 ? env_gmax : 32;
+    // split points per lane before a span is shared between lanes (power of two)
+    if (a.tpl <= 0) a.tpl = g_tune_tpl > 0 ? g_tune_tpl : 4;
+    // CTA = 3 roles x LPR lanes; LPR >= the number of spans of the shortest width keeps every width to one round
+    if (a.threads <= 0) a.threads = env_threads > 0 ? env_threads : (a.N <= 33 ? 96 : (a.N <= 65 ? 192 : 384));
+    if (a.threads <= 96) return launch_nt<96>(a, passes, st);
+    if (a.threads <= 192) return launch_nt<192>(a, passes, st);
+    return launch_nt<384>(a, passes, st);
 }
 
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,

@@ -29,14 +29,17 @@ struct DmvArgs {
     int npass;         // 1: only `first_pass`; 2: log and max CTAs interleaved
     int first_pass;    // 0 = log, 1 = max
     int gmax;          // max lanes per span (1, 2, 4, 8); 0 = choose from the batch size
-    int threads;       // CTA size (64, 128, 256); 0 = choose from N
+    int threads;       // CTA size (96, 192, 384); 0 = choose from N
+    long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
+    int tpl;           // split points per lane before a span is shared between lanes (1..32, power of 2); 0 = auto
 };
 
 // passes bitmask: 1 = log semiring, 2 = max semiring
 size_t dmv_chart_bytes(int N, int passes);
 bool dmv_fits_smem(int N, int passes);
 int dmv_grid_for_workspace(int B);
-void dmv_set_tuning(int gmax, int threads);
+void dmv_set_tuning(int gmax, int threads, int tpl);
+void dmv_set_profile_buffer(long long *buf);
 cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st);
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);
