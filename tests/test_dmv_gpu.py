@@ -12,6 +12,23 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 Z_RTOL, MARG_ATOL, DEC_ATOL = 1e-4, 1e-5, 4e-5
+
+
+def marg_tol(Z):
+    """Per-sentence absolute tolerance for marginals: BASELINE's 1e-5, widened to two fp32 ulps of |log Z| (relative).
+
+    Chart values of a length-40 sentence are ~ -170, where one fp32 ulp is 1.5e-5: two fp32 implementations that
+    differ in the last bit of ONE cell on the main derivation (they must, unless they replay the reference's exact
+    instruction sequence) differ by that factor in every marginal.  tools/dmv_error_study.py shows exactly this:
+    |gpu - ref| <= 2e-6 except for sentences whose log Z differs by one ulp, and there |gpu - fp64| < |ref - fp64|.
+    """
+    return np.maximum(MARG_ATOL, 2.0 ** -22 * np.abs(np.asarray(Z, dtype=np.float64)))
+
+
+def assert_marginals(actual, desired, Z, scale=1.0):
+    tol = marg_tol(Z).reshape((-1,) + (1,) * (actual.ndim - 1)) * scale
+    err = np.abs(actual.astype(np.float64) - desired)
+    assert (err <= tol).all(), f"max |err| {err.max():.3e}, worst err/tol {(err / tol).max():.2f}"
 DMV_CASES = ["dmv_tiny_ragged", "dmv_cfg1", "dmv_cfg1_ragged", "dmv_ties_q025", "dmv_ties_q1", "dmv_ties_zero",
              "dmv_len40"]
 
@@ -50,8 +67,8 @@ def check_all(md, ma, L, dev, marg_atol=MARG_ATOL):
     Z, gdec, gatt = oracle.dmv_log(md, ma, L, trim=True)
     best, heads, arcs, vgdec = oracle.dmv_viterbi(md, ma, L, trim=True)
     np.testing.assert_allclose(out.Z.cpu().numpy(), Z, rtol=Z_RTOL)
-    np.testing.assert_allclose(out.gattach.cpu().numpy(), gatt, atol=marg_atol, rtol=0)
-    np.testing.assert_allclose(out.gdec.cpu().numpy(), gdec, atol=4 * marg_atol, rtol=0)
+    assert_marginals(out.gattach.cpu().numpy(), gatt, Z, marg_atol / MARG_ATOL)
+    assert_marginals(out.gdec.cpu().numpy(), gdec, Z, 4 * marg_atol / MARG_ATOL)
     np.testing.assert_array_equal(out.best.cpu().numpy(), best)
     np.testing.assert_array_equal(out.heads.cpu().numpy(), heads)
     np.testing.assert_array_equal(out.arcs.cpu().numpy(), arcs)
@@ -68,8 +85,8 @@ def test_golden_reference_vectors(golden, dev, name):
     Z, gdec, gatt = ops.dmv_inside_outside(md, ma, L)
     best, heads, arcs, vgdec = ops.dmv_viterbi(md, ma, L, want_gdec=True)
     np.testing.assert_allclose(Z.cpu().numpy(), g["partition"][:, 0], rtol=Z_RTOL)
-    np.testing.assert_allclose(gatt.cpu().numpy(), g["grad_attach"], atol=MARG_ATOL, rtol=0)
-    np.testing.assert_allclose(gdec.cpu().numpy(), g["grad_dec"], atol=DEC_ATOL, rtol=0)
+    assert_marginals(gatt.cpu().numpy(), g["grad_attach"], g["partition"][:, 0])
+    assert_marginals(gdec.cpu().numpy(), g["grad_dec"], g["partition"][:, 0], 4)
     np.testing.assert_array_equal(best.cpu().numpy(), g["max"][:, 0])
     np.testing.assert_array_equal(heads.cpu().numpy(), g["heads"])
     np.testing.assert_array_equal(vgdec.cpu().numpy(), g["vgrad_dec"])
@@ -156,7 +173,7 @@ def test_cfg2_shape_ragged_sorted(dev):
     L = torch.randint(4, 41, (128,), generator=g).sort(descending=True).values
     L[0] = 40
     md, ma, L = synth(128, 40, 2, L)
-    out = check_all(md, ma, L, dev, marg_atol=2e-5)  # fp32 noise floor at len 40 (see test_noise_floor_vs_f64)
+    out = check_all(md, ma, L, dev)
     m = out.gattach.cpu().numpy().sum(-1)
     for b in range(128):
         np.testing.assert_allclose(m[b, :, 1:L[b] + 1].sum(0), 1.0, atol=1e-4)
@@ -174,7 +191,7 @@ def test_noise_floor_vs_f64(dev):
     _, _, gpu = ops.dmv_inside_outside(_t(md, dev), _t(ma, dev), _t(L, dev))
     e_gpu = np.abs(gpu.cpu().numpy() - g64).max()
     e_ref = np.abs(g32 - g64).max()
-    assert e_gpu < max(2.0 * e_ref, 1e-5), (e_gpu, e_ref)
+    assert e_gpu < max(1.5 * e_ref, 1e-5), (e_gpu, e_ref)
 
 
 @pytest.mark.parametrize("quant", [1.0, 0.5, 0.25])
@@ -208,12 +225,12 @@ def test_long_sentences(dev, B, n):
     g = torch.Generator().manual_seed(n)
     L = torch.randint(n // 2, n + 1, (B,), generator=g)
     L[0] = n
-    check_all(*synth(B, n, 40 + n, L), dev, marg_atol=5e-5)
+    check_all(*synth(B, n, 40 + n, L), dev)
 
 
 def test_cfg3_sweep_small(dev):
     for n in (8, 16, 32):
-        check_all(*synth(512, n, 3), dev, marg_atol=2e-5)
+        check_all(*synth(512, n, 3), dev)
 
 
 @pytest.mark.parametrize("gmax,threads,tpl", [(1, 96, 8), (1, 192, 1), (2, 192, 4), (8, 192, 2), (32, 192, 1),
@@ -226,7 +243,7 @@ def test_launch_tuning_does_not_change_results(dev, gmax, threads, tpl):
         g = torch.Generator().manual_seed(5)
         L = torch.randint(1, 41, (48,), generator=g)
         L[0] = 40
-        check_all(*synth(48, 40, 50 + gmax, L, quant=0.5 if gmax == 2 else None), dev, marg_atol=2e-5)
+        check_all(*synth(48, 40, 50 + gmax, L, quant=0.5 if gmax == 2 else None), dev)
     finally:
         check(lib().vlgae_dmv_set_tuning(0, 0, 0), "set_tuning")
 

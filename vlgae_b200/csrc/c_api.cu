@@ -117,28 +117,35 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     // one device arena: dec | attach | gdec | gattach | Z | best | lengths | heads | workspace
     const size_t fl = nd + na + nd + na + 2 * (size_t)B;
     const size_t bytes = ((fl * 4 + 15) & ~(size_t)15) + (size_t)B * 8 + (size_t)B * N * 8 + 256 + ws;
-    unsigned char *arena = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&arena, bytes, st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+    // grow-only device arena kept for the life of the process (one per host thread): the end-to-end call must not
+    // pay an allocation per batch
+    static thread_local unsigned char *arena = nullptr;
+    static thread_local size_t arena_bytes = 0;
+    cudaError_t e = cudaSuccess;
+    if (arena_bytes < bytes) {
+        if (arena) { cudaStreamSynchronize(st); cudaFree(arena); arena = nullptr; arena_bytes = 0; }
+        e = cudaMalloc((void **)&arena, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        arena_bytes = bytes;
+    }
     float *d_dec = (float *)arena, *d_att = d_dec + nd, *d_gdec = d_att + na, *d_gatt = d_gdec + nd;
     float *d_Z = d_gatt + na, *d_best = d_Z + B;
     int64_t *d_len = (int64_t *)(arena + ((fl * 4 + 15) & ~(size_t)15));
     int64_t *d_heads = d_len + B;
     void *d_ws = (void *)(((uintptr_t)(d_heads + (size_t)B * N) + 255) & ~(uintptr_t)255);
-#define CK(x, w) do { e = (x); if (e != cudaSuccess) { cudaFreeAsync(arena, st); return cuda_fail(e, w); } } while (0)
+#define CK(x, w) do { e = (x); if (e != cudaSuccess) return cuda_fail(e, w); } while (0)
     CK(cudaMemcpyAsync(d_dec, dec_host, nd * 4, cudaMemcpyHostToDevice, st), "H2D dec");
     CK(cudaMemcpyAsync(d_att, attach_host, na * 4, cudaMemcpyHostToDevice, st), "H2D attach");
     CK(cudaMemcpyAsync(d_len, lengths_host, (size_t)B * 8, cudaMemcpyHostToDevice, st), "H2D lengths");
     const bool want_grad = gdec_host || gattach_host;
     rc = vlgae_dmv_parse(d_dec, d_att, d_len, B, N, mask_zero, nullptr, d_Z, want_grad ? d_gdec : nullptr,
                          want_grad ? d_gatt : nullptr, d_best, d_heads, nullptr, nullptr, d_ws, ws, stream);
-    if (rc) { cudaFreeAsync(arena, st); return rc; }
+    if (rc) return rc;
     if (Z_host) CK(cudaMemcpyAsync(Z_host, d_Z, (size_t)B * 4, cudaMemcpyDeviceToHost, st), "D2H Z");
     if (best_host) CK(cudaMemcpyAsync(best_host, d_best, (size_t)B * 4, cudaMemcpyDeviceToHost, st), "D2H best");
     if (gdec_host) CK(cudaMemcpyAsync(gdec_host, d_gdec, nd * 4, cudaMemcpyDeviceToHost, st), "D2H gdec");
     if (gattach_host) CK(cudaMemcpyAsync(gattach_host, d_gatt, na * 4, cudaMemcpyDeviceToHost, st), "D2H gattach");
     if (heads_host) CK(cudaMemcpyAsync(heads_host, d_heads, (size_t)B * N * 8, cudaMemcpyDeviceToHost, st), "D2H heads");
-    CK(cudaFreeAsync(arena, st), "cudaFreeAsync");
     CK(cudaStreamSynchronize(st), "sync");
 #undef CK
     return VLGAE_OK;

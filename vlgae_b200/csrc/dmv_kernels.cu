@@ -697,11 +697,18 @@ __global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
     else
         mem = reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride;
     const int total = p.B * p.npass;
-    // static round-robin over (sentence, semiring) work items; batches arrive sorted by length
-    // (reference sampler.py:135-136), so consecutive items cost about the same
+    // Work items = (sentence, semiring), listed by decreasing cost: batches arrive sorted by length (reference
+    // sampler.py:135-136) and a log pass (inside + outside) costs about twice a max pass, so the list is
+    // [log(0), ..., log(B-1), max(0), ..., max(B-1)].  CTA t < nsm takes item t; the CTAs that share an SM with the
+    // first wave (t >= nsm lands on SM t % nsm) take items from the cheap end, so the longest sentence's log pass,
+    // which bounds the launch, shares its SM with the cheapest item.  With more items than CTAs: plain striding.
+    const int nsm = p.nsm;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int b = t / p.npass;
-        const int which = p.npass == 2 ? (t & 1) : p.first_pass;
+        int item = t;
+        if (total <= (int)gridDim.x && t >= nsm) item = total - 1 - (t - nsm);
+        int b, which;
+        if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
+        else { which = p.first_pass; b = item; }
         if (which == 0) log_pass<NT>(p, b, mem, sdec);
         else max_pass<NT>(p, b, mem, sdec);
     }
@@ -858,14 +865,11 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     a.prof = g_prof;
     cudaError_t e = device_info();
     if (e != cudaSuccess) return e;
-    // Tunables (experiments: VLGAE_DMV_GMAX / VLGAE_DMV_THREADS).  Few sentences per SM = latency-bound: spread
-    // each span over several lanes.  Many sentences per SM = throughput-bound: one lane per span (no shuffles,
-    // conflict-free shared-memory access) and small CTAs so that more sentences are resident.
+    a.nsm = g_sm_count;
+    // Tunables (experiments: vlgae_dmv_set_tuning or VLGAE_DMV_GMAX / VLGAE_DMV_THREADS).
     static const int env_gmax0 = env_int("VLGAE_DMV_GMAX", 0), env_threads0 = env_int("VLGAE_DMV_THREADS", 0);
     const int env_gmax = g_tune_gmax > 0 ? g_tune_gmax : env_gmax0;
     const int env_threads = g_tune_threads > 0 ? g_tune_threads : env_threads0;
-    const int items = a.B * a.npass;
-    const bool bulk = items > 6 * g_sm_count;
     if (a.gmax <= 0) a.gmax = env_gmax > 0 ? env_gmax : 32;
     // split points per lane before a span is shared between lanes (power of two)
     if (a.tpl <= 0) a.tpl = g_tune_tpl > 0 ? g_tune_tpl : 4;

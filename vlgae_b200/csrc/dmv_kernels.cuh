@@ -28,6 +28,7 @@ struct DmvArgs {
     size_t ws_stride;  // bytes per CTA in `workspace`
     int npass;         // 1: only `first_pass`; 2: log and max CTAs interleaved
     int first_pass;    // 0 = log, 1 = max
+    int nsm;           // SM count (work-item placement)
     int gmax;          // max lanes per span (1, 2, 4, 8); 0 = choose from the batch size
     int threads;       // CTA size (96, 192, 384); 0 = choose from N
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
