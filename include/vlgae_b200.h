@@ -41,6 +41,7 @@ extern "C" {
 #define VLGAE_E_ARCH 4      /* device is not sm_100                              */
 
 #define VLGAE_DMV_MAX_N 256 /* chart positions incl. ROOT (reference data: <= 51) */
+#define VLGAE_ALIGN_MAX_D 128 /* feature width of the alignment contraction (reference: 128) */
 
 /* ABI version (bumped on any signature change). */
 int vlgae_version(void);
@@ -129,6 +130,20 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
  */
 int vlgae_dmv_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                     float *dec_w, float *attach_w, void *stream);
+
+/*
+ * Alignment scores (word / arc queries x scene-graph factors).
+ * Replaces  gather_logit_simple   src/model/joint.py:406-419:
+ *   out[b][a][q][v] = sum_d txt_feat[b][q][d] * vis_feat[a][v][d];  neg_fill where !vis_mask[a][v] or !txt_mask[b][q]
+ *   vis_feat [A][V][D] f32, vis_mask [A][V] bool (1 byte), txt_feat [B][Q][D] f32, txt_mask [B][Q] bool, out [B][A][Q][V] f32
+ * One pass: bf16 tcgen05 MMAs (split = 3: hi/lo operand split, fp32-class result; split = 1: plain bf16), masks fused
+ * into the store.  neg_fill is the reference's -INF = -1e20 (src/__init__.py:110, bound at joint.py:16).
+ * workspace: vlgae_align_workspace_bytes(A, V, B, Q, D) bytes (packed bf16 operand tiles).
+ */
+size_t vlgae_align_workspace_bytes(int A, int V, int B, int Q, int D);
+int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                       const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
+                       float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
 int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);

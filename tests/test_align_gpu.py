@@ -1,0 +1,78 @@
+"""Parity of the tcgen05 alignment kernel (through the C ABI) with the oracle / the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def run(vis, vm, txt, tm, dev, split=3):
+    from vlgae_b200.alignment import gather_logit_simple
+
+    out = gather_logit_simple(_t(vis, dev), _t(vm, dev), _t(txt, dev), _t(tm, dev), split=split)
+    torch.cuda.synchronize()
+    assert out.names == ("B", "A", "Q", "V")
+    return out.rename(None).cpu().numpy()
+
+
+def check(got, want, vis, txt, split):
+    masked = want == -1e20
+    assert ((got == -1e20) == masked).all(), "mask pattern differs"
+    # error model of the split-bf16 product: 3 terms kept -> relative 2^-16 per product, accumulated in fp32
+    scale = np.sqrt((vis.astype(np.float64) ** 2).sum(-1)).max() * np.sqrt((txt.astype(np.float64) ** 2).sum(-1)).max()
+    tol = scale * (2.0 ** -15 if split == 3 else 2.0 ** -7)
+    err = np.abs(got - want)[~masked].max() if (~masked).any() else 0.0
+    assert err <= tol, (err, tol)
+    return err
+
+
+@pytest.mark.parametrize("name", ["align_small", "align_mid"])
+@pytest.mark.parametrize("split", [3, 1])
+def test_golden_reference_vectors(golden, dev, name, split):
+    g = golden(name)
+    got = run(g["vis_feat"], g["vis_mask"], g["txt_feat"], g["txt_mask"], dev, split)
+    check(got, g["attmap"], g["vis_feat"], g["txt_feat"], split)
+    if split == 3:
+        np.testing.assert_allclose(got.max(-1), g["max_v"], rtol=1e-4, atol=2e-3)
+        np.testing.assert_allclose(got.max(2), g["max_q"], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("A,V,B,Q,D", [(2, 1369, 3, 82, 128), (1, 128, 1, 16, 64), (3, 129, 2, 130, 128),
+                                       (5, 300, 7, 33, 100), (2, 40, 2, 1, 8)])
+def test_shapes_against_oracle(dev, A, V, B, Q, D):
+    rng = np.random.default_rng(A * 1000 + V)
+    vis = rng.normal(size=(A, V, D)).astype(np.float32)
+    txt = rng.normal(size=(B, Q, D)).astype(np.float32)
+    vm = rng.random((A, V)) > 0.2
+    tm = rng.random((B, Q)) > 0.2
+    want = oracle.gather_logit_simple(vis, vm, txt, tm)
+    got = run(vis, vm, txt, tm, dev)
+    check(got, want, vis, txt, 3)
+
+
+def test_reduced_and_drop_in_signature(golden, dev):
+    from vlgae_b200.alignment import gather_logit_reduced_impl, gather_logit_simple_impl
+
+    g = golden("align_mid")
+    vis = (_t(g["vis_feat"], dev).refine_names("A", "V", "D"), _t(g["vis_mask"], dev).refine_names("A", "V"), None)
+    txt = (_t(g["txt_feat"], dev).refine_names("B", "Q", "D"), _t(g["txt_mask"], dev).refine_names("B", "Q"),
+           _t(g["txt_marginal"], dev))
+    att = gather_logit_simple_impl(None, {}, vis, txt, None)
+    assert att.names == ("B", "A", "Q", "V")
+    logit = att.max("V").values.log_softmax("A")  # the consumer's first steps (joint.py:473-476)
+    assert logit.names == ("B", "A", "Q")
+    att.rename(None)[0, 0, 0, 0] = 1.0  # writable, not aliased
+    red = gather_logit_reduced_impl(None, {}, vis, txt, None)
+    np.testing.assert_allclose(red.cpu().numpy(), g["reduced"], rtol=1e-4, atol=2e-3)

@@ -1,0 +1,393 @@
+// align_kernels.cu -- word/arc x scene-graph-factor alignment scores on the sm_100a tensor cores.
+//
+// Replaces  gather_logit_simple / gather_logit_reduced   /root/reference/src/model/joint.py:406-432
+//   attmap[b, a, q, v] = < txt[b, q, :], vis[a, v, :] >,  then -INF where vis_mask[a, v] or txt_mask[b, q] is false.
+// The reference runs a cuBLAS fp32 SGEMM plus two full passes of masked_fill_ over the 7.4 GB result; here the
+// contraction, both masks and the store are one kernel, and the result is written exactly once.
+//
+// Mapping onto tcgen05:  D[v][q] = sum_d vis[a, v, d] * txt[b, q, d]
+//   M = 128 factors v of one image a      (operand A, K-major, resident in shared memory for a whole work item)
+//   N = Q queries of one caption b, <= 128 (operand B, K-major, streamed through a ring of shared-memory stages)
+//   K = D <= 128
+// so that TMEM lane = v and TMEM column = q: the 32 threads of an epilogue warp hold 32 consecutive v of one q in
+// the same register, and a store of that register is one coalesced 128-byte row segment of attmap[b, a, q, :].
+//
+// Precision: operands are split on the fly into bf16 hi + bf16 lo (x = hi + lo + O(2^-17 x)) and three MMAs
+// accumulate hi*hi + lo*hi + hi*lo in fp32 TMEM -- fp32-class logits (|err| ~ 1e-5 |x||y| sqrt(D)) from the bf16 pipe.
+//
+// Data movement: a pre-pass (align_pack_kernel) writes both operands as bf16 tiles that are already the 128-byte
+// swizzled shared-memory image tcgen05 expects, so the main kernel moves them with plain 1-D bulk TMA copies
+// (cp.async.bulk ... mbarrier::complete_tx) -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer
+// (+ TMEM allocation), warps 2-5 = epilogue (TMEM -> registers -> masks -> global).  Four TMEM accumulators of 128
+// columns let the MMAs of tile i+1.. overlap the stores of tile i.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "align_kernels.cuh"
+
+namespace vlgae {
+namespace {
+
+constexpr int TILE_M = 128;          // factors per tile (TMEM lanes)
+constexpr int CHUNK_A = TILE_M * 128;  // bytes of one (part, k-block) chunk of operand A: 128 rows x 64 bf16
+constexpr int NACC = 4;              // TMEM accumulators (128 columns each)
+constexpr int kThreads = 192;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp gets lane (quadrant*32 + i), columns c0 .. c0+31
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (dense), sm_100 version
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    const uint32_t lo = ((saddr & 0x3FFFF) >> 4) | (1u << 16);  // start address | LBO = 1 (unused for swizzled K-major)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B | version 1 | SWIZZLE_128B
+    return ((uint64_t)hi << 32) | lo;
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass: fp32 [G][R][D] -> per (g, row tile of 128) bf16 hi / lo chunks in the swizzled smem image
+//   chunk order inside a tile: [hi kb0][hi kb1]..[lo kb0][lo kb1]..; each chunk `rows_per_chunk` rows x 128 B
+//   element (r, k): byte r*128 + (((k%64)/8) ^ (r%8))*16 + (k%8)*2 of chunk k/64
+// also packs a bool mask [G][R] into bit words [G][tiles][4] (bit r%32 of word r/32 inside the tile)
+// ---------------------------------------------------------------------------------------------
+__global__ void align_pack_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, int G, int R, int D,
+                                  int KB, int rows_per_chunk, size_t tile_stride_bytes, int tiles, uint8_t *out,
+                                  uint32_t *maskbits) {
+    // one thread per (g, tile, row, 8-element group): writes one 16-byte unit of hi and of lo
+    const int groups = KB * 8;
+    const size_t total = (size_t)G * tiles * rows_per_chunk * groups;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(t % groups);
+        size_t u = t / groups;
+        const int r = (int)(u % rows_per_chunk); u /= rows_per_chunk;
+        const int tile = (int)(u % tiles);
+        const int g = (int)(u / tiles);
+        const int row = tile * TILE_M + r;
+        const int k0 = grp * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (row < R && k0 + e < D) ? x[((size_t)g * R + row) * D + k0 + e] : 0.f;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * e] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1));
+            hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const int kb = grp >> 3, c = grp & 7;
+        const size_t chunk_bytes = (size_t)rows_per_chunk * 128;
+        uint8_t *tile_base = out + ((size_t)g * tiles + tile) * tile_stride_bytes;
+        const size_t off = (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);
+        *reinterpret_cast<uint4 *>(tile_base + (size_t)kb * chunk_bytes + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(tile_base + (size_t)(KB + kb) * chunk_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (maskbits && grp == 0 && (r & 31) == 0) {
+            uint32_t w = 0;
+            for (int e = 0; e < 32; ++e) {
+                const int rr = row + e;
+                if (rr < R && mask[(size_t)g * R + rr]) w |= 1u << e;
+            }
+            maskbits[((size_t)g * tiles + tile) * 4 + (r >> 5)] = w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct AlignSmem {
+    uint64_t vis_full, vis_empty;
+    uint64_t txt_full[8], txt_empty[8];
+    uint64_t acc_full[NACC], acc_empty[NACC];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // [vis tile: 2*KB chunks of 16 KB][stage 0: 2*KB chunks of nq*128 B] ... [AlignSmem]
+    const int KB = p.KB, nq = p.nq, S = p.stages;
+    const uint32_t vis_bytes = 2u * KB * CHUNK_A;
+    const uint32_t chunk_b = (uint32_t)nq * 128u;
+    const uint32_t stage_bytes = 2u * KB * chunk_b;
+    uint8_t *s_vis = smem;
+    uint8_t *s_txt = smem + vis_bytes;
+    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + vis_bytes + (size_t)S * stage_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&sb->vis_full, 1);
+        mbar_init(&sb->vis_empty, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&sb->txt_full[s], 1); mbar_init(&sb->txt_empty[s], 1); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sb->tmem_base;
+
+    // work items: (a, v-tile, chunk of captions); tiles inside an item: (b, q-tile)
+    const int VT = p.VT, QT = p.QT, BCH = p.BCH;
+    const int n_items = p.A * VT * BCH;
+    const int b_per = (p.B + BCH - 1) / BCH;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it_vis = 0, it_txt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int a = item / (VT * BCH), rem = item - a * VT * BCH;
+                const int vt = rem / BCH, bc = rem - vt * BCH;
+                const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
+                mbar_wait(&sb->vis_empty, (it_vis & 1) ^ 1);
+                mbar_expect_tx(&sb->vis_full, vis_bytes);
+                bulk_g2s(s_vis, p.vis_packed + ((size_t)a * VT + vt) * vis_bytes, vis_bytes, &sb->vis_full);
+                ++it_vis;
+                for (int b = b0; b < b1; ++b)
+                    for (int qt = 0; qt < QT; ++qt) {
+                        const int s = it_txt % S;
+                        mbar_wait(&sb->txt_empty[s], ((it_txt / S) & 1) ^ 1);
+                        mbar_expect_tx(&sb->txt_full[s], stage_bytes);
+                        // the packed caption tile has chunks of 128 rows; copy the first nq rows of each chunk
+                        const uint8_t *src = p.txt_packed + ((size_t)b * QT + qt) * (size_t)(2 * KB * CHUNK_A);
+                        for (int ch = 0; ch < 2 * KB; ++ch)
+                            bulk_g2s(s_txt + (size_t)s * stage_bytes + (size_t)ch * chunk_b, src + (size_t)ch * CHUNK_A,
+                                     chunk_b, &sb->txt_full[s]);
+                        ++it_txt;
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_bf16(TILE_M, nq);
+            uint32_t it_vis = 0, it_txt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int a = item / (VT * BCH), rem = item - a * VT * BCH;
+                const int vt = rem / BCH, bc = rem - vt * BCH;
+                (void)a; (void)vt;
+                const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
+                mbar_wait(&sb->vis_full, it_vis & 1);
+                ++it_vis;
+                const int ntile = (b1 - b0) * QT;
+                for (int t = 0; t < ntile; ++t) {
+                    const int s = it_txt % S, acc = it_txt % NACC;
+                    mbar_wait(&sb->txt_full[s], (it_txt / S) & 1);
+                    mbar_wait(&sb->acc_empty[acc], ((it_txt / NACC) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+                    const uint32_t a_base = smem_u32(s_vis), b_base = smem_u32(s_txt + (size_t)s * stage_bytes);
+                    uint32_t first = 0;
+                    // hi*hi + lo*hi + hi*lo  (parts: 0 = hi, 1 = lo)
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const int pa = term == 1 ? 1 : 0, pb = term == 2 ? 1 : 0;
+                        if (term > 0 && p.split == 1) break;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint64_t ad = smem_desc_sw128(a_base + (uint32_t)(pa * KB + kb) * CHUNK_A);
+                            const uint64_t bd = smem_desc_sw128(b_base + (uint32_t)(pb * KB + kb) * chunk_b);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle atom
+                                tc_mma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first);
+                                first = 1;
+                            }
+                        }
+                    }
+                    tc_commit(&sb->txt_empty[s]);   // stage may be refilled once these MMAs have read it
+                    tc_commit(&sb->acc_full[acc]);  // accumulator ready for the epilogue
+                    ++it_txt;
+                }
+                tc_commit(&sb->vis_empty);  // the image tile may be replaced
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> masks -> global =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        uint32_t it_txt = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int a = item / (VT * BCH), rem = item - a * VT * BCH;
+            const int vt = rem / BCH, bc = rem - vt * BCH;
+            const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
+            const int v = vt * TILE_M + quad * 32 + lane;
+            const bool v_ok = v < p.V;
+            const bool v_keep = v_ok && p.vis_mask[(size_t)a * p.V + v] != 0;
+            for (int b = b0; b < b1; ++b)
+                for (int qt = 0; qt < QT; ++qt) {
+                    const int acc = it_txt % NACC;
+                    mbar_wait(&sb->acc_full[acc], (it_txt / NACC) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + (uint32_t)acc * 128u + ((uint32_t)(quad * 32) << 16);
+                    const uint4 mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + ((size_t)b * QT + qt) * 4);
+                    const uint32_t mw[4] = {mb.x, mb.y, mb.z, mb.w};
+                    const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
+                    float *orow = p.out + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M) * p.V + v;
+                    for (int c0 = 0; c0 < q_lim; c0 += 32) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + (uint32_t)c0, r);
+                        const uint32_t w = mw[c0 >> 5];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j < q_lim && v_ok) {
+                                const bool keep = v_keep && ((w >> j) & 1u);
+                                orow[(size_t)(c0 + j) * p.V] = keep ? __uint_as_float(r[j]) : p.neg;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
+                    ++it_txt;
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_align_sm = 0, g_align_smem = 0;
+static cudaError_t align_device_info() {
+    if (g_align_sm) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_align_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    return cudaDeviceGetAttribute(&g_align_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+}
+
+AlignPlan align_plan(int A, int V, int B, int Q, int D) {
+    AlignPlan pl{};
+    pl.KB = (D + 63) / 64;
+    pl.VT = (V + TILE_M - 1) / TILE_M;
+    pl.QT = (Q + TILE_M - 1) / TILE_M;
+    const int qmax = Q < TILE_M ? Q : TILE_M;
+    pl.nq = (qmax + 15) & ~15;
+    pl.tile_bytes = (size_t)2 * pl.KB * CHUNK_A;
+    pl.vis_packed_bytes = (size_t)A * pl.VT * pl.tile_bytes;
+    pl.txt_packed_bytes = (size_t)B * pl.QT * pl.tile_bytes;
+    pl.maskbits_bytes = (size_t)B * pl.QT * 4 * sizeof(uint32_t);
+    return pl;
+}
+
+size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
+    const AlignPlan pl = align_plan(A, V, B, Q, D);
+    return pl.vis_packed_bytes + pl.txt_packed_bytes + ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
+}
+
+cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                         int V, int B, int Q, int D, float neg, int split, float *out, void *workspace,
+                         cudaStream_t st) {
+    cudaError_t e = align_device_info();
+    if (e != cudaSuccess) return e;
+    const AlignPlan pl = align_plan(A, V, B, Q, D);
+    uint8_t *ws = reinterpret_cast<uint8_t *>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    uint8_t *vis_packed = ws;
+    uint8_t *txt_packed = vis_packed + pl.vis_packed_bytes;
+    uint32_t *maskbits = reinterpret_cast<uint32_t *>(txt_packed + pl.txt_packed_bytes);
+
+    {   // pack both operands (bf16 hi / lo, swizzled tile images)
+        const size_t nv = (size_t)A * pl.VT * TILE_M * pl.KB * 8, nt = (size_t)B * pl.QT * TILE_M * pl.KB * 8;
+        int gv = (int)((nv + 255) / 256), gt = (int)((nt + 255) / 256);
+        const int cap = g_align_sm * 16;
+        if (gv > cap) gv = cap;
+        if (gt > cap) gt = cap;
+        align_pack_kernel<<<gv, 256, 0, st>>>(vis, nullptr, A, V, D, pl.KB, TILE_M, pl.tile_bytes, pl.VT, vis_packed, nullptr);
+        align_pack_kernel<<<gt, 256, 0, st>>>(txt, txt_mask, B, Q, D, pl.KB, TILE_M, pl.tile_bytes, pl.QT, txt_packed, maskbits);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+
+    AlignArgs a{};
+    a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;
+    a.out = out; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
+    a.neg = neg; a.split = split == 1 ? 1 : 3;
+    const size_t vis_bytes = pl.tile_bytes, stage_bytes = (size_t)2 * pl.KB * pl.nq * 128;
+    int stages = (int)(((size_t)g_align_smem - vis_bytes - 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 1) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const size_t smem_bytes = vis_bytes + (size_t)stages * stage_bytes + sizeof(AlignSmem) + 64;
+    // enough work items for ~4 waves of persistent CTAs: split the captions of one (image, v-tile) into chunks
+    int bch = 1;
+    while ((long long)A * pl.VT * bch < 4LL * g_align_sm && bch < B) bch <<= 1;
+    if (bch > B) bch = B;
+    a.BCH = bch;
+    e = cudaFuncSetAttribute(align_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    int grid = g_align_sm;
+    if (grid > A * pl.VT * bch) grid = A * pl.VT * bch;
+    align_gemm_kernel<<<grid, kThreads, smem_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace vlgae

@@ -1,0 +1,33 @@
+// align_kernels.cuh -- internal interface between the C ABI (c_api.cu) and the alignment kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vlgae {
+
+struct AlignArgs {
+    const uint8_t *vis_packed;     // [A][VT][2*KB chunks of 128 rows x 128 B]   bf16 hi / lo, swizzled tile images
+    const uint8_t *txt_packed;     // [B][QT][2*KB chunks of 128 rows x 128 B]
+    const uint32_t *txt_maskbits;  // [B][QT][4]
+    const uint8_t *vis_mask;       // [A][V] bool
+    float *out;                    // [B][A][Q][V]
+    int A, V, B, Q;
+    int KB, VT, QT, nq;  // k-blocks of 64, v-tiles, q-tiles, padded queries per tile (multiple of 16, <= 128)
+    int BCH, stages, split;
+    float neg;
+};
+
+struct AlignPlan {
+    int KB, VT, QT, nq;
+    size_t tile_bytes, vis_packed_bytes, txt_packed_bytes, maskbits_bytes;
+};
+
+AlignPlan align_plan(int A, int V, int B, int Q, int D);
+size_t align_workspace_bytes(int A, int V, int B, int Q, int D);
+// split = 3: bf16 hi/lo split, three MMAs per product (fp32-class); split = 1: single bf16 MMA
+cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                         int V, int B, int Q, int D, float neg, int split, float *out, void *workspace,
+                         cudaStream_t st);
+
+}  // namespace vlgae

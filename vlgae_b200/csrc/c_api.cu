@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "../../include/vlgae_b200.h"
+#include "align_kernels.cuh"
 #include "dmv_kernels.cuh"
 
 namespace {
@@ -165,6 +166,26 @@ int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float
     if (B <= 0 || inner == 0) return VLGAE_OK;
     cudaError_t e = vlgae::launch_scale_rows(in, g, B, inner, out, (cudaStream_t)stream);
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "scale_rows launch");
+}
+
+size_t vlgae_align_workspace_bytes(int A, int V, int B, int Q, int D) {
+    if (A <= 0 || V <= 0 || B <= 0 || Q <= 0 || D <= 0 || D > VLGAE_ALIGN_MAX_D) return 0;
+    return vlgae::align_workspace_bytes(A, V, B, Q, D);
+}
+
+int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                       const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
+                       float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!vis_feat || !vis_mask || !txt_feat || !txt_mask || !out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (A < 0 || V < 0 || B < 0 || Q < 0) return fail(VLGAE_E_INVALID, "%s", "negative extent");
+    if (D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "D must be in [1, 128]");
+    if (split != 1 && split != 3) return fail(VLGAE_E_INVALID, "%s", "split must be 1 or 3");
+    if (A == 0 || V == 0 || B == 0 || Q == 0) return VLGAE_OK;
+    const size_t need = vlgae::align_workspace_bytes(A, V, B, Q, D);
+    if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "alignment workspace too small");
+    cudaError_t e = vlgae::launch_align(vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D, neg_fill, split, out,
+                                        workspace, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align launch");
 }
 
 static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
