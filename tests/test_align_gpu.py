@@ -18,10 +18,11 @@ def _t(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
 
-def run(vis, vm, txt, tm, dev, split=3):
+def run(vis, vm, txt, tm, dev, split=3, pad_rows=True):
     from vlgae_b200.alignment import gather_logit_simple
 
-    out = gather_logit_simple(_t(vis, dev), _t(vm, dev), _t(txt, dev), _t(tm, dev), split=split)
+    out = gather_logit_simple(_t(vis, dev), _t(vm, dev), _t(txt, dev), _t(tm, dev), split=split, pad_rows=pad_rows)
+    assert out.is_contiguous() or pad_rows
     torch.cuda.synchronize()
     assert out.names == ("B", "A", "Q", "V")
     return out.rename(None).cpu().numpy()
@@ -59,6 +60,8 @@ def test_shapes_against_oracle(dev, A, V, B, Q, D):
     tm = rng.random((B, Q)) > 0.2
     want = oracle.gather_logit_simple(vis, vm, txt, tm)
     got = run(vis, vm, txt, tm, dev)
+    check(got, want, vis, txt, 3)
+    got = run(vis, vm, txt, tm, dev, pad_rows=False)
     check(got, want, vis, txt, 3)
 
 

@@ -26,18 +26,18 @@ vm = torch.rand(args.A, args.V, generator=g, device=dev) > 0.1
 tm = torch.rand(args.B, args.Q, generator=g, device=dev) > 0.1
 out_bytes = args.A * args.B * args.Q * args.V * 4
 flops = 2.0 * args.A * args.B * args.Q * args.V * args.D
-for split in (3, 1):
+for split, pad in ((3, True), (3, False), (1, True)):
     for _ in range(2):
-        out = gather_logit_simple(vis, vm, txt, tm, split=split, named=False)
+        out = gather_logit_simple(vis, vm, txt, tm, split=split, named=False, pad_rows=pad)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.iters):
-        out = gather_logit_simple(vis, vm, txt, tm, split=split, named=False)
+        out = gather_logit_simple(vis, vm, txt, tm, split=split, named=False, pad_rows=pad)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
-    print(f"split={split}: {ms:.3f} ms  {out_bytes / ms / 1e6:.0f} GB/s written  {flops * (3 if split == 3 else 1) / ms / 1e9:.0f} "
+    print(f"split={split} pad_rows={pad}: {ms:.3f} ms  {out_bytes / ms / 1e6:.0f} GB/s written  {flops * (3 if split == 3 else 1) / ms / 1e9:.0f} "
           f"TFLOP/s issued (bf16)  [{args.B}x{args.A}x{args.Q}x{args.V}, out {out_bytes / 2**30:.2f} GiB]")
 # reference arithmetic for context: fp32 einsum + 2 masked fills (what joint.py:413-418 runs on the GPU)
 torch.backends.cuda.matmul.allow_tf32 = False

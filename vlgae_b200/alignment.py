@@ -36,8 +36,14 @@ def _workspace(dev, nbytes):
     return ws
 
 
-def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=-INF, named=True):
-    """attmap [B, A, Q, V] = <txt[b,q,:], vis[a,v,:]> with both masks applied (joint.py:406-419)."""
+def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=-INF, named=True, pad_rows=True):
+    """attmap [B, A, Q, V] = <txt[b,q,:], vis[a,v,:]> with both masks applied (joint.py:406-419).
+
+    pad_rows: allocate rows of ``ceil(V / 8) * 8`` floats and return the ``[..., :V]`` view (same shape, dtype and
+    values; last-dim stride 1, not contiguous).  Every consumer in joint.py indexes / reduces / sorts, none calls
+    ``.view``; sector-aligned rows roughly halve the time of this write-bound operator.  ``pad_rows=False`` gives the
+    reference's dense layout.
+    """
     vis_feat, vis_mask, txt_feat, txt_mask = map(_plain, (vis_feat, vis_mask, txt_feat, txt_mask))
     dev = vis_feat.device
     if dev.type != "cuda":
@@ -50,15 +56,18 @@ def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=
     tf = txt_feat.detach().to(torch.float32).contiguous()
     vm = vis_mask.to(torch.bool).contiguous().view(torch.uint8)
     tm = txt_mask.to(torch.bool).contiguous().view(torch.uint8)
-    out = torch.empty((B, A, Q, V), dtype=torch.float32, device=dev)
+    ldv = (V + 7) // 8 * 8 if pad_rows else V
+    out = torch.empty((B, A, Q, ldv), dtype=torch.float32, device=dev)
     need = lib().vlgae_align_workspace_bytes(A, V, B, Q, D)
     if need == 0 and out.numel() > 0:
         raise VlgaeError(f"gather_logit: unsupported shape (D = {D} > 128?)")
     ws = _workspace(dev, max(need, 1))
     with torch.cuda.device(dev):
         check(lib().vlgae_align_logits(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D,
-                                       float(neg), int(split), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       float(neg), int(split), out.data_ptr(), ldv, ws.data_ptr(), ws.numel(),
                                        torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits")
+    if ldv != V:
+        out = out[..., :V]
     if named:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

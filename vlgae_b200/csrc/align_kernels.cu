@@ -18,11 +18,12 @@
 // Data movement: a pre-pass (align_pack_kernel) writes both operands as bf16 tiles that are already the 128-byte
 // swizzled shared-memory image tcgen05 expects, so the main kernel moves them with plain 1-D bulk TMA copies
 // (cp.async.bulk ... mbarrier::complete_tx) -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer
-// (+ TMEM allocation), warps 2-5 = epilogue (TMEM -> registers -> masks -> global).  Four TMEM accumulators of 128
+// (+ TMEM allocation), warps 2-9 = epilogue (TMEM -> registers -> masks -> global).  Four TMEM accumulators of 128
 // columns let the MMAs of tile i+1.. overlap the stores of tile i.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "align_kernels.cuh"
 
@@ -32,7 +33,8 @@ namespace {
 constexpr int TILE_M = 128;          // factors per tile (TMEM lanes)
 constexpr int CHUNK_A = TILE_M * 128;  // bytes of one (part, k-block) chunk of operand A: 128 rows x 64 bf16
 constexpr int NACC = 4;              // TMEM accumulators (128 columns each)
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each takes every other 16-column chunk
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -85,6 +87,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         mbar_init(&sb->vis_full, 1);
         mbar_init(&sb->vis_empty, 1);
         for (int s = 0; s < S; ++s) { mbar_init(&sb->txt_full[s], 1); mbar_init(&sb->txt_empty[s], 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], 4); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
@@ -263,7 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> masks -> global =====================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;   // which of the two warps of the quadrant
         uint32_t it_txt = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int a = item / (VT * BCH), rem = item - a * VT * BCH;
@@ -272,33 +286,45 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
             const int v = vt * TILE_M + quad * 32 + lane;
             const bool v_ok = v < p.V;
             const bool v_keep = v_ok && p.vis_mask[(size_t)a * p.V + v] != 0;
-            for (int b = b0; b < b1; ++b)
-                for (int qt = 0; qt < QT; ++qt) {
-                    const int acc = it_txt % NACC;
-                    mbar_wait(&sb->acc_full[acc], (it_txt / NACC) & 1);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + (uint32_t)acc * 128u + ((uint32_t)(quad * 32) << 16);
-                    const uint4 mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + ((size_t)b * QT + qt) * 4);
-                    const uint32_t mw[4] = {mb.x, mb.y, mb.z, mb.w};
-                    const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
-                    float *orow = p.out + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M) * p.V + v;
-                    for (int c0 = 0; c0 < q_lim; c0 += 32) {
-                        uint32_t r[32];
-                        tc_ld32(taddr + (uint32_t)c0, r);
-                        const uint32_t w = mw[c0 >> 5];
+            const uint32_t V = (uint32_t)p.ldv;  // row stride of the output (>= V; a multiple of 8 keeps stores sector-aligned)
+            const int ntile = (b1 - b0) * QT;
+            // caption mask bits of the next tile are fetched while the current one is stored
+            uint4 mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + (size_t)b0 * QT * 4);
+            for (int t = 0; t < ntile; ++t) {
+                const int b = b0 + t / QT, qt = t - (t / QT) * QT;
+                const uint4 mb_cur = mb;
+                if (t + 1 < ntile) mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + ((size_t)b0 * QT + t + 1) * 4);
+                const int acc = it_txt % NACC;
+                mbar_wait(&sb->acc_full[acc], (it_txt / NACC) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t)acc * 128u + ((uint32_t)(quad * 32) << 16);
+                const uint32_t mw[4] = {mb_cur.x, mb_cur.y, mb_cur.z, mb_cur.w};
+                const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
+                float *orow = p.out + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M) * p.ldv + v;
+                for (int c0 = half * 16; c0 < q_lim; c0 += 32) {
+                    uint32_t r[16];
+                    if (!(p.debug & 2)) tc_ld16(taddr + (uint32_t)c0, r);
+                    else { for (int j = 0; j < 16; ++j) r[j] = 0; }
+                    // bit j set = keep the score of query c0 + j for this factor; a masked factor clears them all
+                    const uint32_t w = v_keep ? (mw[c0 >> 5] >> (c0 & 31)) : 0u;
+                    float *o = orow + (size_t)c0 * V;
+                    if (v_ok && !(p.debug & 1)) {
+                        if (c0 + 16 <= q_lim) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (c0 + j < q_lim && v_ok) {
-                                const bool keep = v_keep && ((w >> j) & 1u);
-                                orow[(size_t)(c0 + j) * p.V] = keep ? __uint_as_float(r[j]) : p.neg;
-                            }
+                            for (int j = 0; j < 16; ++j)  // streaming stores: the result is written exactly once
+                                __stcs(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : p.neg);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < q_lim) __stcs(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : p.neg);
                         }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
-                    ++it_txt;
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
+                ++it_txt;
+            }
         }
     }
     tc_fence_before();
@@ -345,7 +371,7 @@ size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
 }
 
 cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
-                         int V, int B, int Q, int D, float neg, int split, float *out, void *workspace,
+                         int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
                          cudaStream_t st) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
@@ -369,8 +395,9 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
 
     AlignArgs a{};
     a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;
-    a.out = out; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
+    a.out = out; a.ldv = ldv; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.neg = neg; a.split = split == 1 ? 1 : 3;
+    { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     const size_t vis_bytes = pl.tile_bytes, stage_bytes = (size_t)2 * pl.KB * pl.nq * 128;
     int stages = (int)(((size_t)g_align_smem - vis_bytes - 1024) / stage_bytes);
     if (stages > 8) stages = 8;

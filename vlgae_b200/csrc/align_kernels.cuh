@@ -11,10 +11,11 @@ struct AlignArgs {
     const uint8_t *txt_packed;     // [B][QT][2*KB chunks of 128 rows x 128 B]
     const uint32_t *txt_maskbits;  // [B][QT][4]
     const uint8_t *vis_mask;       // [A][V] bool
-    float *out;                    // [B][A][Q][V]
+    float *out;                    // [B][A][Q][ldv], ldv >= V
+    int ldv;
     int A, V, B, Q;
     int KB, VT, QT, nq;  // k-blocks of 64, v-tiles, q-tiles, padded queries per tile (multiple of 16, <= 128)
-    int BCH, stages, split;
+    int BCH, stages, split, debug;
     float neg;
 };
 
@@ -27,7 +28,7 @@ AlignPlan align_plan(int A, int V, int B, int Q, int D);
 size_t align_workspace_bytes(int A, int V, int B, int Q, int D);
 // split = 3: bf16 hi/lo split, three MMAs per product (fp32-class); split = 1: single bf16 MMA
 cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
-                         int V, int B, int Q, int D, float neg, int split, float *out, void *workspace,
+                         int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
                          cudaStream_t st);
 
 }  // namespace vlgae

@@ -175,16 +175,17 @@ size_t vlgae_align_workspace_bytes(int A, int V, int B, int Q, int D) {
 
 int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
                        const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
-                       float *out, void *workspace, size_t workspace_bytes, void *stream) {
+                       float *out, int out_row_stride, void *workspace, size_t workspace_bytes, void *stream) {
     if (!vis_feat || !vis_mask || !txt_feat || !txt_mask || !out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
     if (A < 0 || V < 0 || B < 0 || Q < 0) return fail(VLGAE_E_INVALID, "%s", "negative extent");
     if (D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "D must be in [1, 128]");
     if (split != 1 && split != 3) return fail(VLGAE_E_INVALID, "%s", "split must be 1 or 3");
+    if (out_row_stride < V) return fail(VLGAE_E_INVALID, "%s", "out_row_stride must be >= V");
     if (A == 0 || V == 0 || B == 0 || Q == 0) return VLGAE_OK;
     const size_t need = vlgae::align_workspace_bytes(A, V, B, Q, D);
     if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "alignment workspace too small");
     cudaError_t e = vlgae::launch_align(vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D, neg_fill, split, out,
-                                        workspace, (cudaStream_t)stream);
+                                        out_row_stride, workspace, (cudaStream_t)stream);
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align launch");
 }
 
