@@ -212,6 +212,62 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# alignment leg (second kernel of the hot path; reported beside the headline, not part of `value`)
+# ----------------------------------------------------------------------------------------------------------
+def alignment_leg(dev, iters=10):
+    """gather_logit_simple at the cfg2 shape: A = B = 128 images/captions, Q = 2 * 41 queries, V = 36 + 36^2 + 36 + 1
+    = 1369 factors, D = 128.  HBM-write-bound: 4 * B * A * Q * V bytes must be written once."""
+    import torch
+
+    import oracle
+    from vlgae_b200.alignment import gather_logit_simple
+
+    A = B = BATCH_PER_GPU
+    Q, V, D = 2 * (MAX_LEN + 1), 36 + 36 * 36 + 36 + 1, 128
+    g = torch.Generator(device=dev).manual_seed(99)
+    vis = torch.randn(A, V, D, generator=g, device=dev)
+    txt = torch.randn(B, Q, D, generator=g, device=dev)
+    vm = torch.rand(A, V, generator=g, device=dev) > 0.1
+    tm = torch.rand(B, Q, generator=g, device=dev) > 0.1
+    out = None
+    for _ in range(2):
+        out = gather_logit_simple(vis, vm, txt, tm, named=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = gather_logit_simple(vis, vm, txt, tm, named=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    # parity on a corner block against the oracle (numpy fp32 restatement of joint.py:406-419)
+    nb, na = 2, 3
+    want = oracle.gather_logit_simple(vis[:na].cpu().numpy(), vm[:na].cpu().numpy(), txt[:nb].cpu().numpy(),
+                                      tm[:nb].cpu().numpy())
+    got = out[:nb, :na].cpu().numpy()
+    masked = want == -1e20
+    err = float(np.abs(got - want)[~masked].max())
+    peak = None
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:  # noqa: BLE001
+        peak, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    out_bytes = 4.0 * B * A * Q * V
+    gbs = out_bytes / (ms * 1e-3) / 1e9
+    return {
+        "workload": f"gather_logit_simple A={A} V={V} B={B} Q={Q} D={D} (cfg2), bf16 hi/lo split x3 on tcgen05, "
+                    "rows padded to 8 floats", "ms": ms, "captions_per_s": B / (ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                     "traffic": None, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
+                     "kernel": "align_gemm_kernel (+ align_pack_kernel x2)"},
+        "tensor_tflops_issued": 3 * 2.0 * A * B * Q * V * D / (ms * 1e-3) / 1e12,
+        "parity": {"mask_pattern_equal": bool(((got == -1e20) == masked).all()), "max_abs_err_vs_fp32_oracle": err},
+        "gpu_launches_per_call": 3,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
@@ -349,6 +405,13 @@ def run_b200_arm(args):
     h2d = md0.nbytes + ma0.nbytes + L0.nbytes
     d2h = h_Z.numel() * 4 + h_best.numel() * 4 + h_gatt.numel() * 4 + h_gdec.numel() * 4 + h_heads.numel() * 8
 
+    # ---- alignment kernel, reported separately (rank 0 only) ----
+    align = None
+    if rank == 0 and not args.no_align:
+        del pool, pmd, pma
+        torch.cuda.empty_cache()
+        align = alignment_leg(dev)
+
     # ---- max over ranks ----
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -387,6 +450,8 @@ def run_b200_arm(args):
         }
         if cb is not None:
             line["cpu_baseline"] = cb
+        if align is not None:
+            line["alignment"] = align
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -399,6 +464,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-align", action="store_true", help="skip the alignment-kernel leg")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 200:

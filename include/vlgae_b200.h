@@ -132,6 +132,20 @@ int vlgae_dmv_merge(const float *dec, const float *attach, const float *root, in
                     float *dec_w, float *attach_w, void *stream);
 
 /*
+ * Arc-factored projective dependency CRF (MBR decoding).
+ * Replaces  DependencyCRF(arc, lengths).partition / .max / .marginals / .argmax
+ *           src/model/torch_struct/distributions.py:269-299 -> deptree.py:25-76,146-162 (+ helpers.py:118-154)
+ *   arc [B][N][N] (head, child); positions beyond lengths[b] are treated as `fill` (deptree.py:159-161; the
+ *   reference's run-time global NEGINF); mask_zero = value of the single-root mask (class attr zero, deptree.py:72-73).
+ *   semiring 0 = log: out[b] = log Z, marginals = arc marginals;  1 = max: out[b] = best score, marginals = 0/1
+ *   indicator of the best tree (torch.max first-index tie rule), heads[b][c] = head of word c (0 elsewhere).
+ *   marginals / heads may be NULL (then only the forward sweep runs).
+ */
+size_t vlgae_deptree_workspace_bytes(int B, int N);
+int vlgae_deptree(const float *arc, const int64_t *lengths, int B, int N, float fill, float mask_zero, int semiring,
+                  float *out, float *marginals, int64_t *heads, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Alignment scores (word / arc queries x scene-graph factors).
  * Replaces  gather_logit_simple   src/model/joint.py:406-419:
  *   out[b][a][q][v] = sum_d txt_feat[b][q][d] * vis_feat[a][v][d];  neg_fill where !vis_mask[a][v] or !txt_mask[b][q]

@@ -278,3 +278,30 @@ def test_host_buffer_entry_point(dev):
     np.testing.assert_allclose(gatt, ogatt, atol=MARG_ATOL)
     np.testing.assert_array_equal(best, obest)
     np.testing.assert_array_equal(heads, oheads)
+
+
+@pytest.mark.parametrize("name", ["deptree_rand", "deptree_mbr", "deptree_ties"])
+def test_dependency_crf_golden(golden, dev, name):
+    """DependencyCRF (MBR decoding path, ldndmv.py:294-299) against the reference's golden vectors."""
+    import vlgae_b200.torch_struct as ts
+    from vlgae_b200.torch_struct import DependencyCRF
+
+    g = golden(name)
+    old = ts.semirings.semirings.NEGINF
+    ts.semirings.semirings.NEGINF = -1e20  # what src.setup_inf(1e20) does in the reference
+    try:
+        arc, L = _t(g["arc"], dev), _t(g["lengths"], dev)
+        d = DependencyCRF(arc, L)
+        assert d.partition.shape == (len(L),)
+        np.testing.assert_allclose(d.partition.cpu().numpy(), g["partition"], rtol=1e-4)
+        np.testing.assert_allclose(d.marginals.cpu().numpy(), g["marginals"], atol=3e-5)
+        np.testing.assert_array_equal(d.max.cpu().numpy(), g["max"])
+        np.testing.assert_array_equal(d.argmax.cpu().numpy().astype(np.int8), g["argmax"])
+        # the caller's decode (ldndmv.py:296-299)
+        a = d.argmax.nonzero()
+        predicted = L.new_zeros(len(L), arc.shape[1] - 1)
+        predicted[a[:, 0], a[:, 2] - 1] = a[:, 1]
+        _, _, oheads = oracle.deptree(g["arc"], g["lengths"], semiring="max", fill=-1e20)
+        np.testing.assert_array_equal(predicted.cpu().numpy(), oheads[:, 1:])
+    finally:
+        ts.semirings.semirings.NEGINF = old

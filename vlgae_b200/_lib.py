@@ -30,6 +30,9 @@ PROTOTYPES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlgae_dmv_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                 c_void_p]),
+    "vlgae_deptree_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vlgae_deptree": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_void_p]),
     "vlgae_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vlgae_align_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

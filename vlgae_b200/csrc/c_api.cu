@@ -5,6 +5,7 @@
 
 #include "../../include/vlgae_b200.h"
 #include "align_kernels.cuh"
+#include "deptree_kernels.cuh"
 #include "dmv_kernels.cuh"
 
 namespace {
@@ -166,6 +167,26 @@ int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float
     if (B <= 0 || inner == 0) return VLGAE_OK;
     cudaError_t e = vlgae::launch_scale_rows(in, g, B, inner, out, (cudaStream_t)stream);
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "scale_rows launch");
+}
+
+size_t vlgae_deptree_workspace_bytes(int B, int N) {
+    if (B <= 0 || N < 1 || N > VLGAE_DMV_MAX_N) return 0;
+    return (size_t)B * vlgae::deptree_ws_stride(N);
+}
+
+int vlgae_deptree(const float *arc, const int64_t *lengths, int B, int N, float fill, float mask_zero, int semiring,
+                  float *out, float *marginals, int64_t *heads, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!arc || !lengths || !out) return fail(VLGAE_E_INVALID, "%s", "arc, lengths and out must be non-null");
+    if (B < 0 || N < 1 || N > VLGAE_DMV_MAX_N) return fail(VLGAE_E_INVALID, "%s", "bad B or N");
+    if (semiring != 0 && semiring != 1) return fail(VLGAE_E_INVALID, "%s", "semiring must be 0 (log) or 1 (max)");
+    if (B == 0) return VLGAE_OK;
+    if (!workspace || workspace_bytes < vlgae_deptree_workspace_bytes(B, N))
+        return fail(VLGAE_E_WORKSPACE, "%s", "deptree workspace too small");
+    vlgae::DepTreeArgs a;
+    a.arc = arc; a.lengths = lengths; a.B = B; a.N = N; a.fill = fill; a.mask_zero = mask_zero;
+    a.out = out; a.marg = marginals; a.heads = heads; a.workspace = workspace; a.ws_stride = vlgae::deptree_ws_stride(N);
+    cudaError_t e = vlgae::launch_deptree(a, semiring, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "deptree launch");
 }
 
 size_t vlgae_align_workspace_bytes(int A, int V, int B, int Q, int D) {
