@@ -13,7 +13,7 @@ from vlgae_b200 import ops  # noqa: E402
 from vlgae_b200._lib import check, lib  # noqa: E402
 
 dev = torch.device("cuda:0")
-for B, n, ragged in [(128, 40, "cfg2"), (1, 40, None), (128, 16, None)]:
+for B, n, ragged in [(128, 40, "cfg2"), (1, 40, None), (128, 16, None), (1, 8, None), (512, 8, None), (1184, 11, None)]:
     md, ma, L = synth(B, n, 7, ragged)
     tmd, tma, tL = [torch.from_numpy(x).to(dev) for x in (md, ma, L)]
     out = ops.ParseBuffers(B, n + 1, dev)

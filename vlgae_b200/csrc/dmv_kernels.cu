@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
     float *sdec = reinterpret_cast<float *>(smem_raw);
     void *mem;
     if (SMEM)
-        mem = smem_raw + (((size_t)p.N * 8 * sizeof(float) + 15) & ~(size_t)15);
+        mem = smem_raw + (((size_t)p.smem_n * 8 * sizeof(float) + 15) & ~(size_t)15);
     else
         mem = reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride;
     const int total = p.B * p.npass;
@@ -709,6 +709,11 @@ __global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }
+        {   // length buckets: a launch whose shared memory is sized for nb_hi positions skips the other sentences
+            int len = (int)p.lengths[b];
+            len = len < 0 ? 0 : (len > p.N - 1 ? p.N - 1 : len);
+            if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
+        }
         if (which == 0) log_pass<NT>(p, b, mem, sdec);
         else max_pass<NT>(p, b, mem, sdec);
     }
@@ -823,12 +828,14 @@ int dmv_grid_for_workspace(int B) {
 }
 
 template <int NT>
-static cudaError_t launch_nt(DmvArgs a, int passes, cudaStream_t st) {
+static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
+    // `cap` = chart positions this launch is sized for (a.N, or the upper end of a length bucket)
     cudaError_t e = device_info();
     if (e != cudaSuccess) return e;
-    const size_t chart = dmv_chart_bytes(a.N, passes);
-    const size_t smem_need = dec_bytes(a.N) + chart;
+    const size_t chart = dmv_chart_bytes(cap, passes);
+    const size_t smem_need = dec_bytes(cap) + chart;
     const int total = a.B * a.npass;
+    a.smem_n = cap;
     if (smem_need <= (size_t)g_smem_optin) {
         auto k = dmv_kernel<NT, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need);
@@ -844,10 +851,17 @@ static cudaError_t launch_nt(DmvArgs a, int passes, cudaStream_t st) {
         auto k = dmv_kernel<NT, false>;
         int grid = dmv_grid_for_workspace(a.B);
         if (grid > total) grid = total;
-        a.ws_stride = chart;
-        k<<<grid, NT, dec_bytes(a.N), st>>>(a);
+        a.ws_stride = dmv_chart_bytes(a.N, passes);
+        k<<<grid, NT, dec_bytes(cap), st>>>(a);
     }
     return cudaGetLastError();
+}
+
+static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads, cudaStream_t st) {
+    if (threads <= 0) threads = cap <= 33 ? 96 : (cap <= 65 ? 192 : 384);
+    if (threads <= 96) return launch_nt<96>(a, passes, cap, st);
+    if (threads <= 192) return launch_nt<192>(a, passes, cap, st);
+    return launch_nt<384>(a, passes, cap, st);
 }
 
 static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
@@ -874,10 +888,29 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     // split points per lane before a span is shared between lanes (power of two)
     if (a.tpl <= 0) a.tpl = g_tune_tpl > 0 ? g_tune_tpl : 4;
     // CTA = 3 roles x LPR lanes; LPR >= the number of spans of the shortest width keeps every width to one round
-    if (a.threads <= 0) a.threads = env_threads > 0 ? env_threads : (a.N <= 33 ? 96 : (a.N <= 65 ? 192 : 384));
-    if (a.threads <= 96) return launch_nt<96>(a, passes, st);
-    if (a.threads <= 192) return launch_nt<192>(a, passes, st);
-    return launch_nt<384>(a, passes, st);
+    const int threads = a.threads > 0 ? a.threads : env_threads;
+    a.nb_lo = 0; a.nb_hi = a.N;
+    // Throughput regime (more work items than one resident wave at the padded length): one launch per length bucket,
+    // shared memory sized for the bucket, so short sentences run at 10-20 CTAs per SM instead of the 3 a 40-word
+    // chart allows.  Sentences outside a launch's bucket are skipped by its CTAs (no host knowledge of the lengths,
+    // no sorting assumption).  Longest bucket first.
+    static const int env_bucket = env_int("VLGAE_DMV_BUCKETS", 1);
+    const size_t full_need = dec_bytes(a.N) + dmv_chart_bytes(a.N, passes);
+    const int occ_full = full_need <= (size_t)g_smem_optin ? (int)((size_t)g_smem_optin / full_need) : 2;
+    const bool bulk = env_bucket && (long long)a.B * a.npass > 2LL * g_sm_count * (occ_full < 1 ? 1 : occ_full);
+    if (!bulk) return launch_cap(a, passes, a.N, threads, st);
+    static const int caps[] = {8, 12, 16, 20, 24, 28, 33, 41, 49, 65, 97, 129, 256};
+    int nb = 0, bounds[16];
+    for (int c : caps) if (c < a.N) bounds[nb++] = c;
+    bounds[nb++] = a.N;
+    for (int k = nb - 1; k >= 0; --k) {
+        DmvArgs bkt = a;
+        bkt.nb_hi = bounds[k];
+        bkt.nb_lo = k > 0 ? bounds[k - 1] + 1 : 0;
+        e = launch_cap(bkt, passes, bounds[k], threads, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,

@@ -29,6 +29,8 @@ struct DmvArgs {
     int npass;         // 1: only `first_pass`; 2: log and max CTAs interleaved
     int first_pass;    // 0 = log, 1 = max
     int nsm;           // SM count (work-item placement)
+    int nb_lo, nb_hi;  // this launch handles sentences with nb_lo <= len + 1 <= nb_hi (length buckets)
+    int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
     int gmax;          // max lanes per span (1, 2, 4, 8); 0 = choose from the batch size
     int threads;       // CTA size (96, 192, 384); 0 = choose from N
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
