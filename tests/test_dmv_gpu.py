@@ -234,7 +234,7 @@ def test_cfg3_sweep_small(dev):
 
 
 @pytest.mark.parametrize("gmax,threads,tpl", [(1, 96, 8), (1, 192, 1), (2, 192, 4), (8, 192, 2), (32, 192, 1),
-                                              (4, 384, 8), (32, 96, 2), (32, 192, 32)])
+                                              (4, 384, 8), (32, 768, 2), (32, 192, 32)])
 def test_launch_tuning_does_not_change_results(dev, gmax, threads, tpl):
     from vlgae_b200._lib import check, lib
 

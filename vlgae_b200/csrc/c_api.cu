@@ -53,8 +53,8 @@ int vlgae_dmv_set_profile_buffer(void *device_buf) {
 }
 int vlgae_dmv_set_tuning(int gmax, int threads, int tpl) {
     if ((gmax != 0 && gmax != 1 && gmax != 2 && gmax != 4 && gmax != 8 && gmax != 16 && gmax != 32) ||
-        (threads != 0 && threads != 96 && threads != 192 && threads != 384))
-        return fail(VLGAE_E_INVALID, "%s", "gmax must be 0/1/2/4/8/16/32 and threads 0/96/192/384");
+        (threads != 0 && threads != 96 && threads != 192 && threads != 384 && threads != 768))
+        return fail(VLGAE_E_INVALID, "%s", "gmax must be 0/1/2/4/8/16/32 and threads 0/96/192/384/768");
     if (tpl < 0 || tpl > 32 || (tpl & (tpl - 1))) return fail(VLGAE_E_INVALID, "%s", "tpl must be 0 or a power of two <= 32");
     vlgae::dmv_set_tuning(gmax, threads, tpl);
     return VLGAE_OK;

@@ -39,6 +39,10 @@ constexpr float NEG_BIG = -3.0e38f;  // finite stand-in for -inf (no NaN from (-
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr int KCH = 4;  // split points per lane per chunk of the streaming logsumexp
+constexpr int OB = 4;   // split points per lane per batch of the reverse sweep (batched variant)
+// Batching the read-modify-writes of the reverse sweep (all loads, then math, then stores) was measured SLOWER on B200
+// (cfg2: 111 us vs 78 us) -- the extra live registers cost more than the exposed LDS latency; kept for reference.
+constexpr bool kBatchOutside = false;
 
 // exp / log on the MUFU pipe: one FMUL + MUFU.EX2 / MUFU.LG2 + FMUL (flush-to-zero variants: no denormal fix-up code)
 __device__ __forceinline__ float fexp(float x) {
@@ -170,31 +174,58 @@ struct LogChart {
 __device__ __forceinline__ float2 &lo2(float4 &v) { return *reinterpret_cast<float2 *>(&v.x); }
 __device__ __forceinline__ float2 &hi2(float4 &v) { return *reinterpret_cast<float2 *>(&v.z); }
 
-// per-width geometry of one thread inside its role (t = lane index inside the role, LPR = lanes per role)
-struct Geo {
-    int g, lg, sub, ncell, cpr_log2, nrounds, first_cell;
-    __device__ __forceinline__ Geo(int w, int Nb, int t, int lpr_log2, int gmax_log2, int tpl_log2) {
-        ncell = Nb - w;
-        lg = lanes_log2(ncell, w, lpr_log2, gmax_log2, tpl_log2);
-        g = 1 << lg;
-        sub = t & (g - 1);
-        first_cell = t >> lg;
-        cpr_log2 = lpr_log2 - lg;
-        nrounds = (ncell + (1 << cpr_log2) - 1) >> cpr_log2;
+// Per-lane geometry of a role, carried from one width to the next.  For a fixed number of lanes per span the span
+// (i, i + w) a lane works on, its first split point and the forward operand stream do not depend on w, and the backward
+// stream / the span's own cell move by first differences of the triangular index -- three integer adds per width
+// instead of re-deriving everything (the closed forms are evaluated only when the lanes-per-span changes).
+// Every role has at least as many lanes as the shortest width has spans (LPR >= N - 1), so a width is one round.
+struct Walk {
+    int lg, rbeg, own, i1, st1, i2, st2;
+    template <int ROLE, bool SKIP_OWN>
+    __device__ __forceinline__ void reset(int w, int t, int lg_, int Nb) {
+        lg = lg_;
+        const int g = 1 << lg, sub = t & (g - 1), i = t >> lg;
+        rbeg = (SKIP_OWN && ROLE == 1 && sub == 0) ? g : sub;
+        own = cidx(i, w, Nb);
+        const int d1 = ROLE == 2 ? rbeg + 1 : rbeg;           // forward stream: cells (i, d1 + k g)
+        i1 = cidx(i, d1, Nb);
+        st1 = g * Nb - g * d1 - ((g * (g - 1)) >> 1);
+        const int lo2 = ROLE == 1 ? i + rbeg : i + rbeg + 1;  // backward stream: cells (lo2 + k g, d2 - k g)
+        const int d2 = ROLE == 1 ? w - rbeg : w - 1 - rbeg;
+        i2 = cidx(lo2, d2, Nb);
+        st2 = -g * Nb + g * d2 - ((g * (g + 1)) >> 1) + g;
+    }
+    template <int ROLE>
+    __device__ __forceinline__ void up(int w, int Nb) {  // w -> w + 1
+        own += Nb - w;                                   // D(w + 1) - D(w)
+        const int d2 = ROLE == 1 ? w - rbeg : w - 1 - rbeg;
+        i2 += Nb - d2;
+        st2 += 1 << lg;
+    }
+    template <int ROLE>
+    __device__ __forceinline__ void down(int w, int Nb) {  // w -> w - 1
+        own -= Nb - (w - 1);
+        const int d2 = ROLE == 1 ? w - rbeg : w - 1 - rbeg;
+        i2 -= Nb - (d2 - 1);
+        st2 -= 1 << lg;
     }
 };
 
 // per-kernel constants of one thread
 struct Lane {
-    int role, t, lpr_log2, gmax_log2, tpl_log2;
+    int role, t, lpr_log2;
+    const unsigned char *lgtab;  // lanes-per-span (log2) of every width, built once per sentence
     template <int NT>
-    __device__ __forceinline__ void init(const DmvArgs &p) {
+    __device__ __forceinline__ void init(const DmvArgs &p, unsigned char *tab, int Nb) {
         constexpr int LPR = NT / 3;
-        lpr_log2 = LPR == 32 ? 5 : (LPR == 64 ? 6 : 7);
+        lpr_log2 = LPR == 32 ? 5 : (LPR == 64 ? 6 : (LPR == 128 ? 7 : 8));
         role = threadIdx.x >> lpr_log2;
         t = threadIdx.x & (LPR - 1);
-        gmax_log2 = 31 - __clz(p.gmax);
-        tpl_log2 = 31 - __clz(p.tpl);
+        const int gmax_log2 = 31 - __clz(p.gmax), tpl_log2 = 31 - __clz(p.tpl);
+        lgtab = tab;
+        for (int w = 1 + (int)threadIdx.x; w < Nb; w += NT)
+            tab[w] = (unsigned char)lanes_log2(Nb - w, w, lpr_log2, gmax_log2, tpl_log2);
+        __syncthreads();
     }
 };
 
@@ -202,15 +233,6 @@ struct Lane {
 //   role X  (steps 1, 2, dmv.py:50,54): CR[i][i+rp] (.zw of C4) with CL[j][i+rp+1] (.xy of C4)
 //   role CL (step 3, dmv.py:58):        CL[i+rp][i][NO] (.y of C4) with IL[j][i+rp];        rp = 0 merged separately
 //   role CR (step 4, dmv.py:61):        IR[i][i+1+rp] with CR[i+1+rp][j][NO] (.w of C4);    rp = w-1 merged separately
-template <int ROLE>
-__device__ __forceinline__ void role_range(int i, int w, int g, int sub, int Nb, bool has, int &rbeg, int &rend,
-                                           Stream &s1, Stream &s2) {
-    rbeg = (ROLE == 1 && sub == 0) ? g : sub;
-    rend = has ? (ROLE == 2 ? w - 1 : w) : 0;
-    if (ROLE == 0) { s1.fwd(i, rbeg, g, Nb); s2.bwd(i + rbeg + 1, w - 1 - rbeg, g, Nb); }
-    else if (ROLE == 1) { s1.fwd(i, rbeg, g, Nb); s2.bwd(i + rbeg, w - rbeg, g, Nb); }
-    else { s1.fwd(i, rbeg + 1, g, Nb); s2.bwd(i + rbeg + 1, w - 1 - rbeg, g, Nb); }
-}
 // the two terms of one split point
 template <int ROLE, typename Chart>
 __device__ __forceinline__ void role_terms(const Chart &c, int i1, int i2, float &t0, float &t1) {
@@ -232,58 +254,52 @@ __device__ __forceinline__ void role_terms(const Chart &c, int i1, int i2, float
 // log semiring, one width of the inside sweep (dmv.py:47-63)
 // ---------------------------------------------------------------------------------------------
 template <int NT, int ROLE>
-__device__ __forceinline__ void inside_role(const LogChart &c, const Lane &ln, int w, int Nb, int len, float mask_zero,
-                                            bool keep_x) {
-    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
-    const int g = q.g, sub = q.sub, lg = q.lg;
-    for (int round = 0; round < q.nrounds; ++round) {
-        const int i = q.first_cell + (round << q.cpr_log2);
-        const bool has = i < q.ncell;
-        const int j = i + w;
-        const int own = cidx(i, w, Nb);
-        Lse2 acc;
-        acc.init();
-        int rbeg, rend;
-        Stream s1, s2;
-        role_range<ROLE>(i, w, g, sub, Nb, has, rbeg, rend, s1, s2);
-        for (int r0 = rbeg; r0 < rend; r0 += g * KCH) {
-            const int n = min(KCH, (rend - r0 + g - 1) >> lg);
-            float t0[KCH], t1[KCH];
+__device__ __forceinline__ void inside_role(const LogChart &c, const Walk &wk, int t, int w, int Nb, int len,
+                                            float mask_zero, bool keep_x) {
+    const int lg = wk.lg, g = 1 << lg, sub = t & (g - 1), i = t >> lg;
+    const bool has = i < Nb - w;
+    const int j = i + w, own = wk.own;
+    const int rend = has ? (ROLE == 2 ? w - 1 : w) : 0;
+    const int dec = 1 << (2 * lg);
+    int a1 = wk.i1, s1 = wk.st1, a2 = wk.i2, s2 = wk.st2;
+    Lse2 acc;
+    acc.init();
+    for (int r0 = wk.rbeg; r0 < rend; r0 += g * KCH) {
+        const int n = min(KCH, (rend - r0 + g - 1) >> lg);
+        float t0[KCH], t1[KCH];
 #pragma unroll
-            for (int k = 0; k < KCH; ++k) {
-                t0[k] = NEG_BIG; t1[k] = NEG_BIG;
-                if (k < n) role_terms<ROLE>(c, s1.idx, s2.idx, t0[k], t1[k]);
-                s1.next(); s2.next();
-            }
-            acc.add_chunk(t0, t1, n);
+        for (int k = 0; k < KCH; ++k) {
+            t0[k] = NEG_BIG; t1[k] = NEG_BIG;
+            if (k < n) role_terms<ROLE>(c, a1, a2, t0[k], t1[k]);
+            a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
         }
-        acc.combine(g);
-        if (ROLE == 0) {
-            float2 arcL, arcR;
-            if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }  // attach + dec[GO], pre-added (dmv.py:36-37)
-            __syncwarp();
-            if (has && sub == 0) {
-                const float XL = acc.m0 + flog(acc.s0), XR = acc.m1 + flog(acc.s1);
-                c.IL[own] = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
-                c.IR[own] = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
-                if (keep_x) { c.GA[own].w = XL; c.GB[own].w = XR; }
-            }
-            // role X publishes IL / IR of this width; roles CL, CR wait for it once per width
-            if (round == q.nrounds - 1) named_arrive(NT);
-        } else {
-            if (round == 0) named_sync(NT);
-            if (has && sub == 0) {
-                if (ROLE == 1) {
-                    const float2 il = c.IL[own];
-                    const float cii = c.C4[i].y;  // CL[i][i][NO]
-                    lo2(c.C4[own]) = acc.finish_with(cii + il.x, cii + il.y);
-                } else {
-                    const float2 ir = c.IR[own];
-                    const float cjj = c.C4[j].w;  // CR[j][j][NO]
-                    float2 r = acc.finish_with(ir.x + cjj, ir.y + cjj);
-                    if (i == 0 && w != len) r = make_float2(mask_zero, mask_zero);  // single root (dmv.py:63)
-                    hi2(c.C4[own]) = r;
-                }
+        acc.add_chunk(t0, t1, n);
+    }
+    acc.combine(g);
+    if (ROLE == 0) {
+        float2 arcL, arcR;
+        if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }  // attach + dec[GO], pre-added (dmv.py:36-37)
+        __syncwarp();
+        if (has && sub == 0) {
+            const float XL = acc.m0 + flog(acc.s0), XR = acc.m1 + flog(acc.s1);
+            c.IL[own] = make_float2(XL + arcL.x, XL + arcL.y);  // dmv.py:51-52
+            c.IR[own] = make_float2(XR + arcR.x, XR + arcR.y);  // dmv.py:55-56
+            if (keep_x) { c.GA[own].w = XL; c.GB[own].w = XR; }
+        }
+        named_arrive(NT);  // role X publishes IL / IR of this width; roles CL, CR wait for it
+    } else {
+        named_sync(NT);
+        if (has && sub == 0) {
+            if (ROLE == 1) {
+                const float2 il = c.IL[own];
+                const float cii = c.C4[i].y;  // CL[i][i][NO]
+                lo2(c.C4[own]) = acc.finish_with(cii + il.x, cii + il.y);
+            } else {
+                const float2 ir = c.IR[own];
+                const float cjj = c.C4[j].w;  // CR[j][j][NO]
+                float2 r = acc.finish_with(ir.x + cjj, ir.y + cjj);
+                if (i == 0 && w != len) r = make_float2(mask_zero, mask_zero);  // single root (dmv.py:63)
+                hi2(c.C4[own]) = r;
             }
         }
     }
@@ -292,97 +308,182 @@ __device__ __forceinline__ void inside_role(const LogChart &c, const Lane &ln, i
 // ---------------------------------------------------------------------------------------------
 // log semiring, one width of the reverse sweep (replaces autograd through the chart, helpers.py:150-154)
 // ---------------------------------------------------------------------------------------------
-template <int NT, int ROLE>
-__device__ __forceinline__ void outside_role(const LogChart &c, const Lane &ln, int w, int Nb, int len) {
-    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
-    const int g = q.g, sub = q.sub;
-    for (int round = 0; round < q.nrounds; ++round) {
-        const int i = q.first_cell + (round << q.cpr_log2);
-        const bool has = i < q.ncell;
-        const int j = i + w;
-        const int own = cidx(i, w, Nb);
-        float2 gcr = make_float2(0.f, 0.f), gcl = gcr, outR = gcr, outL = gcr;
-        float XL = 0.f, XR = 0.f;
-        if (has) {
-            const float4 ga = c.GA[own], gb = c.GB[own];
-            const float4 co = c.C4[own];
-            gcr = make_float2(ga.x, ga.y + gb.z);
-            gcl = make_float2(gb.x, gb.y + ga.z);
-            outR = make_float2(co.z, co.w);
-            outL = make_float2(co.x, co.y);
-            XL = ga.w; XR = gb.w;
-            if (i == 0 && w != len) {  // masked cell (dmv.py:63) passes nothing back: p = 0 * exp(-big) = 0
-                gcr = make_float2(0.f, 0.f);
-                outR = make_float2(-NEG_BIG, -NEG_BIG);
-            }
+template <int NT, int ROLE, bool LAT>
+__device__ __forceinline__ void outside_role(const LogChart &c, const Walk &wk, int t, int w, int Nb, int len) {
+    const int lg = wk.lg, g = 1 << lg, sub = t & (g - 1), i = t >> lg;
+    const bool has = i < Nb - w;
+    const int j = i + w, own = wk.own;
+    const int dec = 1 << (2 * lg);
+    int a1 = wk.i1, s1 = wk.st1, a2 = wk.i2, s2 = wk.st2;
+    float2 gcr = make_float2(0.f, 0.f), gcl = gcr, outR = gcr, outL = gcr;
+    float XL = 0.f, XR = 0.f;
+    if (has) {
+        const float4 ga = c.GA[own], gb = c.GB[own];
+        const float4 co = c.C4[own];
+        gcr = make_float2(ga.x, ga.y + gb.z);
+        gcl = make_float2(gb.x, gb.y + ga.z);
+        outR = make_float2(co.z, co.w);
+        outL = make_float2(co.x, co.y);
+        XL = ga.w; XR = gb.w;
+        if (i == 0 && w != len) {  // masked cell (dmv.py:63) passes nothing back: p = 0 * exp(-big) = 0
+            gcr = make_float2(0.f, 0.f);
+            outR = make_float2(-NEG_BIG, -NEG_BIG);
         }
-        const int rend = has ? w : 0;
-        if (ROLE == 0) {
-            // parents IL[j][i], IR[i][j] (steps 1, 2 transposed) -> CR[i][r][.], CL[j][r+1][.]
-            // their gradient is complete once the span's own complete items have contributed (r = j resp. r = i)
-            float2 giR = make_float2(0.f, 0.f), giL = giR;
-            if (has) {
-                const float2 il = c.IL[own], ir = c.IR[own];
-                const float cii = c.C4[i].y, cjj = c.C4[j].w;
-                giR = c.gIR[own]; giL = c.gIL[own];
-                giR.x += gcr.x * fexp(ir.x + cjj - outR.x); giR.y += gcr.y * fexp(ir.y + cjj - outR.y);
-                giL.x += gcl.x * fexp(cii + il.x - outL.x); giL.y += gcl.y * fexp(cii + il.y - outL.y);
-            }
-            __syncwarp();
-            if (has && sub == 0) { c.gIR[own] = giR; c.gIL[own] = giL; }  // final: d Z / d attach of this span
-            const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
-            Stream sa, sb;
-            sa.fwd(i, sub, g, Nb);
-            sb.bwd(i + sub + 1, w - 1 - sub, g, Nb);
-#pragma unroll 2
-            for (int rp = sub; rp < rend; rp += g) {
-                const float2 a = hi2(c.C4[sa.idx]);
-                const float2 b = lo2(c.C4[sb.idx]);
-                const float pL = gxL * fexp(a.y + b.x - XL);
-                const float pR = gxR * fexp(a.x + b.y - XR);
-                float2 A = lo2(c.GA[sa.idx]); A.x += pR; A.y += pL; lo2(c.GA[sa.idx]) = A;
-                float2 B = lo2(c.GB[sb.idx]); B.x += pL; B.y += pR; lo2(c.GB[sb.idx]) = B;
-                sa.next(); sb.next();
-            }
-        } else if (ROLE == 1) {
-            // parent CL[j][i][v] (step 3 transposed) -> CL[r][i][NO], IL[j][r][v]; IL[j][i] itself is role X's
-            Stream sa, se;
-            sa.fwd(i, sub, g, Nb);
-            se.bwd(i + sub, w - sub, g, Nb);
-#pragma unroll 2
-            for (int rp = sub; rp < rend; rp += g) {
-                const float cl = c.C4[sa.idx].y;
-                const float2 e = c.IL[se.idx];
-                const float q0 = gcl.x * fexp(cl + e.x - outL.x);
-                const float q1 = gcl.y * fexp(cl + e.y - outL.y);
-                c.GA[sa.idx].z += q0 + q1;
-                if (rp > 0) { float2 u = c.gIL[se.idx]; u.x += q0; u.y += q1; c.gIL[se.idx] = u; }
-                sa.next(); se.next();
+    }
+    const int rend = has ? w : 0;
+    if (ROLE == 0) {
+        // parents IL[j][i], IR[i][j] (steps 1, 2 transposed) -> CR[i][r][.], CL[j][r+1][.]
+        // their gradient is complete once the span's own complete items have contributed (r = j resp. r = i)
+        float2 giR = make_float2(0.f, 0.f), giL = giR;
+        if (has) {
+            const float2 il = c.IL[own], ir = c.IR[own];
+            const float cii = c.C4[i].y, cjj = c.C4[j].w;
+            giR = c.gIR[own]; giL = c.gIL[own];
+            giR.x += gcr.x * fexp(ir.x + cjj - outR.x); giR.y += gcr.y * fexp(ir.y + cjj - outR.y);
+            giL.x += gcl.x * fexp(cii + il.x - outL.x); giL.y += gcl.y * fexp(cii + il.y - outL.y);
+        }
+        __syncwarp();
+        if (has && sub == 0) { c.gIR[own] = giR; c.gIL[own] = giL; }  // final: d Z / d attach of this span
+        const float gxR = giR.x + giR.y, gxL = giL.x + giL.y;
+        if (LAT && kBatchOutside) {
+            // latency variant (registers to spare): split points in batches of OB -- all loads (operands and
+            // read-modify-write targets) first, then the math, then the stores.  The targets of one lane are distinct
+            // cells, so batching is safe, and it takes the LDS latency off the dependent chain.
+            for (int r0 = sub; r0 < rend; r0 += OB * g) {
+                int ia[OB], ib[OB];
+                float2 a[OB], b[OB], A[OB], B[OB];
+#pragma unroll
+                for (int k = 0; k < OB; ++k) {
+                    ia[k] = a1; ib[k] = a2;
+                    if (r0 + k * g < rend) { a[k] = hi2(c.C4[a1]); b[k] = lo2(c.C4[a2]); A[k] = lo2(c.GA[a1]); B[k] = lo2(c.GB[a2]); }
+                    a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+                }
+#pragma unroll
+                for (int k = 0; k < OB; ++k)
+                    if (r0 + k * g < rend) {
+                        const float pL = gxL * fexp(a[k].y + b[k].x - XL);
+                        const float pR = gxR * fexp(a[k].x + b[k].y - XR);
+                        A[k].x += pR; A[k].y += pL; B[k].x += pL; B[k].y += pR;
+                        lo2(c.GA[ia[k]]) = A[k]; lo2(c.GB[ib[k]]) = B[k];
+                    }
             }
         } else {
-            // parent CR[i][j][v] (step 4 transposed) -> IR[i][r][v], CR[r][j][NO]; IR[i][j] itself is role X's
-            Stream sf, sb;
-            sf.fwd(i, sub + 1, g, Nb);
-            sb.bwd(i + sub + 1, w - 1 - sub, g, Nb);
 #pragma unroll 2
             for (int rp = sub; rp < rend; rp += g) {
-                const float2 f = c.IR[sf.idx];
-                const float cr = c.C4[sb.idx].w;
-                const float p0 = gcr.x * fexp(f.x + cr - outR.x);
-                const float p1 = gcr.y * fexp(f.y + cr - outR.y);
-                c.GB[sb.idx].z += p0 + p1;
-                if (rp < w - 1) { float2 t = c.gIR[sf.idx]; t.x += p0; t.y += p1; c.gIR[sf.idx] = t; }
-                sf.next(); sb.next();
+                const float2 a = hi2(c.C4[a1]);
+                const float2 b = lo2(c.C4[a2]);
+                const float pL = gxL * fexp(a.y + b.x - XL);
+                const float pR = gxR * fexp(a.x + b.y - XR);
+                float2 A = lo2(c.GA[a1]); A.x += pR; A.y += pL; lo2(c.GA[a1]) = A;
+                float2 B = lo2(c.GB[a2]); B.x += pL; B.y += pR; lo2(c.GB[a2]) = B;
+                a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
             }
         }
+    } else if (ROLE == 1) {
+        // parent CL[j][i][v] (step 3 transposed) -> CL[r][i][NO], IL[j][r][v]; IL[j][i] itself is role X's
+        if (LAT && kBatchOutside) {
+            for (int r0 = sub; r0 < rend; r0 += OB * g) {
+                int ia[OB], ib[OB];
+                float cl[OB], gz[OB];
+                float2 e[OB], u[OB];
+#pragma unroll
+                for (int k = 0; k < OB; ++k) {
+                    ia[k] = a1; ib[k] = a2;
+                    if (r0 + k * g < rend) { cl[k] = c.C4[a1].y; e[k] = c.IL[a2]; gz[k] = c.GA[a1].z; u[k] = c.gIL[a2]; }
+                    a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+                }
+#pragma unroll
+                for (int k = 0; k < OB; ++k)
+                    if (r0 + k * g < rend) {
+                        const float q0 = gcl.x * fexp(cl[k] + e[k].x - outL.x);
+                        const float q1 = gcl.y * fexp(cl[k] + e[k].y - outL.y);
+                        c.GA[ia[k]].z = gz[k] + (q0 + q1);
+                        if (r0 + k * g > 0) { u[k].x += q0; u[k].y += q1; c.gIL[ib[k]] = u[k]; }
+                    }
+            }
+        } else {
+#pragma unroll 2
+            for (int rp = sub; rp < rend; rp += g) {
+                const float cl = c.C4[a1].y;
+                const float2 e = c.IL[a2];
+                const float q0 = gcl.x * fexp(cl + e.x - outL.x);
+                const float q1 = gcl.y * fexp(cl + e.y - outL.y);
+                c.GA[a1].z += q0 + q1;
+                if (rp > 0) { float2 u = c.gIL[a2]; u.x += q0; u.y += q1; c.gIL[a2] = u; }
+                a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+            }
+        }
+    } else {
+        // parent CR[i][j][v] (step 4 transposed) -> IR[i][r][v], CR[r][j][NO]; IR[i][j] itself is role X's
+        if (LAT && kBatchOutside) {
+            for (int r0 = sub; r0 < rend; r0 += OB * g) {
+                int ia[OB], ib[OB];
+                float cr[OB], gz[OB];
+                float2 f[OB], tt[OB];
+#pragma unroll
+                for (int k = 0; k < OB; ++k) {
+                    ia[k] = a1; ib[k] = a2;
+                    if (r0 + k * g < rend) { f[k] = c.IR[a1]; cr[k] = c.C4[a2].w; gz[k] = c.GB[a2].z; tt[k] = c.gIR[a1]; }
+                    a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+                }
+#pragma unroll
+                for (int k = 0; k < OB; ++k)
+                    if (r0 + k * g < rend) {
+                        const float p0 = gcr.x * fexp(f[k].x + cr[k] - outR.x);
+                        const float p1 = gcr.y * fexp(f[k].y + cr[k] - outR.y);
+                        c.GB[ib[k]].z = gz[k] + (p0 + p1);
+                        if (r0 + k * g < w - 1) { tt[k].x += p0; tt[k].y += p1; c.gIR[ia[k]] = tt[k]; }
+                    }
+            }
+        } else {
+#pragma unroll 2
+            for (int rp = sub; rp < rend; rp += g) {
+                const float2 f = c.IR[a1];
+                const float cr = c.C4[a2].w;
+                const float p0 = gcr.x * fexp(f.x + cr - outR.x);
+                const float p1 = gcr.y * fexp(f.y + cr - outR.y);
+                c.GB[a2].z += p0 + p1;
+                if (rp < w - 1) { float2 tt = c.gIR[a1]; tt.x += p0; tt.y += p1; c.gIR[a1] = tt; }
+                a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+            }
+        }
+    }
+}
+
+// the width loops of one role: geometry is re-derived only when the lanes-per-span of the width changes
+template <int NT, int ROLE>
+__device__ __forceinline__ void inside_sweep(const LogChart &c, const Lane &ln, int Nb, int len, float mask_zero,
+                                             bool keep_x) {
+    Walk wk;
+    wk.lg = -1;
+#pragma unroll 1
+    for (int w = 1; w < Nb; ++w) {
+        const int lg = ln.lgtab[w];
+        if (lg != wk.lg) wk.template reset<ROLE, true>(w, ln.t, lg, Nb);
+        inside_role<NT, ROLE>(c, wk, ln.t, w, Nb, len, mask_zero, keep_x);
+        __syncthreads();
+        wk.template up<ROLE>(w, Nb);
+    }
+}
+template <int NT, int ROLE, bool LAT>
+__device__ __forceinline__ void outside_sweep(const LogChart &c, const Lane &ln, int Nb, int len) {
+    Walk wk;
+    wk.lg = -1;
+#pragma unroll 1
+    for (int w = Nb - 1; w >= 1; --w) {
+        const int lg = ln.lgtab[w];
+        if (lg != wk.lg) wk.template reset<ROLE, false>(w, ln.t, lg, Nb);
+        outside_role<NT, ROLE, LAT>(c, wk, ln.t, w, Nb, len);
+        __syncthreads();
+        wk.template down<ROLE>(w, Nb);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // log semiring: inside + outside for one sentence
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
+template <int NT, bool LAT>
+__device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec, unsigned char *lgtab) {
     const int tid = threadIdx.x;
     const int N = p.N;
     int len = (int)p.lengths[b];
@@ -418,25 +519,19 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
 
     if (prof) p.prof[0] = clock64() - t0c;
     Lane ln;
-    ln.init<NT>(p);
-    for (int w = 1; w < Nb; ++w) {
-        if (ln.role == 0) inside_role<NT, 0>(c, ln, w, Nb, len, p.mask_zero, want_grad);
-        else if (ln.role == 1) inside_role<NT, 1>(c, ln, w, Nb, len, p.mask_zero, want_grad);
-        else inside_role<NT, 2>(c, ln, w, Nb, len, p.mask_zero, want_grad);
-        __syncthreads();
-    }
+    ln.init<NT>(p, lgtab, Nb);
+    if (ln.role == 0) inside_sweep<NT, 0>(c, ln, Nb, len, p.mask_zero, want_grad);
+    else if (ln.role == 1) inside_sweep<NT, 1>(c, ln, Nb, len, p.mask_zero, want_grad);
+    else inside_sweep<NT, 2>(c, ln, Nb, len, p.mask_zero, want_grad);
     if (prof) p.prof[1] = clock64() - t0c;
     if (tid == 0) p.Z[b] = c.C4[cidx(0, len, Nb)].w;  // dmv.py:65
     if (!want_grad) { __syncthreads(); return; }
 
     if (tid == 0) c.GB[cidx(0, len, Nb)].z = p.gZ ? p.gZ[b] : 1.f;
     __syncthreads();
-    for (int w = Nb - 1; w >= 1; --w) {
-        if (ln.role == 0) outside_role<NT, 0>(c, ln, w, Nb, len);
-        else if (ln.role == 1) outside_role<NT, 1>(c, ln, w, Nb, len);
-        else outside_role<NT, 2>(c, ln, w, Nb, len);
-        __syncthreads();
-    }
+    if (ln.role == 0) outside_sweep<NT, 0, LAT>(c, ln, Nb, len);
+    else if (ln.role == 1) outside_sweep<NT, 1, LAT>(c, ln, Nb, len);
+    else outside_sweep<NT, 2, LAT>(c, ln, Nb, len);
     if (prof) p.prof[2] = clock64() - t0c;
     // ---------------- outputs ----------------
     if (p.gattach) {
@@ -491,80 +586,90 @@ struct ProfAcc { };
 #define PROF_MARK(slot) do { } while (0)
 #endif
 template <int NT, int ROLE>
-__device__ __forceinline__ void viterbi_role(const MaxChart &c, const Lane &ln, int w, int Nb, int len,
+__device__ __forceinline__ void viterbi_role(const MaxChart &c, const Walk &wk, int t, int w, int Nb, int len,
                                              float mask_zero, ProfAcc &pa) {
     PROF_MARK(0);
-    const Geo q(w, Nb, ln.t, ln.lpr_log2, ln.gmax_log2, ln.tpl_log2);
-    const int g = q.g, sub = q.sub;
-    for (int round = 0; round < q.nrounds; ++round) {
-        const int i = q.first_cell + (round << q.cpr_log2);
-        const bool has = i < q.ncell;
-        const int j = i + w;
-        const int own = cidx(i, w, Nb);
-        Max2 acc;
-        acc.init();
-        int rbeg, rend;
-        Stream s1, s2;
-        role_range<ROLE>(i, w, g, sub, Nb, has, rbeg, rend, s1, s2);
-        PROF_MARK(1);
-        for (int r0 = rbeg; r0 < rend; r0 += 4 * g) {
-            float t0[4], t1[4];
+    const int lg = wk.lg, g = 1 << lg, sub = t & (g - 1), i = t >> lg;
+    const bool has = i < Nb - w;
+    const int j = i + w, own = wk.own;
+    const int rend = has ? (ROLE == 2 ? w - 1 : w) : 0;
+    const int dec = 1 << (2 * lg);
+    int a1 = wk.i1, s1 = wk.st1, a2 = wk.i2, s2 = wk.st2;
+    Max2 acc;
+    acc.init();
+    PROF_MARK(1);
+    for (int r0 = wk.rbeg; r0 < rend; r0 += 4 * g) {
+        float t0[4], t1[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                t0[k] = NEG_BIG; t1[k] = NEG_BIG;
-                if (r0 + k * g < rend) {
-                    role_terms<ROLE>(c, s1.idx, s2.idx, t0[k], t1[k]);  // plain fp32 adds: nothing to contract
-                }
-                s1.next(); s2.next();
-            }
+        for (int k = 0; k < 4; ++k) {
+            t0[k] = NEG_BIG; t1[k] = NEG_BIG;
+            if (r0 + k * g < rend) role_terms<ROLE>(c, a1, a2, t0[k], t1[k]);  // plain fp32 adds: nothing to contract
+            a1 += s1; s1 -= dec; a2 += s2; s2 -= dec;
+        }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc.add(t0[k], t1[k], r0 + k * g);  // NEG_BIG never beats a real term
+        for (int k = 0; k < 4; ++k) acc.add(t0[k], t1[k], r0 + k * g);  // NEG_BIG never beats a real term
+    }
+    PROF_MARK(2);
+    acc.combine(g);
+    PROF_MARK(3);
+    if (ROLE == 0) {
+        float2 arcL, arcR;
+        if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }
+        __syncwarp();
+        if (has && sub == 0) {
+            c.IL[own] = make_float2(__fadd_rn(acc.v0, arcL.x), __fadd_rn(acc.v0, arcL.y));
+            c.IR[own] = make_float2(__fadd_rn(acc.v1, arcR.x), __fadd_rn(acc.v1, arcR.y));
+            c.bp[own * 6 + 0] = (uint8_t)acc.a0; c.bp[own * 6 + 1] = (uint8_t)acc.a1;
         }
-        PROF_MARK(2);
-        acc.combine(g);
-        PROF_MARK(3);
-        if (ROLE == 0) {
-            float2 arcL, arcR;
-            if (has) { arcL = c.IL[own]; arcR = c.IR[own]; }
-            __syncwarp();
-            if (has && sub == 0) {
-                c.IL[own] = make_float2(__fadd_rn(acc.v0, arcL.x), __fadd_rn(acc.v0, arcL.y));
-                c.IR[own] = make_float2(__fadd_rn(acc.v1, arcR.x), __fadd_rn(acc.v1, arcR.y));
-                c.bp[own * 6 + 0] = (uint8_t)acc.a0; c.bp[own * 6 + 1] = (uint8_t)acc.a1;
+        PROF_MARK(4);
+        named_arrive(NT);
+        PROF_MARK(5);
+    } else {
+        named_sync(NT);
+        PROF_MARK(5);
+        if (has && sub == 0) {
+            if (ROLE == 1) {  // the span's own incomplete item is split 0: it wins ties
+                const float2 il = c.IL[own];
+                const float cii = c.C4[i].y;
+                const float t0 = __fadd_rn(cii, il.x), t1 = __fadd_rn(cii, il.y);
+                if (t0 >= acc.v0) { acc.v0 = t0; acc.a0 = 0; }
+                if (t1 >= acc.v1) { acc.v1 = t1; acc.a1 = 0; }
+                lo2(c.C4[own]) = make_float2(acc.v0, acc.v1);
+                c.bp[own * 6 + 2] = (uint8_t)acc.a0; c.bp[own * 6 + 3] = (uint8_t)acc.a1;
+            } else {  // the span's own incomplete item is split w-1: it loses ties
+                const float2 ir = c.IR[own];
+                const float cjj = c.C4[j].w;
+                const float t0 = __fadd_rn(ir.x, cjj), t1 = __fadd_rn(ir.y, cjj);
+                if (t0 > acc.v0) { acc.v0 = t0; acc.a0 = w - 1; }
+                if (t1 > acc.v1) { acc.v1 = t1; acc.a1 = w - 1; }
+                if (i == 0 && w != len) { acc.v0 = mask_zero; acc.v1 = mask_zero; }
+                hi2(c.C4[own]) = make_float2(acc.v0, acc.v1);
+                c.bp[own * 6 + 4] = (uint8_t)acc.a0; c.bp[own * 6 + 5] = (uint8_t)acc.a1;
             }
-            PROF_MARK(4);
-            if (round == q.nrounds - 1) named_arrive(NT);
-            PROF_MARK(5);
-        } else {
-            if (round == 0) named_sync(NT);
-            PROF_MARK(5);
-            if (has && sub == 0) {
-                if (ROLE == 1) {  // the span's own incomplete item is split 0: it wins ties
-                    const float2 il = c.IL[own];
-                    const float cii = c.C4[i].y;
-                    const float t0 = __fadd_rn(cii, il.x), t1 = __fadd_rn(cii, il.y);
-                    if (t0 >= acc.v0) { acc.v0 = t0; acc.a0 = 0; }
-                    if (t1 >= acc.v1) { acc.v1 = t1; acc.a1 = 0; }
-                    lo2(c.C4[own]) = make_float2(acc.v0, acc.v1);
-                    c.bp[own * 6 + 2] = (uint8_t)acc.a0; c.bp[own * 6 + 3] = (uint8_t)acc.a1;
-                } else {  // the span's own incomplete item is split w-1: it loses ties
-                    const float2 ir = c.IR[own];
-                    const float cjj = c.C4[j].w;
-                    const float t0 = __fadd_rn(ir.x, cjj), t1 = __fadd_rn(ir.y, cjj);
-                    if (t0 > acc.v0) { acc.v0 = t0; acc.a0 = w - 1; }
-                    if (t1 > acc.v1) { acc.v1 = t1; acc.a1 = w - 1; }
-                    if (i == 0 && w != len) { acc.v0 = mask_zero; acc.v1 = mask_zero; }
-                    hi2(c.C4[own]) = make_float2(acc.v0, acc.v1);
-                    c.bp[own * 6 + 4] = (uint8_t)acc.a0; c.bp[own * 6 + 5] = (uint8_t)acc.a1;
-                }
-            }
-            PROF_MARK(4);
         }
+        PROF_MARK(4);
+    }
+}
+
+template <int NT, int ROLE>
+__device__ __forceinline__ void viterbi_sweep(const MaxChart &c, const Lane &ln, int Nb, int len, float mask_zero,
+                                              ProfAcc &pa) {
+    Walk wk;
+    wk.lg = -1;
+#pragma unroll 1
+    for (int w = 1; w < Nb; ++w) {
+        const int lg = ln.lgtab[w];
+        if (lg != wk.lg) wk.template reset<ROLE, true>(w, ln.t, lg, Nb);
+        viterbi_role<NT, ROLE>(c, wk, ln.t, w, Nb, len, mask_zero, pa);
+        PROF_MARK(6);
+        __syncthreads();
+        PROF_MARK(7);
+        wk.template up<ROLE>(w, Nb);
     }
 }
 
 template <int NT>
-__device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
+__device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec, unsigned char *lgtab) {
     const int tid = threadIdx.x;
     const int N = p.N;
     int len = (int)p.lengths[b];
@@ -605,20 +710,15 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
 
     if (prof) p.prof[4] = clock64() - t0c;
     Lane ln;
-    ln.init<NT>(p);
+    ln.init<NT>(p, lgtab, Nb);
     ProfAcc pa;
 #ifdef VLGAE_PROF_DETAIL
     for (int k = 0; k < 8; ++k) pa.v[k] = 0;
     pa.last = clock64();
 #endif
-    for (int w = 1; w < Nb; ++w) {
-        if (ln.role == 0) viterbi_role<NT, 0>(c, ln, w, Nb, len, p.mask_zero, pa);
-        else if (ln.role == 1) viterbi_role<NT, 1>(c, ln, w, Nb, len, p.mask_zero, pa);
-        else viterbi_role<NT, 2>(c, ln, w, Nb, len, p.mask_zero, pa);
-        PROF_MARK(6);
-        __syncthreads();
-        PROF_MARK(7);
-    }
+    if (ln.role == 0) viterbi_sweep<NT, 0>(c, ln, Nb, len, p.mask_zero, pa);
+    else if (ln.role == 1) viterbi_sweep<NT, 1>(c, ln, Nb, len, p.mask_zero, pa);
+    else viterbi_sweep<NT, 2>(c, ln, Nb, len, p.mask_zero, pa);
 #ifdef VLGAE_PROF_DETAIL
     if (p.prof && b == 0 && (tid == 0 || tid == NT / 3 || tid == 2 * NT / 3))
         for (int k = 0; k < 8; ++k) p.prof[8 + (tid / (NT / 3)) * 8 + k] = pa.v[k];
@@ -687,9 +787,12 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec) {
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent CTAs stride over (sentence, semiring) work items
 // ---------------------------------------------------------------------------------------------
-template <int NT, bool SMEM>
-__global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
+// LAT = latency variant: registers uncapped (fewer CTAs per SM, no spills, batched reverse sweep) for launches whose
+// work items are all resident at once; the throughput variant caps registers for 6 / 3 CTAs per SM.
+template <int NT, bool SMEM, bool LAT>
+__global__ void __launch_bounds__(NT, LAT ? (NT == 96 ? 4 : 2) : (NT == 96 ? 6 : (NT == 192 ? 3 : 1))) dmv_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned char s_lgtab[260];
     float *sdec = reinterpret_cast<float *>(smem_raw);
     void *mem;
     if (SMEM)
@@ -714,8 +817,8 @@ __global__ void __launch_bounds__(NT) dmv_kernel(DmvArgs p) {
             len = len < 0 ? 0 : (len > p.N - 1 ? p.N - 1 : len);
             if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         }
-        if (which == 0) log_pass<NT>(p, b, mem, sdec);
-        else max_pass<NT>(p, b, mem, sdec);
+        if (which == 0) log_pass<NT, LAT>(p, b, mem, sdec, s_lgtab);
+        else max_pass<NT>(p, b, mem, sdec, s_lgtab);
     }
 }
 
@@ -827,7 +930,7 @@ int dmv_grid_for_workspace(int B) {
     return B * 2 < cap ? B * 2 : cap;
 }
 
-template <int NT>
+template <int NT, bool LAT>
 static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
     // `cap` = chart positions this launch is sized for (a.N, or the upper end of a length bucket)
     cudaError_t e = device_info();
@@ -837,7 +940,7 @@ static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
     const int total = a.B * a.npass;
     a.smem_n = cap;
     if (smem_need <= (size_t)g_smem_optin) {
-        auto k = dmv_kernel<NT, true>;
+        auto k = dmv_kernel<NT, true, LAT>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -848,7 +951,7 @@ static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
         if (grid > total) grid = total;
         k<<<grid, NT, smem_need, st>>>(a);
     } else {
-        auto k = dmv_kernel<NT, false>;
+        auto k = dmv_kernel<NT, false, false>;
         int grid = dmv_grid_for_workspace(a.B);
         if (grid > total) grid = total;
         a.ws_stride = dmv_chart_bytes(a.N, passes);
@@ -857,11 +960,14 @@ static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads, cudaStream_t st) {
-    if (threads <= 0) threads = cap <= 33 ? 96 : (cap <= 65 ? 192 : 384);
-    if (threads <= 96) return launch_nt<96>(a, passes, cap, st);
-    if (threads <= 192) return launch_nt<192>(a, passes, cap, st);
-    return launch_nt<384>(a, passes, cap, st);
+static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads, bool lat, cudaStream_t st) {
+    // CTA = 3 roles x LPR lanes with LPR >= cap - 1 (every width is one round); a tuning request can only widen it
+    const int need = cap <= 33 ? 96 : (cap <= 65 ? 192 : (cap <= 129 ? 384 : 768));
+    if (threads < need) threads = need;
+    if (threads <= 96) return lat ? launch_nt<96, true>(a, passes, cap, st) : launch_nt<96, false>(a, passes, cap, st);
+    if (threads <= 192) return lat ? launch_nt<192, true>(a, passes, cap, st) : launch_nt<192, false>(a, passes, cap, st);
+    if (threads <= 384) return launch_nt<384, false>(a, passes, cap, st);
+    return launch_nt<768, false>(a, passes, cap, st);
 }
 
 static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
@@ -895,10 +1001,11 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     // chart allows.  Sentences outside a launch's bucket are skipped by its CTAs (no host knowledge of the lengths,
     // no sorting assumption).  Longest bucket first.
     static const int env_bucket = env_int("VLGAE_DMV_BUCKETS", 1);
-    const size_t full_need = dec_bytes(a.N) + dmv_chart_bytes(a.N, passes);
-    const int occ_full = full_need <= (size_t)g_smem_optin ? (int)((size_t)g_smem_optin / full_need) : 2;
-    const bool bulk = env_bucket && (long long)a.B * a.npass > 2LL * g_sm_count * (occ_full < 1 ? 1 : occ_full);
-    if (!bulk) return launch_cap(a, passes, a.N, threads, st);
+    const long long items = (long long)a.B * a.npass;
+    const bool bulk = env_bucket && items > 8192;
+    // latency variant (uncapped registers, 2 CTAs per SM; 4 for the 96-thread CTA) when every work item is resident
+    const bool lat = items <= (long long)g_sm_count * (a.N <= 33 ? 4 : 2);
+    if (!bulk) return launch_cap(a, passes, a.N, threads, lat, st);
     static const int caps[] = {8, 12, 16, 20, 24, 28, 33, 41, 49, 65, 97, 129, 256};
     int nb = 0, bounds[16];
     for (int c : caps) if (c < a.N) bounds[nb++] = c;
@@ -907,7 +1014,7 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
         DmvArgs bkt = a;
         bkt.nb_hi = bounds[k];
         bkt.nb_lo = k > 0 ? bounds[k - 1] + 1 : 0;
-        e = launch_cap(bkt, passes, bounds[k], threads, st);
+        e = launch_cap(bkt, passes, bounds[k], threads, false, st);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
