@@ -259,7 +259,8 @@ def alignment_leg(dev, iters=10):
         "workload": f"gather_logit_simple A={A} V={V} B={B} Q={Q} D={D} (cfg2), bf16 hi/lo split x3 on tcgen05, "
                     "rows padded to 8 floats", "ms": ms, "captions_per_s": B / (ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                     "traffic": None, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu capture, profiles/r1_align_kernel.txt)
+                     "traffic": 8.293e9, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
                      "kernel": "align_gemm_kernel (+ align_pack_kernel x2)"},
         "tensor_tflops_issued": 3 * 2.0 * A * B * Q * V * D / (ms * 1e-3) / 1e12,
         "parity": {"mask_pattern_equal": bool(((got == -1e20) == masked).all()), "max_abs_err_vs_fp32_oracle": err},
@@ -439,7 +440,10 @@ def run_b200_arm(args):
                     "heads_bit_exact": e2e_ok},
             "gpu_launches": args.steps,
             "roofline": {"bound": "sfu", "achieved": achieved / 1e9, "peak": peaks["mufu"] / 1e9, "unit": "Gop/s",
-                         "frac": achieved / peaks["mufu"], "traffic": None,
+                         "frac": achieved / peaks["mufu"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the ncu --set full capture
+                         # summarised in profiles/r1_dmv_kernel.txt (outputs stay in L2 at capture time)
+                         "traffic": 1.024e6,
                          "kernel": "dmv_kernel<192,true> (3 role groups x 64 lanes, chart in shared memory)", "algorithmic_mufu_ops_per_launch": wc["mufu"],
                          "peak_source": "measured live: ex2.approx.f32 microbenchmark (vlgae_microbench_mufu)",
                          "fp32_frac": (wc["fp32"] / per_launch_s) / peaks["fp32"],
