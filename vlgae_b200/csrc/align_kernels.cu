@@ -27,13 +27,29 @@
 
 #include "align_kernels.cuh"
 
+#ifndef VLGAE_ST_MODE
+#define VLGAE_ST_MODE 0
+#endif
+#if VLGAE_ST_MODE == 0
+#define ALIGN_ST(p, v) __stcs(p, v)
+#elif VLGAE_ST_MODE == 1
+#define ALIGN_ST(p, v) (*(p) = (v))
+#elif VLGAE_ST_MODE == 2
+#define ALIGN_ST(p, v) __stcg(p, v)
+#else
+#define ALIGN_ST(p, v) __stwt(p, v)
+#endif
+
 namespace vlgae {
 namespace {
 
 constexpr int TILE_M = 128;          // factors per tile (TMEM lanes)
 constexpr int CHUNK_A = TILE_M * 128;  // bytes of one (part, k-block) chunk of operand A: 128 rows x 64 bf16
-constexpr int NACC = 4;              // TMEM accumulators (128 columns each)
-constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each takes every other 16-column chunk
+constexpr int MAX_ACC = 8;           // TMEM accumulators: as many as fit behind operand A (columns 0..127), stride = nq rounded to 32
+#ifndef VLGAE_EPI_WARPS
+#define VLGAE_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = VLGAE_EPI_WARPS;  // kEpiWarps / 4 warps per TMEM lane quadrant, interleaved over 16-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 // ---------------------------------------------------------------------------------------------
@@ -78,6 +94,39 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// variants with a compile-time accumulate flag (no predicate set-up from a register in the issue loop)
+template <int ACC>
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
+}
+// A operand from tensor memory (TS form): lane = row of A, 8 columns (16 bf16 along K) per MMA
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bits (one UMMA_K slice of a K-major operand), lanes = rows
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t dst_tmem, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(dst_tmem), "l"(sdesc) : "memory");
+}
+
 // 32 lanes x 16 columns of fp32: thread i of the warp gets lane (quadrant*32 + i), columns c0 .. c0+15
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -98,6 +147,41 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
 __device__ __forceinline__ uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// the same load without the wait: several can be in flight; tc_wait_ld ties the registers to the wait
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// shared -> global bulk copy (TMA), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(float *dst, const float *src, int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+// wait until at most `pending` of this thread's bulk groups still read shared memory
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -155,27 +239,29 @@ __global__ void align_pack_kernel(const float *__restrict__ x, const uint8_t *__
 struct AlignSmem {
     uint64_t vis_full, vis_empty;
     uint64_t txt_full[8], txt_empty[8];
-    uint64_t acc_full[NACC], acc_empty[NACC];
+    uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
     uint32_t tmem_base;
 };
 
+template <int KB, bool TS, bool BULK>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // [vis tile: 2*KB chunks of 16 KB][stage 0: 2*KB chunks of nq*128 B] ... [AlignSmem]
-    const int KB = p.KB, nq = p.nq, S = p.stages;
+    // [vis tile: 2*KB chunks of 16 KB][stage 0: 2*KB chunks of nq*128 B] ... [BULK: output tile nq x 128 fp32][AlignSmem]
+    const int nq = p.nq, S = p.stages;
     const uint32_t vis_bytes = 2u * KB * CHUNK_A;
     const uint32_t chunk_b = (uint32_t)nq * 128u;
     const uint32_t stage_bytes = 2u * KB * chunk_b;
     uint8_t *s_vis = smem;
     uint8_t *s_txt = smem + vis_bytes;
-    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + vis_bytes + (size_t)S * stage_bytes);
+    float *s_out = reinterpret_cast<float *>(smem + vis_bytes + (size_t)S * stage_bytes);
+    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + vis_bytes + (size_t)S * stage_bytes + (BULK ? (size_t)nq * 512 : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(&sb->vis_full, 1);
         mbar_init(&sb->vis_empty, 1);
         for (int s = 0; s < S; ++s) { mbar_init(&sb->txt_full[s], 1); mbar_init(&sb->txt_empty[s], 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], kEpiWarps); }
+        for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
@@ -186,133 +272,268 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sb->tmem_base;
+    // TS: a CTA keeps TWO image tiles (256 factors) in tensor memory and runs every caption tile against both, which
+    // halves the caption bytes streamed from L2 per output byte -- with one tile the kernel moves as many bytes L2 -> SM
+    // as it writes, and the L2 slices (~12 TB/s for reads + writes + write-back together) are what saturates.
+    constexpr int PAIR = TS ? 2 : 1;
+    constexpr uint32_t A_COLS = 64u * KB;  // tensor-memory columns of one image tile (hi + lo, 32 per 64-wide k-block)
+    const uint32_t ACC_COL0 = TS ? PAIR * A_COLS : 0u, acc_stride = (uint32_t)((nq + 31) & ~31);
+    const uint32_t NACC = min((uint32_t)MAX_ACC, (512u - ACC_COL0) / acc_stride);
 
-    // work items: (a, v-tile, chunk of captions); tiles inside an item: (b, q-tile)
+    // work items: (a, group of PAIR v-tiles, chunk of captions) -- full groups first, the odd last v-tiles after them, so
+    // that the static round-robin deal stays balanced; tiles inside an item: (b, q-tile, v-tile of the group)
     const int VT = p.VT, QT = p.QT, BCH = p.BCH;
-    const int n_items = p.A * VT * BCH;
+    const int VG = VT / PAIR;                        // full groups per image
+    const int n_full = p.A * VG * BCH;
+    const int n_items = n_full + (VT % PAIR ? p.A * BCH : 0);
     const int b_per = (p.B + BCH - 1) / BCH;
+    auto decode = [&](int item, int &a, int &vt0, int &ntv, int &b0, int &b1) {
+        int bc;
+        if (item < n_full) {
+            a = item / (VG * BCH);
+            const int rem = item - a * VG * BCH;
+            const int g = rem / BCH;
+            bc = rem - g * BCH;
+            vt0 = g * PAIR;
+            ntv = PAIR;
+        } else {
+            const int j = item - n_full;
+            a = j / BCH;
+            bc = j - a * BCH;
+            vt0 = VG * PAIR;
+            ntv = VT - vt0;
+        }
+        b0 = bc * b_per;
+        b1 = min(p.B, b0 + b_per);
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it_vis = 0, it_txt = 0;
+            uint32_t it_vis = 0, s = 0, s_phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int a = item / (VT * BCH), rem = item - a * VT * BCH;
-                const int vt = rem / BCH, bc = rem - vt * BCH;
-                const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
-                mbar_wait(&sb->vis_empty, (it_vis & 1) ^ 1);
-                mbar_expect_tx(&sb->vis_full, vis_bytes);
-                bulk_g2s(s_vis, p.vis_packed + ((size_t)a * VT + vt) * vis_bytes, vis_bytes, &sb->vis_full);
-                ++it_vis;
+                int a, vt0, ntv, b0, b1;
+                decode(item, a, vt0, ntv, b0, b1);
+                for (int t = 0; t < ntv; ++t) {  // TS: one after the other through the same buffer (copied on to TMEM)
+                    mbar_wait(&sb->vis_empty, (it_vis & 1) ^ 1);
+                    mbar_expect_tx(&sb->vis_full, vis_bytes);
+                    bulk_g2s(s_vis, p.vis_packed + ((size_t)a * VT + vt0 + t) * vis_bytes, vis_bytes, &sb->vis_full);
+                    ++it_vis;
+                }
                 for (int b = b0; b < b1; ++b)
                     for (int qt = 0; qt < QT; ++qt) {
-                        const int s = it_txt % S;
-                        mbar_wait(&sb->txt_empty[s], ((it_txt / S) & 1) ^ 1);
-                        mbar_expect_tx(&sb->txt_full[s], stage_bytes);
-                        // the packed caption tile has chunks of 128 rows; copy the first nq rows of each chunk
-                        const uint8_t *src = p.txt_packed + ((size_t)b * QT + qt) * (size_t)(2 * KB * CHUNK_A);
-                        for (int ch = 0; ch < 2 * KB; ++ch)
-                            bulk_g2s(s_txt + (size_t)s * stage_bytes + (size_t)ch * chunk_b, src + (size_t)ch * CHUNK_A,
-                                     chunk_b, &sb->txt_full[s]);
-                        ++it_txt;
+                        mbar_wait(&sb->txt_empty[s], s_phase ^ 1);
+                        if (p.debug & 8) {  // measurement aid: no caption traffic
+                            mbar_arrive(&sb->txt_full[s]);
+                        } else {
+                            mbar_expect_tx(&sb->txt_full[s], stage_bytes);
+                            // the packed caption tile has chunks of 128 rows; copy the first nq rows of each chunk
+                            const uint8_t *src = p.txt_packed + ((size_t)b * QT + qt) * (size_t)(2 * KB * CHUNK_A);
+                            for (int ch = 0; ch < 2 * KB; ++ch)
+                                bulk_g2s(s_txt + (size_t)s * stage_bytes + (size_t)ch * chunk_b, src + (size_t)ch * CHUNK_A,
+                                         chunk_b, &sb->txt_full[s]);
+                        }
+                        if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
                     }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One thread issues every MMA, so its instruction stream must stay well under the tensor time of a tile
+        // (24 MMAs x 48 clk): descriptors are formed once per tile / per item and advanced by compile-time constants.
         if (lane == 0) {
             const uint32_t idesc = idesc_bf16(TILE_M, nq);
-            uint32_t it_vis = 0, it_txt = 0;
+            const uint64_t cb4 = (uint64_t)(chunk_b >> 4);  // descriptor units (16 B) between caption chunks
+            uint32_t it_vis = 0, s = 0, s_phase = 0, acc = 0, acc_phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int a = item / (VT * BCH), rem = item - a * VT * BCH;
-                const int vt = rem / BCH, bc = rem - vt * BCH;
-                (void)a; (void)vt;
-                const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
-                mbar_wait(&sb->vis_full, it_vis & 1);
-                ++it_vis;
+                int a, vt0, ntv, b0, b1;
+                decode(item, a, vt0, ntv, b0, b1);
+                const uint64_t a_desc0 = smem_desc_sw128(smem_u32(s_vis));
+                if (TS) {
+                    // Image tiles -> tensor memory once per work item (tcgen05.cp runs in issue order behind the MMAs
+                    // of the previous item): the MMAs then read only the caption operand from shared memory -- with
+                    // both operands in shared memory a 128 x 96 x 16 MMA needs 149 B/clk, above the 128 B/clk an SM has.
+                    for (int t = 0; t < ntv; ++t) {
+                        mbar_wait(&sb->vis_full, it_vis & 1);
+                        ++it_vis;
+                        tc_fence_after();
+#pragma unroll
+                        for (int c = 0; c < 2 * KB; ++c)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_cp_128x256b(tmem_base + (uint32_t)t * A_COLS + (uint32_t)(c * 32 + k * 8),
+                                               a_desc0 + (uint64_t)(c * (CHUNK_A >> 4) + k * 2));
+                        tc_commit(&sb->vis_empty);  // the shared-memory copy may be replaced as soon as the copies retire
+                    }
+                } else {
+                    mbar_wait(&sb->vis_full, it_vis & 1);
+                    ++it_vis;
+                }
                 const int ntile = (b1 - b0) * QT;
-                for (int t = 0; t < ntile; ++t) {
-                    const int s = it_txt % S, acc = it_txt % NACC;
-                    mbar_wait(&sb->txt_full[s], (it_txt / S) & 1);
-                    mbar_wait(&sb->acc_empty[acc], ((it_txt / NACC) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-                    const uint32_t a_base = smem_u32(s_vis), b_base = smem_u32(s_txt + (size_t)s * stage_bytes);
-                    uint32_t first = 0;
-                    // hi*hi + lo*hi + hi*lo  (parts: 0 = hi, 1 = lo)
+                for (int tile = 0; tile < ntile; ++tile) {
+                    mbar_wait(&sb->txt_full[s], s_phase);
+                    const uint64_t b_desc0 = smem_desc_sw128(smem_u32(s_txt + (size_t)s * stage_bytes));
+                    for (int t = 0; t < ntv; ++t) {
+                        mbar_wait(&sb->acc_empty[acc], acc_phase ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * acc_stride;
+                        const uint32_t a_tmem = tmem_base + (uint32_t)t * A_COLS;
+                        // hi*hi + lo*hi + hi*lo  (chunk index = part * KB + kb; parts: 0 = hi, 1 = lo)
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const int pa = term == 1 ? 1 : 0, pb = term == 2 ? 1 : 0;
-                        if (term > 0 && p.split == 1) break;
-                        for (int kb = 0; kb < KB; ++kb) {
-                            const uint64_t ad = smem_desc_sw128(a_base + (uint32_t)(pa * KB + kb) * CHUNK_A);
-                            const uint64_t bd = smem_desc_sw128(b_base + (uint32_t)(pb * KB + kb) * chunk_b);
+                        for (int term = 0; term < 3; ++term) {
+                            const int pa = term == 1 ? 1 : 0, pb = term == 2 ? 1 : 0;
+                            if ((term > 0 && p.split == 1) || (p.debug & 4)) break;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle atom
-                                tc_mma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first);
-                                first = 1;
+                            for (int kb = 0; kb < KB; ++kb) {
+                                const int ca = pa * KB + kb, cbk = pb * KB + kb;
+                                const uint64_t bd = b_desc0 + (uint64_t)cbk * cb4;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle atom
+                                    if (TS) {
+                                        const uint32_t at = a_tmem + (uint32_t)(ca * 32 + k * 8);
+                                        if (term == 0 && kb == 0 && k == 0) tc_mma_ts<0>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
+                                        else tc_mma_ts<1>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
+                                    } else {
+                                        const uint64_t ad = a_desc0 + (uint64_t)(ca * (CHUNK_A >> 4) + k * 2);
+                                        if (term == 0 && kb == 0 && k == 0) tc_mma_ss<0>(d_tmem, ad, bd + (uint64_t)(k * 2), idesc);
+                                        else tc_mma_ss<1>(d_tmem, ad, bd + (uint64_t)(k * 2), idesc);
+                                    }
+                                }
                             }
                         }
+                        tc_commit(&sb->acc_full[acc]);  // accumulator ready for the epilogue
+                        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                     }
                     tc_commit(&sb->txt_empty[s]);   // stage may be refilled once these MMAs have read it
-                    tc_commit(&sb->acc_full[acc]);  // accumulator ready for the epilogue
-                    ++it_txt;
+                    if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
                 }
-                tc_commit(&sb->vis_empty);  // the image tile may be replaced
+                if (!TS) tc_commit(&sb->vis_empty);  // the image tile may be replaced
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> masks -> global =====================
         const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;   // which of the two warps of the quadrant
-        uint32_t it_txt = 0;
+        const int half = (warp - 2) >> 2;   // which of the kEpiWarps / 4 warps of the quadrant
+        // The epilogue warps' own instruction stream bounds the kernel once the tensor pipe is fed (5 cycles per issued
+        // instruction per warp), so it is kept minimal: no divisions, accumulator index / phase carried incrementally,
+        // and per 16-query chunk a warp-uniform fast path (all queries kept -> address + store per element).
+        uint32_t acc = 0, acc_phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int a = item / (VT * BCH), rem = item - a * VT * BCH;
-            const int vt = rem / BCH, bc = rem - vt * BCH;
-            const int b0 = bc * b_per, b1 = min(p.B, b0 + b_per);
-            const int v = vt * TILE_M + quad * 32 + lane;
-            const bool v_ok = v < p.V;
-            const bool v_keep = v_ok && p.vis_mask[(size_t)a * p.V + v] != 0;
+            int a, vt0, ntv, b0, b1;
+            decode(item, a, vt0, ntv, b0, b1);
+            bool v_ok_t[PAIR], v_keep_t[PAIR];
+#pragma unroll
+            for (int t = 0; t < PAIR; ++t) {
+                const int vv = (vt0 + t) * TILE_M + quad * 32 + lane;
+                v_ok_t[t] = t < ntv && vv < p.V;
+                v_keep_t[t] = v_ok_t[t] && p.vis_mask[(size_t)a * p.V + vv] != 0;
+            }
             const uint32_t V = (uint32_t)p.ldv;  // row stride of the output (>= V; a multiple of 8 keeps stores sector-aligned)
-            const int ntile = (b1 - b0) * QT;
+            const float neg = p.neg;
+            const uint4 *mbp = reinterpret_cast<const uint4 *>(p.txt_maskbits) + (size_t)b0 * QT;
             // caption mask bits of the next tile are fetched while the current one is stored
-            uint4 mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + (size_t)b0 * QT * 4);
-            for (int t = 0; t < ntile; ++t) {
-                const int b = b0 + t / QT, qt = t - (t / QT) * QT;
-                const uint4 mb_cur = mb;
-                if (t + 1 < ntile) mb = *reinterpret_cast<const uint4 *>(p.txt_maskbits + ((size_t)b0 * QT + t + 1) * 4);
-                const int acc = it_txt % NACC;
-                mbar_wait(&sb->acc_full[acc], (it_txt / NACC) & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + (uint32_t)acc * 128u + ((uint32_t)(quad * 32) << 16);
-                const uint32_t mw[4] = {mb_cur.x, mb_cur.y, mb_cur.z, mb_cur.w};
-                const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
-                float *orow = p.out + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M) * p.ldv + v;
-                for (int c0 = half * 16; c0 < q_lim; c0 += 32) {
-                    uint32_t r[16];
-                    if (!(p.debug & 2)) tc_ld16(taddr + (uint32_t)c0, r);
-                    else { for (int j = 0; j < 16; ++j) r[j] = 0; }
-                    // bit j set = keep the score of query c0 + j for this factor; a masked factor clears them all
-                    const uint32_t w = v_keep ? (mw[c0 >> 5] >> (c0 & 31)) : 0u;
-                    float *o = orow + (size_t)c0 * V;
-                    if (v_ok && !(p.debug & 1)) {
-                        if (c0 + 16 <= q_lim) {
+            uint4 mb = mbp[0];
+            const size_t tile_rows = (size_t)TILE_M * V, cap_stride = (size_t)p.A * p.Q * V;
+            float *ob = p.out + ((size_t)b0 * p.A + a) * p.Q * V + vt0 * TILE_M + quad * 32 + lane;  // (b0, a, q = 0, v)
+            for (int b = b0; b < b1; ++b, ob += cap_stride) {
+                float *orow0 = ob;
+                for (int qt = 0; qt < QT; ++qt, orow0 += tile_rows) {
+                    const uint4 mb_cur = mb;
+                    ++mbp;
+                    if (b + 1 < b1 || qt + 1 < QT) mb = *mbp;
+                    const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)  // streaming stores: the result is written exactly once
-                                __stcs(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : p.neg);
-                        } else {
+                  for (int t = 0; t < PAIR; ++t) {
+                    if (t >= ntv) break;
+                    const int vt = vt0 + t;
+                    const bool v_ok = v_ok_t[t], v_keep = v_keep_t[t];
+                    float *orow = orow0 + t * TILE_M;
+                    mbar_wait(&sb->acc_full[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ACC_COL0 + acc * acc_stride + ((uint32_t)(quad * 32) << 16);
+                    if (BULK) {
+                        // The output tile is staged in shared memory ([query][128 factors] fp32) and written with one
+                        // 512 B bulk copy (TMA) per query row, so a row segment reaches L2 / HBM as one contiguous write
+                        // and the warps spend ~1 instruction per 16 B instead of 1 per 4 B. Per tile: all chunks
+                        // TMEM -> registers, accumulator released, masks, [previous tile's copies have left shared
+                        // memory], registers -> shared, proxy fence, barrier, <= 11 lanes per warp issue the rows.
+                        constexpr int MAXCH = 8 / (kEpiWarps / 4);  // 16-query chunks of one warp per tile
+                        uint32_t r[MAXCH][16];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < q_lim) __stcs(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : p.neg);
+                        for (int k = 0; k < MAXCH; ++k) {
+                            const int c0 = half * 16 + k * 4 * kEpiWarps;
+                            if (c0 < q_lim && !(p.debug & 2)) tc_ld16_nowait(taddr + (uint32_t)c0, r[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < MAXCH; ++k) tc_wait_ld(r[k]);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);  // the MMAs of a later tile may overwrite it
+#pragma unroll
+                        for (int k = 0; k < MAXCH; ++k) {
+                            const int c0 = half * 16 + k * 4 * kEpiWarps;
+                            const uint32_t w32 = c0 < 32 ? mb_cur.x : (c0 < 64 ? mb_cur.y : (c0 < 96 ? mb_cur.z : mb_cur.w));
+                            const uint32_t w = v_keep ? ((w32 >> (c0 & 31)) & 0xffffu) : 0u;
+                            if (w != 0xffffu) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (!((w >> j) & 1u)) r[k][j] = __float_as_uint(neg);
+                            }
+                        }
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        named_bar(1, 32 * kEpiWarps);
+#pragma unroll
+                        for (int k = 0; k < MAXCH; ++k) {
+                            const int c0 = half * 16 + k * 4 * kEpiWarps;
+                            if (c0 < q_lim) {
+                                float *slot = s_out + (size_t)c0 * TILE_M + quad * 32 + lane;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar(1, 32 * kEpiWarps);
+                        const int row = lane * kEpiWarps + (warp - 2);
+                        if (row < q_lim && !(p.debug & 1))
+                            bulk_s2g(orow - (quad * 32 + lane) + (size_t)row * V, s_out + (size_t)row * TILE_M,
+                                     min(TILE_M, p.ldv - vt * TILE_M) * 4);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                        continue;
+                    } else
+                    for (int c0 = half * 16; c0 < q_lim; c0 += 4 * kEpiWarps) {
+                        uint32_t r[16];
+                        if (!(p.debug & 2)) tc_ld16(taddr + (uint32_t)c0, r);
+                        else { for (int j = 0; j < 16; ++j) r[j] = 0; }
+                        // bit j set = keep the score of query c0 + j (same for every lane of the warp)
+                        const uint32_t w32 = c0 < 32 ? mb_cur.x : (c0 < 64 ? mb_cur.y : (c0 < 96 ? mb_cur.z : mb_cur.w));
+                        const uint32_t w = (w32 >> (c0 & 31)) & 0xffffu;
+                        float *o = orow + (size_t)c0 * V;
+                        if (!v_keep) {  // a masked factor: the whole row segment is -INF (rare, per lane)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(neg);
+                        }
+                        if (v_ok && !(p.debug & 1)) {
+                            if (c0 + 16 <= q_lim && w == 0xffffu) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)  // streaming stores: the result is written exactly once
+                                    ALIGN_ST(o + (uint32_t)j * V, __uint_as_float(r[j]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < q_lim) ALIGN_ST(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : neg);
+                            }
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
+                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+                  }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
-                ++it_txt;
             }
         }
+        if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -385,23 +606,43 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
     a.out = out; a.ldv = ldv; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.neg = neg; a.split = split == 1 ? 1 : 3;
     { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+    { const char *ts = getenv("VLGAE_ALIGN_A_TMEM"); a.a_in_tmem = ts ? atoi(ts) : 1; }
+    // bulk (TMA) stores need 16-byte aligned row segments
+    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = (bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0); }
     const size_t vis_bytes = pl.tile_bytes, stage_bytes = (size_t)2 * pl.KB * pl.nq * 128;
-    int stages = (int)(((size_t)g_align_smem - vis_bytes - 1024) / stage_bytes);
+    const size_t out_tile_bytes = a.bulk ? (size_t)pl.nq * 512 : 0;
+    int stages = (int)(((size_t)g_align_smem - vis_bytes - out_tile_bytes - 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 1) return cudaErrorInvalidValue;
     a.stages = stages;
-    const size_t smem_bytes = vis_bytes + (size_t)stages * stage_bytes + sizeof(AlignSmem) + 64;
-    // enough work items for ~4 waves of persistent CTAs: split the captions of one (image, v-tile) into chunks
+    const size_t smem_bytes = vis_bytes + (size_t)stages * stage_bytes + out_tile_bytes + sizeof(AlignSmem) + 64;
+    // Work items are dealt round-robin to the persistent CTAs: split the captions of one (image, v-tile group) into
+    // chunks until every CTA gets >= 16 items, so the uneven last round costs a few per cent at most.
+    const int pair = a.a_in_tmem ? 2 : 1;
+    const long long groups = (long long)A * ((pl.VT + pair - 1) / pair);
     int bch = 1;
-    while ((long long)A * pl.VT * bch < 4LL * g_align_sm && bch < B) bch <<= 1;
+    while (groups * bch < 16LL * g_align_sm && bch < B) bch <<= 1;
     if (bch > B) bch = B;
     a.BCH = bch;
-    e = cudaFuncSetAttribute(align_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
     int grid = g_align_sm;
-    if (grid > A * pl.VT * bch) grid = A * pl.VT * bch;
-    align_gemm_kernel<<<grid, kThreads, smem_bytes, st>>>(a);
-    return cudaGetLastError();
+    if (grid > groups * bch) grid = (int)(groups * bch);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, kThreads, smem_bytes, st>>>(a);
+        return cudaGetLastError();
+    };
+    const int variant = (pl.KB == 1 ? 0 : 4) | (a.a_in_tmem ? 2 : 0) | (a.bulk ? 1 : 0);
+    switch (variant) {
+        case 0: return launch(align_gemm_kernel<1, false, false>);
+        case 1: return launch(align_gemm_kernel<1, false, true>);
+        case 2: return launch(align_gemm_kernel<1, true, false>);
+        case 3: return launch(align_gemm_kernel<1, true, true>);
+        case 4: return launch(align_gemm_kernel<2, false, false>);
+        case 5: return launch(align_gemm_kernel<2, false, true>);
+        case 6: return launch(align_gemm_kernel<2, true, false>);
+        default: return launch(align_gemm_kernel<2, true, true>);
+    }
 }
 
 }  // namespace vlgae

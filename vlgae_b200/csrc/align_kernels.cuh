@@ -15,7 +15,7 @@ struct AlignArgs {
     int ldv;
     int A, V, B, Q;
     int KB, VT, QT, nq;  // k-blocks of 64, v-tiles, q-tiles, padded queries per tile (multiple of 16, <= 128)
-    int BCH, stages, split, debug;
+    int BCH, stages, split, debug, a_in_tmem, bulk;
     float neg;
 };
 
