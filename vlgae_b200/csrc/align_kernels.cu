@@ -6,51 +6,44 @@
 // contraction, both masks and the store are one kernel, and the result is written exactly once.
 //
 // Mapping onto tcgen05:  D[v][q] = sum_d vis[a, v, d] * txt[b, q, d]
-//   M = 128 factors v of one image a      (operand A, K-major, resident in shared memory for a whole work item)
-//   N = Q queries of one caption b, <= 128 (operand B, K-major, streamed through a ring of shared-memory stages)
+//   M = 128 factors v of one image a      (operand A, in TENSOR MEMORY: two tiles = 256 factors stay resident per CTA)
+//   N = Q queries of one caption b, <= 128 (operand B, K-major, streamed through a ring of shared-memory slots)
 //   K = D <= 128
 // so that TMEM lane = v and TMEM column = q: the 32 threads of an epilogue warp hold 32 consecutive v of one q in
-// the same register, and a store of that register is one coalesced 128-byte row segment of attmap[b, a, q, :].
+// the same register -- a conflict-free shared-memory row segment of the staged output tile [q][128 v].
 //
-// Precision: operands are split on the fly into bf16 hi + bf16 lo (x = hi + lo + O(2^-17 x)) and three MMAs
-// accumulate hi*hi + lo*hi + hi*lo in fp32 TMEM -- fp32-class logits (|err| ~ 1e-5 |x||y| sqrt(D)) from the bf16 pipe.
+// Precision: operands are split into bf16 hi + bf16 lo (x = hi + lo + O(2^-17 x)) and three MMAs accumulate
+// hi*hi + lo*hi + hi*lo in fp32 TMEM -- fp32-class logits (|err| ~ 1e-5 |x||y| sqrt(D)) from the bf16 pipe.
 //
 // Data movement: a pre-pass (align_pack_kernel) writes both operands as bf16 tiles that are already the 128-byte
 // swizzled shared-memory image tcgen05 expects, so the main kernel moves them with plain 1-D bulk TMA copies
-// (cp.async.bulk ... mbarrier::complete_tx) -- no tensor maps.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer
-// (+ TMEM allocation), warps 2-9 = epilogue (TMEM -> registers -> masks -> global).  Four TMEM accumulators of 128
-// columns let the MMAs of tile i+1.. overlap the stores of tile i.
+// (cp.async.bulk ... mbarrier::complete_tx) -- no tensor maps. The result leaves through bulk TMA stores as well.
+// Warp roles (18 warps, one persistent CTA per SM):
+//   warp 0      TMA producer: image-tile chunks and caption tiles into the ring
+//   warp 1      MMA issuer (converged warp, elect.sync): tcgen05.cp image tile -> TMEM, 24 TS-form MMAs per tile pair
+//   warps 2-9   epilogue team 0, warps 10-17 epilogue team 1: alternate accumulators; TMEM -> registers -> vis mask ->
+//               staged tile in shared memory -> one 512 B cp.async.bulk store per query row (masked queries copy a
+//               constant row of -INF instead)
+// What bounds it (cfg2 shape, measured): an SM's path to L2 takes ~19 B/clk of stores whichever way they are issued
+// (5.3 TB/s for the chip at full clock, tools/probes/), and the tensor work holds the clock near 1.6 GHz.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
 
 #include "align_kernels.cuh"
-
-#ifndef VLGAE_ST_MODE
-#define VLGAE_ST_MODE 0
-#endif
-#if VLGAE_ST_MODE == 0
-#define ALIGN_ST(p, v) __stcs(p, v)
-#elif VLGAE_ST_MODE == 1
-#define ALIGN_ST(p, v) (*(p) = (v))
-#elif VLGAE_ST_MODE == 2
-#define ALIGN_ST(p, v) __stcg(p, v)
-#else
-#define ALIGN_ST(p, v) __stwt(p, v)
-#endif
+#include "dmv_kernels.cuh"
 
 namespace vlgae {
 namespace {
 
 constexpr int TILE_M = 128;          // factors per tile (TMEM lanes)
 constexpr int CHUNK_A = TILE_M * 128;  // bytes of one (part, k-block) chunk of operand A: 128 rows x 64 bf16
-constexpr int MAX_ACC = 8;           // TMEM accumulators: as many as fit behind operand A (columns 0..127), stride = nq rounded to 32
-#ifndef VLGAE_EPI_WARPS
-#define VLGAE_EPI_WARPS 8
-#endif
-constexpr int kEpiWarps = VLGAE_EPI_WARPS;  // kEpiWarps / 4 warps per TMEM lane quadrant, interleaved over 16-column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int MAX_ACC = 2;           // TMEM accumulators behind the two image tiles, stride = nq rounded to 32
+constexpr int kTeamWarps = 8;  // an epilogue team: 2 warps per TMEM lane quadrant, interleaved over 16-column chunks
+constexpr int kTeams = 2;      // teams take alternate accumulators, so one stages / stores while the other unloads TMEM
+constexpr int kEpiWarps = kTeamWarps;  // (per team)
+constexpr int kThreads = 64 + 32 * kTeamWarps * kTeams;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -83,49 +76,37 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// Variants for a converged warp: every lane executes the call, one elected lane issues. Inside `if (lane == 0)` the
+// compiler must treat the operands as per-thread values and wraps every tcgen05 instruction in an ELECT / R2UR / branch
+// sequence (~8 instructions, ~70 clk per MMA -- more than the 48 clk the MMA itself takes); in converged code the
+// descriptors stay in uniform registers.
+__device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// variants with a compile-time accumulate flag (no predicate set-up from a register in the issue loop)
-template <int ACC>
-__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar)) : "memory");
 }
 template <int ACC>
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+__device__ __forceinline__ void tc_mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "n"(ACC) : "memory");
 }
-// A operand from tensor memory (TS form): lane = row of A, 8 columns (16 bf16 along K) per MMA
-__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_cp_128x256b_elect(uint32_t dst_tmem, uint64_t sdesc) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.cp.cta_group::1.128x256b [%0], %1;\n\t"
+        "}" ::"r"(dst_tmem), "l"(sdesc) : "memory");
 }
 // shared memory -> tensor memory: 128 rows x 256 bits (one UMMA_K slice of a K-major operand), lanes = rows
-__device__ __forceinline__ void tc_cp_128x256b(uint32_t dst_tmem, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(dst_tmem), "l"(sdesc) : "memory");
-}
 
 // 32 lanes x 16 columns of fp32: thread i of the warp gets lane (quadrant*32 + i), columns c0 .. c0+15
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -172,16 +153,6 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 // shared -> global bulk copy (TMA), tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(float *dst, const float *src, int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-// wait until at most `pending` of this thread's bulk groups still read shared memory
-__device__ __forceinline__ void bulk_wait_read(int pending) {
-    switch (pending) {
-        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
-        default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,53 +208,61 @@ __global__ void align_pack_kernel(const float *__restrict__ x, const uint8_t *__
 // main kernel
 // ---------------------------------------------------------------------------------------------
 struct AlignSmem {
-    uint64_t vis_full, vis_empty;
-    uint64_t txt_full[8], txt_empty[8];
+    uint64_t ring_full[8], ring_empty[8];
     uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
     uint32_t tmem_base;
 };
 
-template <int KB, bool TS, bool BULK>
+// Shared memory:  [ring: S slots of slot_bytes][BULK: NB output tiles of nq x 128 fp32][AlignSmem]
+//   A ring slot holds either one caption tile (2*KB chunks of nq rows x 128 B: hi k-blocks, lo k-blocks) or up to
+//   slot_bytes / 16 KB chunks of an image tile on their way to tensor memory -- the image tiles travel through the same
+//   ring as the captions, so no shared memory is reserved for them and the ring never drains between work items.
+// Tensor memory (512 columns): [image tile 0: 64*KB columns][image tile 1][accumulators, stride = nq rounded to 32]
+//   A CTA keeps TWO image tiles (256 factors) resident and runs every caption tile against both (TS-form MMA, operand A
+//   from tensor memory): with one tile the kernel streams as many caption bytes L2 -> SM as it writes, and the L2
+//   slices, which carry the reads, the writes and the write-back together, are what saturates.
+template <int KB, bool BULK>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // [vis tile: 2*KB chunks of 16 KB][stage 0: 2*KB chunks of nq*128 B] ... [BULK: output tile nq x 128 fp32][AlignSmem]
-    const int nq = p.nq, S = p.stages;
-    const uint32_t vis_bytes = 2u * KB * CHUNK_A;
-    const uint32_t chunk_b = (uint32_t)nq * 128u;
-    const uint32_t stage_bytes = 2u * KB * chunk_b;
-    uint8_t *s_vis = smem;
-    uint8_t *s_txt = smem + vis_bytes;
-    float *s_out = reinterpret_cast<float *>(smem + vis_bytes + (size_t)S * stage_bytes);
-    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + vis_bytes + (size_t)S * stage_bytes + (BULK ? (size_t)nq * 512 : 0));
+    const int nq = p.nq, S = p.stages, NB = p.out_bufs;
+    const uint32_t chunk_b = (uint32_t)nq * 128u;         // one (part, k-block) chunk of a caption tile
+    const uint32_t txt_bytes = 2u * KB * chunk_b;           // a caption tile in a slot
+    const uint32_t slot_bytes = p.slot_bytes;               // >= txt_bytes and >= one image chunk
+    const int cps = (int)(slot_bytes / CHUNK_A);            // image chunks per slot
+    constexpr int PAIR = 2;
+    constexpr uint32_t A_COLS = 64u * KB;  // tensor-memory columns of one image tile (hi + lo, 32 per 64-wide k-block)
+    uint8_t *s_ring = smem;
+    float *s_out = reinterpret_cast<float *>(smem + (size_t)S * slot_bytes);
+    const size_t out_tile_floats = (size_t)p.out_rows * TILE_M;  // rows = min(nq, Q): the queries a tile can hold
+    float *s_neg = s_out + (size_t)NB * out_tile_floats;  // BULK: one row of -INF, the source of masked query rows
+    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + (size_t)S * slot_bytes + (BULK ? (size_t)NB * p.out_rows * 512 + 512 : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(&sb->vis_full, 1);
-        mbar_init(&sb->vis_empty, 1);
-        for (int s = 0; s < S; ++s) { mbar_init(&sb->txt_full[s], 1); mbar_init(&sb->txt_empty[s], 1); }
-        for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], kEpiWarps); }
+        for (int s = 0; s < S; ++s) { mbar_init(&sb->ring_full[s], 1); mbar_init(&sb->ring_empty[s], 1); }
+        for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&sb->acc_full[a], 1); mbar_init(&sb->acc_empty[a], kTeamWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sb->tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    if (BULK && threadIdx.x >= 64 && threadIdx.x < 64 + TILE_M) {
+        s_neg[threadIdx.x - 64] = p.neg;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // the swizzled tile images need 1024-byte alignment
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sb->tmem_base;
-    // TS: a CTA keeps TWO image tiles (256 factors) in tensor memory and runs every caption tile against both, which
-    // halves the caption bytes streamed from L2 per output byte -- with one tile the kernel moves as many bytes L2 -> SM
-    // as it writes, and the L2 slices (~12 TB/s for reads + writes + write-back together) are what saturates.
-    constexpr int PAIR = TS ? 2 : 1;
-    constexpr uint32_t A_COLS = 64u * KB;  // tensor-memory columns of one image tile (hi + lo, 32 per 64-wide k-block)
-    const uint32_t ACC_COL0 = TS ? PAIR * A_COLS : 0u, acc_stride = (uint32_t)((nq + 31) & ~31);
-    const uint32_t NACC = min((uint32_t)MAX_ACC, (512u - ACC_COL0) / acc_stride);
+    const uint32_t ACC_COL0 = PAIR * A_COLS, acc_stride = (uint32_t)((nq + 31) & ~31);
+    constexpr uint32_t NACC = MAX_ACC;
 
     // work items: (a, group of PAIR v-tiles, chunk of captions) -- full groups first, the odd last v-tiles after them, so
     // that the static round-robin deal stays balanced; tiles inside an item: (b, q-tile, v-tile of the group)
     const int VT = p.VT, QT = p.QT, BCH = p.BCH;
-    const int VG = VT / PAIR;                        // full groups per image
+    const int VG = VT / PAIR;  // full groups per image
     const int n_full = p.A * VG * BCH;
     const int n_items = n_full + (VT % PAIR ? p.A * BCH : 0);
     const int b_per = (p.B + BCH - 1) / BCH;
@@ -292,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         if (item < n_full) {
             a = item / (VG * BCH);
             const int rem = item - a * VG * BCH;
-            const int g = rem / BCH;
-            bc = rem - g * BCH;
+            bc = rem / VG;  // v-tile group fastest: neighbouring CTAs write neighbouring segments of the same rows
+            const int g = rem - bc * VG;
             vt0 = g * PAIR;
             ntv = PAIR;
         } else {
@@ -310,28 +289,32 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it_vis = 0, s = 0, s_phase = 0;
+            uint32_t s = 0, s_phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int a, vt0, ntv, b0, b1;
                 decode(item, a, vt0, ntv, b0, b1);
-                for (int t = 0; t < ntv; ++t) {  // TS: one after the other through the same buffer (copied on to TMEM)
-                    mbar_wait(&sb->vis_empty, (it_vis & 1) ^ 1);
-                    mbar_expect_tx(&sb->vis_full, vis_bytes);
-                    bulk_g2s(s_vis, p.vis_packed + ((size_t)a * VT + vt0 + t) * vis_bytes, vis_bytes, &sb->vis_full);
-                    ++it_vis;
+                for (int t = 0; t < ntv; ++t) {  // image tiles: 2*KB chunks of 16 KB, `cps` per slot
+                    const uint8_t *src = p.vis_packed + ((size_t)a * VT + vt0 + t) * (size_t)(2 * KB * CHUNK_A);
+                    for (int c = 0; c < 2 * KB; c += cps) {
+                        const uint32_t bytes = (uint32_t)min(cps, 2 * KB - c) * CHUNK_A;
+                        mbar_wait(&sb->ring_empty[s], s_phase ^ 1);
+                        mbar_expect_tx(&sb->ring_full[s], bytes);
+                        bulk_g2s(s_ring + (size_t)s * slot_bytes, src + (size_t)c * CHUNK_A, bytes, &sb->ring_full[s]);
+                        if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
+                    }
                 }
                 for (int b = b0; b < b1; ++b)
                     for (int qt = 0; qt < QT; ++qt) {
-                        mbar_wait(&sb->txt_empty[s], s_phase ^ 1);
+                        mbar_wait(&sb->ring_empty[s], s_phase ^ 1);
                         if (p.debug & 8) {  // measurement aid: no caption traffic
-                            mbar_arrive(&sb->txt_full[s]);
+                            mbar_arrive(&sb->ring_full[s]);
                         } else {
-                            mbar_expect_tx(&sb->txt_full[s], stage_bytes);
+                            mbar_expect_tx(&sb->ring_full[s], txt_bytes);
                             // the packed caption tile has chunks of 128 rows; copy the first nq rows of each chunk
                             const uint8_t *src = p.txt_packed + ((size_t)b * QT + qt) * (size_t)(2 * KB * CHUNK_A);
                             for (int ch = 0; ch < 2 * KB; ++ch)
-                                bulk_g2s(s_txt + (size_t)s * stage_bytes + (size_t)ch * chunk_b, src + (size_t)ch * CHUNK_A,
-                                         chunk_b, &sb->txt_full[s]);
+                                bulk_g2s(s_ring + (size_t)s * slot_bytes + (size_t)ch * chunk_b, src + (size_t)ch * CHUNK_A,
+                                         chunk_b, &sb->ring_full[s]);
                         }
                         if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
                     }
@@ -340,41 +323,46 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // One thread issues every MMA, so its instruction stream must stay well under the tensor time of a tile
-        // (24 MMAs x 48 clk): descriptors are formed once per tile / per item and advanced by compile-time constants.
-        if (lane == 0) {
+        // (24 MMAs x 48 clk): descriptors are formed once per tile and advanced by compile-time constants.
+        {   // the whole warp runs this converged; one elected lane issues each tcgen05 instruction
             const uint32_t idesc = idesc_bf16(TILE_M, nq);
             const uint64_t cb4 = (uint64_t)(chunk_b >> 4);  // descriptor units (16 B) between caption chunks
-            uint32_t it_vis = 0, s = 0, s_phase = 0, acc = 0, acc_phase = 0;
+            uint32_t s = 0, s_phase = 0, acc = 0, acc_phase = 0;
+            long long t_ring = 0, t_acc = 0, t_vis = 0;
+            const long long t_begin = clock64();
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int a, vt0, ntv, b0, b1;
                 decode(item, a, vt0, ntv, b0, b1);
-                const uint64_t a_desc0 = smem_desc_sw128(smem_u32(s_vis));
-                if (TS) {
-                    // Image tiles -> tensor memory once per work item (tcgen05.cp runs in issue order behind the MMAs
-                    // of the previous item): the MMAs then read only the caption operand from shared memory -- with
-                    // both operands in shared memory a 128 x 96 x 16 MMA needs 149 B/clk, above the 128 B/clk an SM has.
-                    for (int t = 0; t < ntv; ++t) {
-                        mbar_wait(&sb->vis_full, it_vis & 1);
-                        ++it_vis;
+                const long long tv0 = clock64();
+                // Image tiles -> tensor memory once per work item. tcgen05.cp executes in issue order behind the MMAs
+                // of the previous item, which still read the old tiles. With operand A in tensor memory the MMAs read
+                // only the caption operand from shared memory -- with both operands there a 128 x 96 x 16 MMA needs
+                // 149 B/clk, more than the 128 B/clk an SM's shared memory delivers.
+                for (int t = 0; t < ntv; ++t)
+                    for (int c = 0; c < 2 * KB; c += cps) {
+                        mbar_wait(&sb->ring_full[s], s_phase);
                         tc_fence_after();
-#pragma unroll
-                        for (int c = 0; c < 2 * KB; ++c)
+                        const uint64_t desc0 = smem_desc_sw128(smem_u32(s_ring + (size_t)s * slot_bytes));
+                        const int n = min(cps, 2 * KB - c);
+                        for (int j = 0; j < n; ++j)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_cp_128x256b(tmem_base + (uint32_t)t * A_COLS + (uint32_t)(c * 32 + k * 8),
-                                               a_desc0 + (uint64_t)(c * (CHUNK_A >> 4) + k * 2));
-                        tc_commit(&sb->vis_empty);  // the shared-memory copy may be replaced as soon as the copies retire
+                                tc_cp_128x256b_elect(tmem_base + (uint32_t)t * A_COLS + (uint32_t)((c + j) * 32 + k * 8),
+                                               desc0 + (uint64_t)(j * (CHUNK_A >> 4) + k * 2));
+                        tc_commit_elect(&sb->ring_empty[s]);  // the slot may be refilled as soon as the copies retire
+                        if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
                     }
-                } else {
-                    mbar_wait(&sb->vis_full, it_vis & 1);
-                    ++it_vis;
-                }
                 const int ntile = (b1 - b0) * QT;
+                t_vis += clock64() - tv0;
                 for (int tile = 0; tile < ntile; ++tile) {
-                    mbar_wait(&sb->txt_full[s], s_phase);
-                    const uint64_t b_desc0 = smem_desc_sw128(smem_u32(s_txt + (size_t)s * stage_bytes));
+                    const long long tr0 = clock64();
+                    mbar_wait(&sb->ring_full[s], s_phase);
+                    t_ring += clock64() - tr0;
+                    const uint64_t b_desc0 = smem_desc_sw128(smem_u32(s_ring + (size_t)s * slot_bytes));
                     for (int t = 0; t < ntv; ++t) {
+                        const long long ta0 = clock64();
                         mbar_wait(&sb->acc_empty[acc], acc_phase ^ 1);
+                        t_acc += clock64() - ta0;
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + ACC_COL0 + acc * acc_stride;
                         const uint32_t a_tmem = tmem_base + (uint32_t)t * A_COLS;
@@ -389,36 +377,37 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                 const uint64_t bd = b_desc0 + (uint64_t)cbk * cb4;
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle atom
-                                    if (TS) {
-                                        const uint32_t at = a_tmem + (uint32_t)(ca * 32 + k * 8);
-                                        if (term == 0 && kb == 0 && k == 0) tc_mma_ts<0>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
-                                        else tc_mma_ts<1>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
-                                    } else {
-                                        const uint64_t ad = a_desc0 + (uint64_t)(ca * (CHUNK_A >> 4) + k * 2);
-                                        if (term == 0 && kb == 0 && k == 0) tc_mma_ss<0>(d_tmem, ad, bd + (uint64_t)(k * 2), idesc);
-                                        else tc_mma_ss<1>(d_tmem, ad, bd + (uint64_t)(k * 2), idesc);
-                                    }
+                                    const uint32_t at = a_tmem + (uint32_t)(ca * 32 + k * 8);
+                                    if (term == 0 && kb == 0 && k == 0) tc_mma_ts_elect<0>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
+                                    else tc_mma_ts_elect<1>(d_tmem, at, bd + (uint64_t)(k * 2), idesc);
                                 }
                             }
                         }
-                        tc_commit(&sb->acc_full[acc]);  // accumulator ready for the epilogue
+                        tc_commit_elect(&sb->acc_full[acc]);  // accumulator ready for the epilogue
                         if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
                     }
-                    tc_commit(&sb->txt_empty[s]);   // stage may be refilled once these MMAs have read it
+                    tc_commit_elect(&sb->ring_empty[s]);  // slot may be refilled once these MMAs have read it
                     if (++s == (uint32_t)S) { s = 0; s_phase ^= 1; }
                 }
-                if (!TS) tc_commit(&sb->vis_empty);  // the image tile may be replaced
+            }
+            if (p.prof && lane == 0) {
+                long long *o = p.prof + (size_t)blockIdx.x * 8;
+                o[0] = clock64() - t_begin; o[1] = t_ring; o[2] = t_acc; o[3] = t_vis;
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> masks -> global =====================
-        const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;   // which of the kEpiWarps / 4 warps of the quadrant
-        // The epilogue warps' own instruction stream bounds the kernel once the tensor pipe is fed (5 cycles per issued
-        // instruction per warp), so it is kept minimal: no divisions, accumulator index / phase carried incrementally,
-        // and per 16-query chunk a warp-uniform fast path (all queries kept -> address + store per element).
-        uint32_t acc = 0, acc_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        // ===================== epilogue: TMEM -> registers -> masks -> (shared ->) global =====================
+        // Per (caption tile, image tile) the serial chain of one team -- wait, TMEM -> registers, barrier, registers ->
+        // shared, proxy fence, barrier, issue -- is ~1.7k clk, longer than the tensor time of the tile (1.2k clk); two
+        // teams on alternate accumulators (each with its own staging tile) take it off the critical path.
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int team = (warp - 2) / kTeamWarps;        // accumulator / staging tile this warp serves
+        const int tw = (warp - 2) % kTeamWarps;
+        const int half = tw >> 2;                        // which of the 2 warps of the quadrant
+        constexpr int MAXCH = 8 / (kEpiWarps / 4);       // 16-query chunks of one warp per tile
+        const int T = p.teams;                           // 1: team 0 serves both accumulators (one staging tile fits)
+        uint32_t gcount = 0;
+        for (int item = blockIdx.x; team < T && item < n_items; item += gridDim.x) {
             int a, vt0, ntv, b0, b1;
             decode(item, a, vt0, ntv, b0, b1);
             bool v_ok_t[PAIR], v_keep_t[PAIR];
@@ -428,11 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                 v_ok_t[t] = t < ntv && vv < p.V;
                 v_keep_t[t] = v_ok_t[t] && p.vis_mask[(size_t)a * p.V + vv] != 0;
             }
-            const uint32_t V = (uint32_t)p.ldv;  // row stride of the output (>= V; a multiple of 8 keeps stores sector-aligned)
+            const uint32_t V = (uint32_t)p.ldv;  // row stride of the output (>= V)
             const float neg = p.neg;
             const uint4 *mbp = reinterpret_cast<const uint4 *>(p.txt_maskbits) + (size_t)b0 * QT;
-            // caption mask bits of the next tile are fetched while the current one is stored
-            uint4 mb = mbp[0];
+            uint4 mb = mbp[0];  // caption mask bits of the next tile are fetched while the current one is stored
             const size_t tile_rows = (size_t)TILE_M * V, cap_stride = (size_t)p.A * p.Q * V;
             float *ob = p.out + ((size_t)b0 * p.A + a) * p.Q * V + vt0 * TILE_M + quad * 32 + lane;  // (b0, a, q = 0, v)
             for (int b = b0; b < b1; ++b, ob += cap_stride) {
@@ -443,21 +431,36 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                     if (b + 1 < b1 || qt + 1 < QT) mb = *mbp;
                     const int q_lim = min(TILE_M, p.Q - qt * TILE_M);
 #pragma unroll
-                  for (int t = 0; t < PAIR; ++t) {
-                    if (t >= ntv) break;
-                    const int vt = vt0 + t;
-                    const bool v_ok = v_ok_t[t], v_keep = v_keep_t[t];
-                    float *orow = orow0 + t * TILE_M;
-                    mbar_wait(&sb->acc_full[acc], acc_phase);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + ACC_COL0 + acc * acc_stride + ((uint32_t)(quad * 32) << 16);
-                    if (BULK) {
-                        // The output tile is staged in shared memory ([query][128 factors] fp32) and written with one
-                        // 512 B bulk copy (TMA) per query row, so a row segment reaches L2 / HBM as one contiguous write
-                        // and the warps spend ~1 instruction per 16 B instead of 1 per 4 B. Per tile: all chunks
-                        // TMEM -> registers, accumulator released, masks, [previous tile's copies have left shared
-                        // memory], registers -> shared, proxy fence, barrier, <= 11 lanes per warp issue the rows.
-                        constexpr int MAXCH = 8 / (kEpiWarps / 4);  // 16-query chunks of one warp per tile
+                    for (int t = 0; t < PAIR; ++t) {
+                        if (t >= ntv) break;
+                        const uint32_t acc = gcount & 1u, acc_phase = (gcount >> 1) & 1u;
+                        ++gcount;
+                        if (T == 2 && acc != (uint32_t)team) continue;
+                        const bool v_ok = v_ok_t[t], v_keep = v_keep_t[t];
+                        float *orow = orow0 + t * TILE_M;
+                        mbar_wait(&sb->acc_full[acc], acc_phase);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ACC_COL0 + acc * acc_stride + ((uint32_t)(quad * 32) << 16);
+                        if constexpr (!BULK) {
+                            // rows that are not 16-byte aligned (odd V without padding): chunk by chunk, one coalesced
+                            // 128 B streaming store per (query, 32 factors)
+                            for (int c0 = half * 16; c0 < q_lim; c0 += 4 * kEpiWarps) {
+                                uint32_t r[16];
+                                tc_ld16(taddr + (uint32_t)c0, r);
+                                const uint32_t w32 = c0 < 32 ? mb_cur.x : (c0 < 64 ? mb_cur.y : (c0 < 96 ? mb_cur.z : mb_cur.w));
+                                const uint32_t w = v_keep ? (w32 >> (c0 & 31)) : 0u;  // bit j = keep the score of query c0 + j
+                                float *o = orow + (size_t)c0 * V;
+                                if (v_ok && !(p.debug & 1)) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (c0 + j < q_lim) __stcs(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : neg);
+                                }
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
+                        } else {
+                        // all chunks of this warp TMEM -> registers, then the accumulator goes back to the MMA warp
                         uint32_t r[MAXCH][16];
 #pragma unroll
                         for (int k = 0; k < MAXCH; ++k) {
@@ -468,68 +471,49 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                         for (int k = 0; k < MAXCH; ++k) tc_wait_ld(r[k]);
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);  // the MMAs of a later tile may overwrite it
+                        if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
+                        if (!v_keep) {  // a masked factor: -INF for every query (per lane, rare)
 #pragma unroll
-                        for (int k = 0; k < MAXCH; ++k) {
-                            const int c0 = half * 16 + k * 4 * kEpiWarps;
-                            const uint32_t w32 = c0 < 32 ? mb_cur.x : (c0 < 64 ? mb_cur.y : (c0 < 96 ? mb_cur.z : mb_cur.w));
-                            const uint32_t w = v_keep ? ((w32 >> (c0 & 31)) & 0xffffu) : 0u;
-                            if (w != 0xffffu) {
+                            for (int k = 0; k < MAXCH; ++k)
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (!((w >> j) & 1u)) r[k][j] = __float_as_uint(neg);
-                            }
+                                for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(neg);
                         }
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        named_bar(1, 32 * kEpiWarps);
+                        {
+                            // The tile is staged in shared memory ([query][128 factors] fp32) and written with one
+                            // 512 B bulk copy (TMA) per query row: a row segment reaches L2 as one contiguous write and
+                            // the warps spend 1 instruction per 4 B on shared memory only. NB tiles alternate, so the
+                            // engine drains one while the next is staged.
+                            float *tile_out = s_out + (size_t)team * out_tile_floats;
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            named_bar(1 + team, 32 * kTeamWarps);  // every issuer's copies out of this tile have been read
 #pragma unroll
-                        for (int k = 0; k < MAXCH; ++k) {
-                            const int c0 = half * 16 + k * 4 * kEpiWarps;
-                            if (c0 < q_lim) {
-                                float *slot = s_out + (size_t)c0 * TILE_M + quad * 32 + lane;
+                            for (int k = 0; k < MAXCH; ++k) {
+                                const int c0 = half * 16 + k * 4 * kEpiWarps;
+                                float *slot = tile_out + (size_t)c0 * TILE_M + quad * 32 + lane;
+                                if (c0 + 16 <= q_lim) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                                    for (int j = 0; j < 16; ++j) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (c0 + j < q_lim) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                                }
                             }
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        named_bar(1, 32 * kEpiWarps);
-                        const int row = lane * kEpiWarps + (warp - 2);
-                        if (row < q_lim && !(p.debug & 1))
-                            bulk_s2g(orow - (quad * 32 + lane) + (size_t)row * V, s_out + (size_t)row * TILE_M,
-                                     min(TILE_M, p.ldv - vt * TILE_M) * 4);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-                        continue;
-                    } else
-                    for (int c0 = half * 16; c0 < q_lim; c0 += 4 * kEpiWarps) {
-                        uint32_t r[16];
-                        if (!(p.debug & 2)) tc_ld16(taddr + (uint32_t)c0, r);
-                        else { for (int j = 0; j < 16; ++j) r[j] = 0; }
-                        // bit j set = keep the score of query c0 + j (same for every lane of the warp)
-                        const uint32_t w32 = c0 < 32 ? mb_cur.x : (c0 < 64 ? mb_cur.y : (c0 < 96 ? mb_cur.z : mb_cur.w));
-                        const uint32_t w = (w32 >> (c0 & 31)) & 0xffffu;
-                        float *o = orow + (size_t)c0 * V;
-                        if (!v_keep) {  // a masked factor: the whole row segment is -INF (rare, per lane)
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(neg);
-                        }
-                        if (v_ok && !(p.debug & 1)) {
-                            if (c0 + 16 <= q_lim && w == 0xffffu) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)  // streaming stores: the result is written exactly once
-                                    ALIGN_ST(o + (uint32_t)j * V, __uint_as_float(r[j]));
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    if (c0 + j < q_lim) ALIGN_ST(o + (uint32_t)j * V, ((w >> j) & 1u) ? __uint_as_float(r[j]) : neg);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            named_bar(1 + team, 32 * kTeamWarps);
+                            // a masked query is a row of -INF: its copy reads the constant row instead of the tile,
+                            // so the caption mask costs the warps nothing
+                            const int row = lane * kTeamWarps + tw;  // <= 16 issuing lanes per warp
+                            if (row < q_lim && !(p.debug & 1)) {
+                                const uint32_t w32 = row < 32 ? mb_cur.x : (row < 64 ? mb_cur.y : (row < 96 ? mb_cur.z : mb_cur.w));
+                                const bool keep = (w32 >> (row & 31)) & 1u;
+                                bulk_s2g(orow - (quad * 32 + lane) + (size_t)row * V, keep ? tile_out + (size_t)row * TILE_M : s_neg,
+                                         min(TILE_M, p.ldv - (vt0 + t) * TILE_M) * 4);
                             }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                         }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sb->acc_empty[acc]);
-                    if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-                  }
                 }
             }
         }
@@ -543,13 +527,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     }
 }
 
-}  // namespace
-
-// ---------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------
-static int g_align_sm = 0, g_align_smem = 0;
-static cudaError_t align_device_info() {
+int g_align_sm = 0, g_align_smem = 0;
+cudaError_t align_device_info() {
     if (g_align_sm) return cudaSuccess;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -558,6 +537,8 @@ static cudaError_t align_device_info() {
     if (e != cudaSuccess) return e;
     return cudaDeviceGetAttribute(&g_align_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 }
+
+}  // namespace
 
 AlignPlan align_plan(int A, int V, int B, int Q, int D) {
     AlignPlan pl{};
@@ -605,21 +586,26 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
     a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;
     a.out = out; a.ldv = ldv; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.neg = neg; a.split = split == 1 ? 1 : 3;
-    { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
-    { const char *ts = getenv("VLGAE_ALIGN_A_TMEM"); a.a_in_tmem = ts ? atoi(ts) : 1; }
-    // bulk (TMA) stores need 16-byte aligned row segments
+    { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }  // measurement aids, see the kernel
+    a.prof = dmv_profile_buffer();
+    // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
     { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = (bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0); }
-    const size_t vis_bytes = pl.tile_bytes, stage_bytes = (size_t)2 * pl.KB * pl.nq * 128;
-    const size_t out_tile_bytes = a.bulk ? (size_t)pl.nq * 512 : 0;
-    int stages = (int)(((size_t)g_align_smem - vis_bytes - out_tile_bytes - 1024) / stage_bytes);
+    // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
+    size_t slot_bytes = (size_t)2 * pl.KB * pl.nq * 128;
+    if (slot_bytes < (size_t)CHUNK_A) slot_bytes = CHUNK_A;
+    const int out_rows = Q < pl.nq ? Q : pl.nq;
+    const size_t out_tile_bytes = (size_t)out_rows * 512, fixed = sizeof(AlignSmem) + 64 + 512;
+    int out_bufs = a.bulk ? 2 : 0;
+    if (out_bufs == 2 && ((size_t)g_align_smem - fixed - 2 * out_tile_bytes) / slot_bytes < 2) out_bufs = 1;
+    int stages = (int)(((size_t)g_align_smem - fixed - out_bufs * out_tile_bytes) / slot_bytes);
     if (stages > 8) stages = 8;
-    if (stages < 1) return cudaErrorInvalidValue;
-    a.stages = stages;
-    const size_t smem_bytes = vis_bytes + (size_t)stages * stage_bytes + out_tile_bytes + sizeof(AlignSmem) + 64;
-    // Work items are dealt round-robin to the persistent CTAs: split the captions of one (image, v-tile group) into
+    if (stages < 2) return cudaErrorInvalidValue;
+    a.stages = stages; a.out_bufs = out_bufs; a.slot_bytes = (uint32_t)slot_bytes;
+    a.teams = a.bulk ? out_bufs : kTeams; a.out_rows = out_rows;
+    const size_t smem_bytes = (size_t)stages * slot_bytes + out_bufs * out_tile_bytes + 512 + sizeof(AlignSmem) + 64;
+    // Work items are dealt round-robin to the persistent CTAs: split the captions of one (image, v-tile pair) into
     // chunks until every CTA gets >= 16 items, so the uneven last round costs a few per cent at most.
-    const int pair = a.a_in_tmem ? 2 : 1;
-    const long long groups = (long long)A * ((pl.VT + pair - 1) / pair);
+    const long long groups = (long long)A * ((pl.VT + 1) / 2);
     int bch = 1;
     while (groups * bch < 16LL * g_align_sm && bch < B) bch <<= 1;
     if (bch > B) bch = B;
@@ -632,17 +618,8 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
         kern<<<grid, kThreads, smem_bytes, st>>>(a);
         return cudaGetLastError();
     };
-    const int variant = (pl.KB == 1 ? 0 : 4) | (a.a_in_tmem ? 2 : 0) | (a.bulk ? 1 : 0);
-    switch (variant) {
-        case 0: return launch(align_gemm_kernel<1, false, false>);
-        case 1: return launch(align_gemm_kernel<1, false, true>);
-        case 2: return launch(align_gemm_kernel<1, true, false>);
-        case 3: return launch(align_gemm_kernel<1, true, true>);
-        case 4: return launch(align_gemm_kernel<2, false, false>);
-        case 5: return launch(align_gemm_kernel<2, false, true>);
-        case 6: return launch(align_gemm_kernel<2, true, false>);
-        default: return launch(align_gemm_kernel<2, true, true>);
-    }
+    if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, true>) : launch(align_gemm_kernel<1, false>);
+    return a.bulk ? launch(align_gemm_kernel<2, true>) : launch(align_gemm_kernel<2, false>);
 }
 
 }  // namespace vlgae

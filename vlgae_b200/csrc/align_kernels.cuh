@@ -15,8 +15,10 @@ struct AlignArgs {
     int ldv;
     int A, V, B, Q;
     int KB, VT, QT, nq;  // k-blocks of 64, v-tiles, q-tiles, padded queries per tile (multiple of 16, <= 128)
-    int BCH, stages, split, debug, a_in_tmem, bulk;
+    int BCH, stages, out_bufs, out_rows, teams, split, debug, bulk;
+    uint32_t slot_bytes;
     float neg;
+    long long *prof;  // debug: per CTA 8 counters of the MMA warp (clocks waiting for captions / accumulators / issuing)
 };
 
 struct AlignPlan {

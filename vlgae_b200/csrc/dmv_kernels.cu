@@ -973,6 +973,7 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads
 static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
 static long long *g_prof = nullptr;
 void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
+long long *dmv_profile_buffer() { return g_prof; }
 void dmv_set_tuning(int gmax, int threads, int tpl) { g_tune_gmax = gmax; g_tune_threads = threads; g_tune_tpl = tpl; }
 
 static int env_int(const char *name, int dflt) {

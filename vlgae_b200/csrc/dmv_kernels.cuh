@@ -43,6 +43,7 @@ bool dmv_fits_smem(int N, int passes);
 int dmv_grid_for_workspace(int B);
 void dmv_set_tuning(int gmax, int threads, int tpl);
 void dmv_set_profile_buffer(long long *buf);
+long long *dmv_profile_buffer();  // nullptr unless a debug buffer was registered
 cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st);
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);
