@@ -960,7 +960,21 @@ static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static int env_int(const char *name, int dflt);
+static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
+
 static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads, bool lat, cudaStream_t st) {
+    // Default schedule: the frontier kernel (dmv_frontier.cu) whenever the chart fits in shared memory.  An explicit
+    // role-kernel tuning (vlgae_dmv_set_tuning / VLGAE_DMV_THREADS / VLGAE_DMV_GMAX) or VLGAE_DMV_KERNEL=role selects
+    // the role-split kernel below, which also covers the long sentences whose chart lives in global memory.
+    static const int env_role = [] { const char *v = getenv("VLGAE_DMV_KERNEL"); return v && v[0] == 'r' ? 1 : 0; }();
+    static const int env_ft = env_int("VLGAE_FRONTIER_THREADS", 0);
+    if (!env_role && g_tune_gmax == 0 && g_tune_threads == 0 && a.threads == 0 && dmv_frontier_fits(cap, passes, g_smem_optin)) {
+        // 512 threads when every work item has an SM to itself (latency regime), else 256 (more CTAs per SM)
+        const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count;
+        const int ft = env_ft > 0 ? env_ft : (cap <= 12 ? 128 : (cap <= 24 || !resident ? 256 : 512));
+        return launch_dmv_frontier(a, passes, cap, ft, g_sm_count, st);
+    }
     // CTA = 3 roles x LPR lanes with LPR >= cap - 1 (every width is one round); a tuning request can only widen it
     const int need = cap <= 33 ? 96 : (cap <= 65 ? 192 : (cap <= 129 ? 384 : 768));
     if (threads < need) threads = need;
@@ -970,7 +984,6 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads
     return launch_nt<768, false>(a, passes, cap, st);
 }
 
-static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
 static long long *g_prof = nullptr;
 void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
 long long *dmv_profile_buffer() { return g_prof; }
