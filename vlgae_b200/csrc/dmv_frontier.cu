@@ -118,9 +118,177 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// register-resident variants: thread t owns the target cells Nb + t + k NT (k < CPT) for the whole sweep and keeps
+// their running state in registers -- no cell decode, no accumulator load / store, no task loop per phase.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int CPT>
+__device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
+    const int tid = threadIdx.x, nc = ncells(Nb);
+    int ow[CPT], oi[CPT];
+    float ax[CPT][4], al[CPT][4], ar[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cc = Nb + tid + k * NT;
+        const int e = cc < nc ? (int)cw[cc] : 0;
+        ow[k] = e >> 8; oi[k] = e & 255;  // width 0 = no cell: never inside a band
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { ax[k][q] = (q & 1) ? 0.f : NEG_BIG; al[k][q] = ax[k][q]; ar[k][q] = ax[k][q]; }
+    }
+#pragma unroll 1
+    for (int s = 0; s <= len; ++s) {
+        const int Ds = dbase(s, Nb);
+        if (s >= 1) {
+            // phase A(s): incomplete items of width s are final
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int w = ow[k], i = oi[k];
+                if (w >= s && w <= 2 * s - 1) {
+                    const int Dd = dbase(w - s, Nb), j = i + w;
+                    const float l3 = c.C4[Dd + i].y;          // CL[i, j-s].NO
+                    const float4 i3 = c.I4[Ds + j - s];        // IL[j-s, j]
+                    const float4 i4 = c.I4[Ds + i];            // IR[i, i+s]
+                    const float r4 = c.C4[Dd + i + s].w;       // CR[i+s, j].NO
+                    lse1(al[k][0], al[k][1], l3 + i3.x);
+                    lse1(al[k][2], al[k][3], l3 + i3.y);
+                    lse1(ar[k][0], ar[k][1], i4.z + r4);
+                    lse1(ar[k][2], ar[k][3], i4.w + r4);
+                    if (w == s) {
+                        float4 v = make_float4(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]),
+                                               lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
+                        if (i == 0 && w != len) { v.z = mask_zero; v.w = mask_zero; }  // single-root mask, dmv.py:63
+                        c.C4[Nb + tid + k * NT] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (s == len) break;
+        // phase B(s): complete items of width s are final
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int w = ow[k], i = oi[k];
+            if (w >= s + 1 && w <= 2 * s + 1) {
+                const int De = dbase(w - 1 - s, Nb), j = i + w;
+                const float4 la = c.C4[Ds + i], ra = c.C4[De + i + s + 1];
+                if (w - 1 - s != s) {
+                    const float4 lb = c.C4[De + i], rb = c.C4[Ds + j - s];
+                    lse2(ax[k][0], ax[k][1], la.w + ra.x, lb.w + rb.x);
+                    lse2(ax[k][2], ax[k][3], la.z + ra.y, lb.z + rb.y);
+                } else {
+                    lse1(ax[k][0], ax[k][1], la.w + ra.x);
+                    lse1(ax[k][2], ax[k][3], la.z + ra.y);
+                }
+                if (w == s + 1) {
+                    const int cc = Nb + tid + k * NT;
+                    const float xl = lse_fin(ax[k][0], ax[k][1]), xr = lse_fin(ax[k][2], ax[k][3]);
+                    const float4 arc = c.I4[cc];
+                    c.I4[cc] = make_float4(xl + arc.x, xl + arc.y, xr + arc.z, xr + arc.w);
+                    c.A0[cc] = make_float4(xl, xr, 0.f, 0.f);
+                }
+                if (w <= 2 * s) {
+                    const int Dd = dbase(w - s, Nb);
+                    const float l3 = la.y;                     // CL[i, i+s].NO
+                    const float4 i3 = c.I4[Dd + i + s];        // IL[i+s, j]
+                    const float4 i4 = c.I4[Dd + i];            // IR[i, j-s]
+                    const float r4 = c.C4[Ds + j - s].w;       // CR[j-s, j].NO
+                    lse1(al[k][0], al[k][1], l3 + i3.x);
+                    lse1(al[k][2], al[k][3], l3 + i3.y);
+                    lse1(ar[k][0], ar[k][1], i4.z + r4);
+                    lse1(ar[k][2], ar[k][3], i4.w + r4);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NT, int CPT>
+__device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
+    const int tid = threadIdx.x, nc = ncells(Nb);
+    int ow[CPT], oi[CPT];
+    float vx[CPT][2], vc[CPT][4];
+    int bx[CPT][2], bc[CPT][4];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cc = Nb + tid + k * NT;
+        const int e = cc < nc ? (int)cw[cc] : 0;
+        ow[k] = e >> 8; oi[k] = e & 255;
+        vx[k][0] = vx[k][1] = NEG_BIG; bx[k][0] = bx[k][1] = 255;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { vc[k][q] = NEG_BIG; bc[k][q] = 255; }
+    }
+#pragma unroll 1
+    for (int s = 0; s <= len; ++s) {
+        const int Ds = dbase(s, Nb);
+        if (s >= 1) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int w = ow[k], i = oi[k];
+                if (w >= s && w <= 2 * s - 1) {
+                    const int Dd = dbase(w - s, Nb), j = i + w;
+                    const float l3 = c.C4[Dd + i].y;
+                    const float4 i3 = c.I4[Ds + j - s];
+                    const float4 i4 = c.I4[Ds + i];
+                    const float r4 = c.C4[Dd + i + s].w;
+                    amax1(vc[k][0], bc[k][0], __fadd_rn(l3, i3.x), w - s);   // CL split r - i, r = j - s
+                    amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), w - s);
+                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.z, r4), s - 1);   // CR split r - i - 1, r = i + s
+                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.w, r4), s - 1);
+                    if (w == s) {
+                        const int cc = Nb + tid + k * NT;
+                        float4 v = make_float4(vc[k][0], vc[k][1], vc[k][2], vc[k][3]);
+                        if (i == 0 && w != len) { v.z = mask_zero; v.w = mask_zero; }
+                        c.C4[cc] = v;
+                        uint8_t *bp = c.bp + cc * 6;
+                        bp[2] = (uint8_t)bc[k][0]; bp[3] = (uint8_t)bc[k][1]; bp[4] = (uint8_t)bc[k][2]; bp[5] = (uint8_t)bc[k][3];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (s == len) break;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int w = ow[k], i = oi[k];
+            if (w >= s + 1 && w <= 2 * s + 1) {
+                const int De = dbase(w - 1 - s, Nb), j = i + w;
+                const float4 la = c.C4[Ds + i], ra = c.C4[De + i + s + 1];
+                amax1(vx[k][0], bx[k][0], __fadd_rn(la.w, ra.x), s);
+                amax1(vx[k][1], bx[k][1], __fadd_rn(la.z, ra.y), s);
+                if (w - 1 - s != s) {
+                    const float4 lb = c.C4[De + i], rb = c.C4[Ds + j - s];
+                    amax1(vx[k][0], bx[k][0], __fadd_rn(lb.w, rb.x), w - 1 - s);
+                    amax1(vx[k][1], bx[k][1], __fadd_rn(lb.z, rb.y), w - 1 - s);
+                }
+                if (w == s + 1) {
+                    const int cc = Nb + tid + k * NT;
+                    const float4 arc = c.I4[cc];
+                    c.I4[cc] = make_float4(__fadd_rn(vx[k][0], arc.x), __fadd_rn(vx[k][0], arc.y),
+                                           __fadd_rn(vx[k][1], arc.z), __fadd_rn(vx[k][1], arc.w));
+                    uint8_t *bp = c.bp + cc * 6;
+                    bp[0] = (uint8_t)bx[k][0]; bp[1] = (uint8_t)bx[k][1];
+                }
+                if (w <= 2 * s) {
+                    const int Dd = dbase(w - s, Nb);
+                    const float l3 = la.y;
+                    const float4 i3 = c.I4[Dd + i + s];
+                    const float4 i4 = c.I4[Dd + i];
+                    const float r4 = c.C4[Ds + j - s].w;
+                    amax1(vc[k][0], bc[k][0], __fadd_rn(l3, i3.x), s);
+                    amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), s);
+                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.z, r4), w - s - 1);
+                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.w, r4), w - s - 1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // log semiring: inside + outside for one sentence
 // ---------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, int CPT>
 __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
@@ -144,6 +312,9 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
     if (prof) p.prof[0] = clock64() - t0c;
 
     // ---------------- inside ----------------
+    if (CPT > 0 && nc - Nb <= CPT * NT) {
+        inside_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
+    } else {
     #pragma unroll 1
     for (int s = 0; s <= len; ++s) {
         if (s >= 1) {
@@ -221,6 +392,7 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
             }
             __syncthreads();
         }
+    }
     }
     if (prof) p.prof[1] = clock64() - t0c;
     if (tid == 0) p.Z[b] = c.C4[cidx(0, len, Nb)].w;  // dmv.py:65
@@ -329,7 +501,7 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
 // items of the back-trace: kind (0 CR, 1 CL, 2 IR, 3 IL) | v << 2 | lo << 3 | hi << 12
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
-template <int NT>
+template <int NT, int CPT>
 __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
@@ -364,6 +536,9 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
     __syncthreads();
     if (prof) p.prof[4] = clock64() - t0c;
 
+    if (CPT > 0 && nc - Nb <= CPT * NT) {
+        viterbi_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
+    } else {
     #pragma unroll 1
     for (int s = 0; s <= len; ++s) {
         if (s >= 1) {
@@ -443,6 +618,7 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
             __syncthreads();
         }
     }
+    }
     if (prof) p.prof[5] = clock64() - t0c;
     if (tid == 0) p.best[b] = c.C4[cidx(0, len, Nb)].w;
 
@@ -507,8 +683,8 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent CTAs stride over (sentence, semiring) work items (same placement rule as dmv_kernels.cu)
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) dmv_frontier_kernel(DmvArgs p) {
+template <int NT, int CPT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 6 : (NT == 64 ? 12 : 1)))) dmv_frontier_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.B * p.npass;
     const int nsm = p.nsm;
@@ -522,8 +698,8 @@ __global__ void __launch_bounds__(NT, 1) dmv_frontier_kernel(DmvArgs p) {
             const int len = clamp_len(p, b);
             if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         }
-        if (which == 0) log_pass<NT>(p, b, smem_raw);
-        else max_pass<NT>(p, b, smem_raw);
+        if (which == 0) log_pass<NT, CPT>(p, b, smem_raw);
+        else max_pass<NT, CPT>(p, b, smem_raw);
     }
 }
 
@@ -542,7 +718,7 @@ size_t frontier_bytes(int cap, int passes) {
 
 bool dmv_frontier_fits(int cap, int passes, int smem_optin) { return cap <= 256 && frontier_bytes(cap, passes) <= (size_t)smem_optin; }
 
-cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st) {
+cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, cudaStream_t st) {
     const size_t smem = frontier_bytes(cap, passes);
     const int total = a.B * a.npass;
     a.smem_n = cap;
@@ -558,10 +734,22 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, int
         kern<<<grid, nt, smem, st>>>(a);
         return cudaGetLastError();
     };
-    if (threads <= 128) return go(dmv_frontier_kernel<128>, 128);
-    if (threads <= 256) return go(dmv_frontier_kernel<256>, 256);
-    if (threads <= 512) return go(dmv_frontier_kernel<512>, 512);
-    return go(dmv_frontier_kernel<1024>, 1024);
+    // cells per thread of the register-resident sweeps (0 = running state in shared memory, any chart size)
+    // running state in registers (thread owns <= 4 target cells for the whole sweep) or in shared memory (any size)
+    static const int env_smem_acc = [] { const char *v = getenv("VLGAE_FRONTIER_SMEM_ACC"); return v && *v ? atoi(v) : -1; }();
+    if (env_smem_acc >= 0) reg_state = env_smem_acc == 0;
+    const int cells = reg_state ? ncells(cap) - cap : (1 << 30);
+    if (threads <= 64) return cells <= 128 ? go(dmv_frontier_kernel<64, 2>, 64) : go(dmv_frontier_kernel<64, 0>, 64);
+    if (threads <= 128) return cells <= 256 ? go(dmv_frontier_kernel<128, 2>, 128) : go(dmv_frontier_kernel<128, 0>, 128);
+    if (threads <= 256) {
+        if (cells <= 512) return go(dmv_frontier_kernel<256, 2>, 256);
+        return cells <= 1024 ? go(dmv_frontier_kernel<256, 4>, 256) : go(dmv_frontier_kernel<256, 0>, 256);
+    }
+    if (threads <= 512) {
+        if (cells <= 512) return go(dmv_frontier_kernel<512, 1>, 512);
+        return cells <= 1024 ? go(dmv_frontier_kernel<512, 2>, 512) : go(dmv_frontier_kernel<512, 0>, 512);
+    }
+    return cells <= 1024 ? go(dmv_frontier_kernel<1024, 1>, 1024) : go(dmv_frontier_kernel<1024, 0>, 1024);
 }
 
 }  // namespace vlgae
