@@ -19,12 +19,14 @@
 // parents each push one product into their two operands; within a phase every accumulator word has a single writer
 // (row owner / column owner / distinct words per item kind), so no atomics.
 //
-// Shared memory per cell (diagonal-major index as in dmv_kernels.cu), log pass 80 B:
-//   C4 = (CL.HAS, CL.NO, CR.HAS, CR.NO)   I4 = (IL.HAS, IL.NO, IR.HAS, IR.NO), pre-loaded with attach + dec[GO]
-//   A0 = inside: running (m, s) of XL, XR      -> after finalisation / outside: (XL, XR, -, -)
-//   A1 = inside: running (m, s) of CL.HAS, CL.NO -> outside: gradient of I4
-//   A2 = inside: running (m, s) of CR.HAS, CR.NO -> outside: gradient of C4
-// max pass 62 B: C4, I4, VX = best (XL, XR), VC = best (CL.HAS, CL.NO, CR.HAS, CR.NO), 6 arg-max bytes.
+// Shared memory per cell (diagonal-major index as in dmv_kernels.cu).  Every item kind is its OWN float2 array
+// (.x = HASCHILD, .y = NOCHILD): neighbouring lanes own neighbouring cells of one width, so a warp's access to one array
+// is 256 contiguous bytes -- two wavefronts, no bank conflicts -- and a task loads only the item kinds it needs.  (With
+// one float4 per cell, 16-byte-strided scalar accesses were 4-way conflicted and half of every float4 load was unused:
+// the reverse sweep was bound by shared-memory wavefronts, 57k of 111k clk for 40 words.)
+//   log pass 88 B: CL, CR, IL, IR (IL / IR pre-loaded with attach + dec[GO]), X = (XL, XR), and 48 B that hold the running
+//   (m, s) pairs while the state lives in shared memory, then the gradients gCL, gCR, gIL, gIR in the reverse sweep.
+//   max pass 62 B: CL, CR, IL, IR, best-so-far VX = (XL, XR), VC = (CL.HAS, CL.NO, CR.HAS, CR.NO), 6 arg-max bytes.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -76,11 +78,13 @@ __device__ __forceinline__ void amax1(float &v, int &a, float t, int idx) {
 }
 
 struct LogChart {
-    float4 *C4, *I4, *A0, *A1, *A2;
+    float2 *CL, *CR, *IL, *IR, *X;   // values; X = (XL, XR) before the arc score is added
+    float4 *A0, *A1, *A2;            // running (m, s) pairs of (XL, XR), (CL.HAS, CL.NO), (CR.HAS, CR.NO)
+    float2 *gCL, *gCR, *gIL, *gIR;   // reverse sweep: gradients (alias A1 / A2)
 };
 struct MaxChart {
-    float4 *C4, *I4, *VC;
-    float2 *VX;
+    float2 *CL, *CR, *IL, *IR, *VX;
+    float4 *VC;
     uint8_t *bp;  // 6 bytes per cell: XL, XR, CL[HAS], CL[NO], CR[HAS], CR[NO]  (first maximal split)
 };
 
@@ -92,28 +96,32 @@ __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
 // stage dec, width-0 complete items (STOP decisions, dmv.py:39-40) and the arc scores attach + dec[GO]
 // (formed first in fp32, exactly as dmv.py:36-37 does).  dec index = dir*4 + val*2 + decision.
 template <int NT>
-__device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, float *sdec, uint16_t *cw, float4 *C4, float4 *I4) {
+__device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, float *sdec, uint16_t *cw, float2 *CL, float2 *CR,
+                                             float2 *IL, float2 *IR) {
     const int tid = threadIdx.x, N = p.N;
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
-    #pragma unroll 1
+#pragma unroll 1
     for (int t = tid; t < Nb * 8; t += NT) sdec[t] = dec[t];
-    #pragma unroll 1
+#pragma unroll 1
     for (int d = tid; d < Nb; d += NT) {  // cell -> (width, left end)
         const int base = dbase(d, Nb);
         for (int lo = 0; lo < Nb - d; ++lo) cw[base + lo] = (uint16_t)((d << 8) | lo);
     }
     __syncthreads();
-    #pragma unroll 1
-    for (int i = tid; i < Nb; i += NT) C4[i] = make_float4(sdec[i * 8 + 1], sdec[i * 8 + 3], sdec[i * 8 + 5], sdec[i * 8 + 7]);
+#pragma unroll 1
+    for (int i = tid; i < Nb; i += NT) {
+        CL[i] = make_float2(sdec[i * 8 + 1], sdec[i * 8 + 3]);
+        CR[i] = make_float2(sdec[i * 8 + 5], sdec[i * 8 + 7]);
+    }
     const int nc = ncells(Nb);
-    #pragma unroll 1
+#pragma unroll 1
     for (int c = Nb + tid; c < nc; c += NT) {
         const int w = cw[c] >> 8, i = cw[c] & 255, j = i + w;
         const float2 al = *reinterpret_cast<const float2 *>(attach + ((size_t)j * N + i) * 2);  // arc j -> i
         const float2 ar = *reinterpret_cast<const float2 *>(attach + ((size_t)i * N + j) * 2);  // arc i -> j
-        I4[c] = make_float4(__fadd_rn(al.x, sdec[j * 8 + 0]), __fadd_rn(al.y, sdec[j * 8 + 2]),
-                            __fadd_rn(ar.x, sdec[i * 8 + 4]), __fadd_rn(ar.y, sdec[i * 8 + 6]));
+        IL[c] = make_float2(__fadd_rn(al.x, sdec[j * 8 + 0]), __fadd_rn(al.y, sdec[j * 8 + 2]));
+        IR[c] = make_float2(__fadd_rn(ar.x, sdec[i * 8 + 4]), __fadd_rn(ar.y, sdec[i * 8 + 6]));
     }
 }
 
@@ -144,19 +152,20 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                 const int w = ow[k], i = oi[k];
                 if (w >= s && w <= 2 * s - 1) {
                     const int Dd = dbase(w - s, Nb), j = i + w;
-                    const float l3 = c.C4[Dd + i].y;          // CL[i, j-s].NO
-                    const float4 i3 = c.I4[Ds + j - s];        // IL[j-s, j]
-                    const float4 i4 = c.I4[Ds + i];            // IR[i, i+s]
-                    const float r4 = c.C4[Dd + i + s].w;       // CR[i+s, j].NO
+                    const float l3 = c.CL[Dd + i].y;          // CL[i, j-s].NO
+                    const float2 i3 = c.IL[Ds + j - s];        // IL[j-s, j]
+                    const float2 i4 = c.IR[Ds + i];            // IR[i, i+s]
+                    const float r4 = c.CR[Dd + i + s].y;       // CR[i+s, j].NO
                     lse1(al[k][0], al[k][1], l3 + i3.x);
                     lse1(al[k][2], al[k][3], l3 + i3.y);
-                    lse1(ar[k][0], ar[k][1], i4.z + r4);
-                    lse1(ar[k][2], ar[k][3], i4.w + r4);
+                    lse1(ar[k][0], ar[k][1], i4.x + r4);
+                    lse1(ar[k][2], ar[k][3], i4.y + r4);
                     if (w == s) {
-                        float4 v = make_float4(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]),
-                                               lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
-                        if (i == 0 && w != len) { v.z = mask_zero; v.w = mask_zero; }  // single-root mask, dmv.py:63
-                        c.C4[Nb + tid + k * NT] = v;
+                        const int cc = Nb + tid + k * NT;
+                        float2 vr = make_float2(lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
+                        if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);  // single-root mask, dmv.py:63
+                        c.CL[cc] = make_float2(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]));
+                        c.CR[cc] = vr;
                     }
                 }
             }
@@ -169,32 +178,34 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
             const int w = ow[k], i = oi[k];
             if (w >= s + 1 && w <= 2 * s + 1) {
                 const int De = dbase(w - 1 - s, Nb), j = i + w;
-                const float4 la = c.C4[Ds + i], ra = c.C4[De + i + s + 1];
+                // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
+                const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
                 if (w - 1 - s != s) {
-                    const float4 lb = c.C4[De + i], rb = c.C4[Ds + j - s];
-                    lse2(ax[k][0], ax[k][1], la.w + ra.x, lb.w + rb.x);
-                    lse2(ax[k][2], ax[k][3], la.z + ra.y, lb.z + rb.y);
+                    const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                    lse2(ax[k][0], ax[k][1], la.y + ra.x, lb.y + rb.x);
+                    lse2(ax[k][2], ax[k][3], la.x + ra.y, lb.x + rb.y);
                 } else {
-                    lse1(ax[k][0], ax[k][1], la.w + ra.x);
-                    lse1(ax[k][2], ax[k][3], la.z + ra.y);
+                    lse1(ax[k][0], ax[k][1], la.y + ra.x);
+                    lse1(ax[k][2], ax[k][3], la.x + ra.y);
                 }
                 if (w == s + 1) {
                     const int cc = Nb + tid + k * NT;
                     const float xl = lse_fin(ax[k][0], ax[k][1]), xr = lse_fin(ax[k][2], ax[k][3]);
-                    const float4 arc = c.I4[cc];
-                    c.I4[cc] = make_float4(xl + arc.x, xl + arc.y, xr + arc.z, xr + arc.w);
-                    c.A0[cc] = make_float4(xl, xr, 0.f, 0.f);
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                    c.IL[cc] = make_float2(xl + arcl.x, xl + arcl.y);
+                    c.IR[cc] = make_float2(xr + arcr.x, xr + arcr.y);
+                    c.X[cc] = make_float2(xl, xr);
                 }
                 if (w <= 2 * s) {
                     const int Dd = dbase(w - s, Nb);
-                    const float l3 = la.y;                     // CL[i, i+s].NO
-                    const float4 i3 = c.I4[Dd + i + s];        // IL[i+s, j]
-                    const float4 i4 = c.I4[Dd + i];            // IR[i, j-s]
-                    const float r4 = c.C4[Ds + j - s].w;       // CR[j-s, j].NO
+                    const float l3 = c.CL[Ds + i].y;           // CL[i, i+s].NO
+                    const float2 i3 = c.IL[Dd + i + s];        // IL[i+s, j]
+                    const float2 i4 = c.IR[Dd + i];            // IR[i, j-s]
+                    const float r4 = c.CR[Ds + j - s].y;       // CR[j-s, j].NO
                     lse1(al[k][0], al[k][1], l3 + i3.x);
                     lse1(al[k][2], al[k][3], l3 + i3.y);
-                    lse1(ar[k][0], ar[k][1], i4.z + r4);
-                    lse1(ar[k][2], ar[k][3], i4.w + r4);
+                    lse1(ar[k][0], ar[k][1], i4.x + r4);
+                    lse1(ar[k][2], ar[k][3], i4.y + r4);
                 }
             }
         }
@@ -226,19 +237,20 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                 const int w = ow[k], i = oi[k];
                 if (w >= s && w <= 2 * s - 1) {
                     const int Dd = dbase(w - s, Nb), j = i + w;
-                    const float l3 = c.C4[Dd + i].y;
-                    const float4 i3 = c.I4[Ds + j - s];
-                    const float4 i4 = c.I4[Ds + i];
-                    const float r4 = c.C4[Dd + i + s].w;
+                    const float l3 = c.CL[Dd + i].y;
+                    const float2 i3 = c.IL[Ds + j - s];
+                    const float2 i4 = c.IR[Ds + i];
+                    const float r4 = c.CR[Dd + i + s].y;
                     amax1(vc[k][0], bc[k][0], __fadd_rn(l3, i3.x), w - s);   // CL split r - i, r = j - s
                     amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), w - s);
-                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.z, r4), s - 1);   // CR split r - i - 1, r = i + s
-                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.w, r4), s - 1);
+                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.x, r4), s - 1);   // CR split r - i - 1, r = i + s
+                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.y, r4), s - 1);
                     if (w == s) {
                         const int cc = Nb + tid + k * NT;
-                        float4 v = make_float4(vc[k][0], vc[k][1], vc[k][2], vc[k][3]);
-                        if (i == 0 && w != len) { v.z = mask_zero; v.w = mask_zero; }
-                        c.C4[cc] = v;
+                        float2 vr = make_float2(vc[k][2], vc[k][3]);
+                        if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);
+                        c.CL[cc] = make_float2(vc[k][0], vc[k][1]);
+                        c.CR[cc] = vr;
                         uint8_t *bp = c.bp + cc * 6;
                         bp[2] = (uint8_t)bc[k][0]; bp[3] = (uint8_t)bc[k][1]; bp[4] = (uint8_t)bc[k][2]; bp[5] = (uint8_t)bc[k][3];
                     }
@@ -252,32 +264,32 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
             const int w = ow[k], i = oi[k];
             if (w >= s + 1 && w <= 2 * s + 1) {
                 const int De = dbase(w - 1 - s, Nb), j = i + w;
-                const float4 la = c.C4[Ds + i], ra = c.C4[De + i + s + 1];
-                amax1(vx[k][0], bx[k][0], __fadd_rn(la.w, ra.x), s);
-                amax1(vx[k][1], bx[k][1], __fadd_rn(la.z, ra.y), s);
+                const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
+                amax1(vx[k][0], bx[k][0], __fadd_rn(la.y, ra.x), s);
+                amax1(vx[k][1], bx[k][1], __fadd_rn(la.x, ra.y), s);
                 if (w - 1 - s != s) {
-                    const float4 lb = c.C4[De + i], rb = c.C4[Ds + j - s];
-                    amax1(vx[k][0], bx[k][0], __fadd_rn(lb.w, rb.x), w - 1 - s);
-                    amax1(vx[k][1], bx[k][1], __fadd_rn(lb.z, rb.y), w - 1 - s);
+                    const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                    amax1(vx[k][0], bx[k][0], __fadd_rn(lb.y, rb.x), w - 1 - s);
+                    amax1(vx[k][1], bx[k][1], __fadd_rn(lb.x, rb.y), w - 1 - s);
                 }
                 if (w == s + 1) {
                     const int cc = Nb + tid + k * NT;
-                    const float4 arc = c.I4[cc];
-                    c.I4[cc] = make_float4(__fadd_rn(vx[k][0], arc.x), __fadd_rn(vx[k][0], arc.y),
-                                           __fadd_rn(vx[k][1], arc.z), __fadd_rn(vx[k][1], arc.w));
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                    c.IL[cc] = make_float2(__fadd_rn(vx[k][0], arcl.x), __fadd_rn(vx[k][0], arcl.y));
+                    c.IR[cc] = make_float2(__fadd_rn(vx[k][1], arcr.x), __fadd_rn(vx[k][1], arcr.y));
                     uint8_t *bp = c.bp + cc * 6;
                     bp[0] = (uint8_t)bx[k][0]; bp[1] = (uint8_t)bx[k][1];
                 }
                 if (w <= 2 * s) {
                     const int Dd = dbase(w - s, Nb);
-                    const float l3 = la.y;
-                    const float4 i3 = c.I4[Dd + i + s];
-                    const float4 i4 = c.I4[Dd + i];
-                    const float r4 = c.C4[Ds + j - s].w;
+                    const float l3 = c.CL[Ds + i].y;
+                    const float2 i3 = c.IL[Dd + i + s];
+                    const float2 i4 = c.IR[Dd + i];
+                    const float r4 = c.CR[Ds + j - s].y;
                     amax1(vc[k][0], bc[k][0], __fadd_rn(l3, i3.x), s);
                     amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), s);
-                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.z, r4), w - s - 1);
-                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.w, r4), w - s - 1);
+                    amax1(vc[k][2], bc[k][2], __fadd_rn(i4.x, r4), w - s - 1);
+                    amax1(vc[k][3], bc[k][3], __fadd_rn(i4.y, r4), w - s - 1);
                 }
             }
         }
@@ -294,165 +306,184 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(mem);
     LogChart c;
-    c.C4 = reinterpret_cast<float4 *>(mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
-    c.I4 = c.C4 + nc; c.A0 = c.I4 + nc; c.A1 = c.A0 + nc; c.A2 = c.A1 + nc;
-    uint16_t *cw = reinterpret_cast<uint16_t *>(c.A2 + nc);
+    unsigned char *base = mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15);
+    if (CPT > 0) {  // running state in registers: only the 32 B of gradients per cell
+        c.A0 = c.A1 = c.A2 = nullptr;
+        c.gCL = reinterpret_cast<float2 *>(base); c.gCR = c.gCL + nc; c.gIL = c.gCR + nc; c.gIR = c.gIL + nc;
+        c.CL = c.gIR + nc;
+    } else {
+        c.A0 = reinterpret_cast<float4 *>(base);
+        c.A1 = c.A0 + nc; c.A2 = c.A1 + nc;
+        c.gCL = reinterpret_cast<float2 *>(c.A1); c.gCR = c.gCL + nc;
+        c.gIL = reinterpret_cast<float2 *>(c.A2); c.gIR = c.gIL + nc;
+        c.CL = reinterpret_cast<float2 *>(c.A2 + nc);
+    }
+    c.CR = c.CL + nc; c.IL = c.CR + nc; c.IR = c.IL + nc; c.X = c.IR + nc;
+    uint16_t *cw = reinterpret_cast<uint16_t *>(c.X + nc);
     const bool want_grad = (p.gdec != nullptr) || (p.gattach != nullptr);
     const bool prof = p.prof && b == 0 && tid == 0;
     long long t0c = 0;
     if (prof) t0c = clock64();
+    constexpr bool reg_state = CPT > 0;  // the launcher picks CPT so that the sentence's cells fit (cap - 1 words)
 
-    stage_inputs<NT>(p, b, Nb, sdec, cw, c.C4, c.I4);
-    {
+    stage_inputs<NT>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    if (!reg_state) {
         const float4 init = make_float4(NEG_BIG, 0.f, NEG_BIG, 0.f);
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = Nb + tid; t < nc; t += NT) { c.A0[t] = init; c.A1[t] = init; c.A2[t] = init; }
     }
     __syncthreads();
     if (prof) p.prof[0] = clock64() - t0c;
 
     // ---------------- inside ----------------
-    if (CPT > 0 && nc - Nb <= CPT * NT) {
+    if (reg_state) {
         inside_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
     } else {
-    #pragma unroll 1
-    for (int s = 0; s <= len; ++s) {
-        if (s >= 1) {
-            // phase A(s): incomplete items of width s are final
-            const int whi = min(2 * s - 1, len);
-            const int c0 = dbase(s, Nb), c1 = dbase(whi + 1, Nb);
-            #pragma unroll 1
-            for (int cc = c0 + tid; cc < c1; cc += NT) {
-                const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                // step 3 (dmv.py:58-59): CL[i,j][v] (+)= CL[i,r].NO + IL[r,j][v], r = j - s
-                const float l3 = c.C4[cidx(i, w - s, Nb)].y;
-                const float4 i3 = c.I4[cidx(j - s, s, Nb)];
-                // step 4 (dmv.py:61-62): CR[i,j][v] (+)= IR[i,r][v] + CR[r,j].NO, r = i + s
-                const float4 i4 = c.I4[cidx(i, s, Nb)];
-                const float r4 = c.C4[cidx(i + s, w - s, Nb)].w;
-                float4 a1 = c.A1[cc], a2 = c.A2[cc];
-                lse1(a1.x, a1.y, l3 + i3.x);
-                lse1(a1.z, a1.w, l3 + i3.y);
-                lse1(a2.x, a2.y, i4.z + r4);
-                lse1(a2.z, a2.w, i4.w + r4);
-                if (w == s) {
-                    float4 v = make_float4(lse_fin(a1.x, a1.y), lse_fin(a1.z, a1.w), lse_fin(a2.x, a2.y), lse_fin(a2.z, a2.w));
-                    if (i == 0 && w != len) { v.z = p.mask_zero; v.w = p.mask_zero; }  // single-root mask, dmv.py:63
-                    c.C4[cc] = v;
-                } else {
-                    c.A1[cc] = a1; c.A2[cc] = a2;
-                }
-            }
-            __syncthreads();
-        }
-        if (s == len) break;
-        // phase B(s): complete items of width s are final
-        {
-            const int ihi = min(2 * s + 1, len), chi = min(2 * s, len);
-            const int i0 = dbase(s + 1, Nb), nI = dbase(ihi + 1, Nb) - i0;
-            const int nC = chi >= s + 1 ? dbase(chi + 1, Nb) - i0 : 0;
-            #pragma unroll 1
-            for (int t = tid; t < nI + nC; t += NT) {
-                if (t < nI) {
-                    const int cc = i0 + t;
+#pragma unroll 1
+        for (int s = 0; s <= len; ++s) {
+            const int Ds = dbase(s, Nb);
+            if (s >= 1) {
+                // phase A(s): incomplete items of width s are final
+                const int whi = min(2 * s - 1, len);
+                const int c1 = dbase(whi + 1, Nb);
+#pragma unroll 1
+                for (int cc = Ds + tid; cc < c1; cc += NT) {
                     const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                    // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
-                    const float4 la = c.C4[cidx(i, s, Nb)], ra = c.C4[cidx(i + s + 1, w - 1 - s, Nb)];
-                    float4 a0 = c.A0[cc];
-                    if (w - 1 - s != s) {
-                        const float4 lb = c.C4[cidx(i, w - 1 - s, Nb)], rb = c.C4[cidx(j - s, s, Nb)];
-                        lse2(a0.x, a0.y, la.w + ra.x, lb.w + rb.x);
-                        lse2(a0.z, a0.w, la.z + ra.y, lb.z + rb.y);
-                    } else {
-                        lse1(a0.x, a0.y, la.w + ra.x);
-                        lse1(a0.z, a0.w, la.z + ra.y);
-                    }
-                    if (w == s + 1) {
-                        const float xl = lse_fin(a0.x, a0.y), xr = lse_fin(a0.z, a0.w);
-                        const float4 arc = c.I4[cc];
-                        c.I4[cc] = make_float4(xl + arc.x, xl + arc.y, xr + arc.z, xr + arc.w);
-                        c.A0[cc] = make_float4(xl, xr, 0.f, 0.f);
-                    } else {
-                        c.A0[cc] = a0;
-                    }
-                } else {
-                    const int cc = i0 + (t - nI);
-                    const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                    const float l3 = c.C4[cidx(i, s, Nb)].y;               // CL[i, i+s].NO
-                    const float4 i3 = c.I4[cidx(i + s, w - s, Nb)];         // IL[i+s, j]
-                    const float4 i4 = c.I4[cidx(i, w - s, Nb)];             // IR[i, j-s]
-                    const float r4 = c.C4[cidx(j - s, s, Nb)].w;            // CR[j-s, j].NO
+                    const int Dd = dbase(w - s, Nb);
+                    // step 3 (dmv.py:58-59): CL[i,j][v] (+)= CL[i,r].NO + IL[r,j][v], r = j - s
+                    const float l3 = c.CL[Dd + i].y;
+                    const float2 i3 = c.IL[Ds + j - s];
+                    // step 4 (dmv.py:61-62): CR[i,j][v] (+)= IR[i,r][v] + CR[r,j].NO, r = i + s
+                    const float2 i4 = c.IR[Ds + i];
+                    const float r4 = c.CR[Dd + i + s].y;
                     float4 a1 = c.A1[cc], a2 = c.A2[cc];
                     lse1(a1.x, a1.y, l3 + i3.x);
                     lse1(a1.z, a1.w, l3 + i3.y);
-                    lse1(a2.x, a2.y, i4.z + r4);
-                    lse1(a2.z, a2.w, i4.w + r4);
-                    c.A1[cc] = a1; c.A2[cc] = a2;
+                    lse1(a2.x, a2.y, i4.x + r4);
+                    lse1(a2.z, a2.w, i4.y + r4);
+                    if (w == s) {
+                        float2 vr = make_float2(lse_fin(a2.x, a2.y), lse_fin(a2.z, a2.w));
+                        if (i == 0 && w != len) vr = make_float2(p.mask_zero, p.mask_zero);  // single-root mask, dmv.py:63
+                        c.CL[cc] = make_float2(lse_fin(a1.x, a1.y), lse_fin(a1.z, a1.w));
+                        c.CR[cc] = vr;
+                    } else {
+                        c.A1[cc] = a1; c.A2[cc] = a2;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
+            if (s == len) break;
+            // phase B(s): complete items of width s are final
+            {
+                const int ihi = min(2 * s + 1, len), chi = min(2 * s, len);
+                const int i0 = dbase(s + 1, Nb), nI = dbase(ihi + 1, Nb) - i0;
+                const int nC = chi >= s + 1 ? dbase(chi + 1, Nb) - i0 : 0;
+#pragma unroll 1
+                for (int t = tid; t < nI + nC; t += NT) {
+                    if (t < nI) {
+                        const int cc = i0 + t;
+                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+                        const int De = dbase(w - 1 - s, Nb);
+                        // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
+                        const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
+                        float4 a0 = c.A0[cc];
+                        if (w - 1 - s != s) {
+                            const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                            lse2(a0.x, a0.y, la.y + ra.x, lb.y + rb.x);
+                            lse2(a0.z, a0.w, la.x + ra.y, lb.x + rb.y);
+                        } else {
+                            lse1(a0.x, a0.y, la.y + ra.x);
+                            lse1(a0.z, a0.w, la.x + ra.y);
+                        }
+                        if (w == s + 1) {
+                            const float xl = lse_fin(a0.x, a0.y), xr = lse_fin(a0.z, a0.w);
+                            const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                            c.IL[cc] = make_float2(xl + arcl.x, xl + arcl.y);
+                            c.IR[cc] = make_float2(xr + arcr.x, xr + arcr.y);
+                            c.X[cc] = make_float2(xl, xr);
+                        } else {
+                            c.A0[cc] = a0;
+                        }
+                    } else {
+                        const int cc = i0 + (t - nI);
+                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+                        const int Dd = dbase(w - s, Nb);
+                        const float l3 = c.CL[Ds + i].y;        // CL[i, i+s].NO
+                        const float2 i3 = c.IL[Dd + i + s];     // IL[i+s, j]
+                        const float2 i4 = c.IR[Dd + i];         // IR[i, j-s]
+                        const float r4 = c.CR[Ds + j - s].y;    // CR[j-s, j].NO
+                        float4 a1 = c.A1[cc], a2 = c.A2[cc];
+                        lse1(a1.x, a1.y, l3 + i3.x);
+                        lse1(a1.z, a1.w, l3 + i3.y);
+                        lse1(a2.x, a2.y, i4.x + r4);
+                        lse1(a2.z, a2.w, i4.y + r4);
+                        c.A1[cc] = a1; c.A2[cc] = a2;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
-    }
     if (prof) p.prof[1] = clock64() - t0c;
-    if (tid == 0) p.Z[b] = c.C4[cidx(0, len, Nb)].w;  // dmv.py:65
+    if (tid == 0) p.Z[b] = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65
     if (!want_grad) { __syncthreads(); return; }
 
     // ---------------- outside (explicit reverse sweep) ----------------
     {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        #pragma unroll 1
-        for (int t = tid; t < nc; t += NT) { c.A1[t] = z; c.A2[t] = z; }
+        float4 *g4 = reinterpret_cast<float4 *>(c.gCL);  // gCL, gCR, gIL, gIR are contiguous: 2 nc float4
+#pragma unroll 1
+        for (int t = tid; t < 2 * nc; t += NT) g4[t] = z;
         __syncthreads();
-        if (tid == 0) c.A2[cidx(0, len, Nb)].w = p.gZ ? p.gZ[b] : 1.f;
+        if (tid == 0) c.gCR[cidx(0, len, Nb)].y = p.gZ ? p.gZ[b] : 1.f;
         __syncthreads();
     }
-    float *gI = reinterpret_cast<float *>(c.A1), *gC = reinterpret_cast<float *>(c.A2);
-    #pragma unroll 1
+#pragma unroll 1
     for (int w = len; w >= 1; --w) {
         const int ntask = (Nb - w) * w;
-        const float rw = 1.0f / (float)w;
+        // task t = (split a, parent i) with i fastest: neighbouring lanes touch neighbouring cells of one width in
+        // every array.  All accumulator words of a task are distinct and are loaded BEFORE the first store (with
+        // interleaved read-modify-writes every load has to stay behind the previous store: possible aliasing).
+        const int np = Nb - w;
+        const unsigned rw = (1u << 20) / (unsigned)np + 1u;  // t / np == (t * rw) >> 20 for t < 4096
         const int pb = dbase(w, Nb);
         // phase A'(w): complete parents of width w (steps 3, 4 transposed)
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = tid; t < ntask; t += NT) {
-            const int i = (int)(((float)t + 0.5f) * rw), a = t - i * w, j = i + w;
-            const float4 gg = c.A2[pb + i], out = c.C4[pb + i];
-            {
-                const int cl = cidx(i, a, Nb), cr = cidx(i + a, w - a, Nb);
-                const float lv = c.C4[cl].y;
-                const float4 rv = c.I4[cr];
-                const float p0 = gg.x * fexp(lv + rv.x - out.x), p1 = gg.y * fexp(lv + rv.y - out.y);
-                gC[cl * 4 + 1] += p0 + p1;
-                gI[cr * 4 + 0] += p0;
-                gI[cr * 4 + 1] += p1;
-            }
+            const int a = (int)(((unsigned)t * rw) >> 20), i = t - a * np;
+            const float2 gl = c.gCL[pb + i], gr = c.gCR[pb + i], outl = c.CL[pb + i], outr = c.CR[pb + i];
+            const int cl3 = cidx(i, a, Nb), cr3 = cidx(i + a, w - a, Nb);
+            const int cl4 = cidx(i, a + 1, Nb), cr4 = cidx(i + a + 1, w - 1 - a, Nb);
+            const float lv3 = c.CL[cl3].y;
+            const float2 rv3 = c.IL[cr3];
+            const float2 lv4 = c.IR[cl4];
+            const float rv4 = c.CR[cr4].y;
+            const float o1 = c.gCL[cl3].y, o4 = c.gCR[cr4].y;
+            const float2 o2 = c.gIL[cr3], o3 = c.gIR[cl4];
+            const float p0 = gl.x * fexp(lv3 + rv3.x - outl.x), p1 = gl.y * fexp(lv3 + rv3.y - outl.y);
+            float q0 = 0.f, q1 = 0.f;
             if (!(i == 0 && w != len)) {  // the mask overwrote CR[0][w]: no gradient passes through it
-                const int cl = cidx(i, a + 1, Nb), cr = cidx(i + a + 1, w - 1 - a, Nb);
-                const float4 lv = c.I4[cl];
-                const float rv = c.C4[cr].w;
-                const float q0 = gg.z * fexp(lv.z + rv - out.z), q1 = gg.w * fexp(lv.w + rv - out.w);
-                gI[cl * 4 + 2] += q0;
-                gI[cl * 4 + 3] += q1;
-                gC[cr * 4 + 3] += q0 + q1;
+                q0 = gr.x * fexp(lv4.x + rv4 - outr.x);
+                q1 = gr.y * fexp(lv4.y + rv4 - outr.y);
             }
-            (void)j;
+            c.gCL[cl3].y = o1 + (p0 + p1);
+            c.gIL[cr3] = make_float2(o2.x + p0, o2.y + p1);
+            c.gIR[cl4] = make_float2(o3.x + q0, o3.y + q1);
+            c.gCR[cr4].y = o4 + (q0 + q1);
         }
         __syncthreads();
         // phase B'(w): incomplete parents of width w (steps 1, 2 transposed)
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = tid; t < ntask; t += NT) {
-            const int i = (int)(((float)t + 0.5f) * rw), a = t - i * w;
-            const float4 gi = c.A1[pb + i];
-            const float4 x = c.A0[pb + i];
-            const float gl = gi.x + gi.y, gr = gi.z + gi.w;
+            const int a = (int)(((unsigned)t * rw) >> 20), i = t - a * np;
+            const float2 gil = c.gIL[pb + i], gir = c.gIR[pb + i], x = c.X[pb + i];
+            const float gl = gil.x + gil.y, gr = gir.x + gir.y;
             const int cl = cidx(i, a, Nb), cr = cidx(i + a + 1, w - 1 - a, Nb);
-            const float4 lv = c.C4[cl], rv = c.C4[cr];
-            const float pl = gl * fexp(lv.w + rv.x - x.x), pr = gr * fexp(lv.z + rv.y - x.y);
-            gC[cl * 4 + 3] += pl;
-            gC[cl * 4 + 2] += pr;
-            gC[cr * 4 + 0] += pl;
-            gC[cr * 4 + 1] += pr;
+            const float2 lv = c.CR[cl], rv = c.CL[cr];
+            const float2 ol = c.gCR[cl], orr = c.gCL[cr];
+            const float pL = gl * fexp(lv.y + rv.x - x.x), pR = gr * fexp(lv.x + rv.y - x.y);
+            c.gCR[cl] = make_float2(ol.x + pR, ol.y + pL);    // CR[i, r]: .HAS from step 2, .NO from step 1
+            c.gCL[cr] = make_float2(orr.x + pL, orr.y + pR);  // CL[r+1, j]: .HAS from step 1, .NO from step 2
         }
         __syncthreads();
     }
@@ -461,31 +492,27 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
     // ---------------- outputs ----------------
     if (p.gattach) {
         float2 *ga = reinterpret_cast<float2 *>(p.gattach + (size_t)b * N * N * 2);
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = tid; t < N * N; t += NT) {
             const int h = t / N, ch = t - h * N;
             float2 v = make_float2(0.f, 0.f);
-            if (h < Nb && ch < Nb && h != ch) {
-                const float4 g = ch < h ? c.A1[cidx(ch, h - ch, Nb)] : c.A1[cidx(h, ch - h, Nb)];
-                v = ch < h ? make_float2(g.x, g.y) : make_float2(g.z, g.w);
-            }
+            if (h < Nb && ch < Nb && h != ch) v = ch < h ? c.gIL[cidx(ch, h - ch, Nb)] : c.gIR[cidx(h, ch - h, Nb)];
             ga[t] = v;
         }
     }
     if (p.gdec) {
         float *gd = p.gdec + (size_t)b * N * 8;
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = tid; t < N * 2; t += NT) {
             const int i = t >> 1, dir = t & 1;
             float2 go = make_float2(0.f, 0.f), stop = make_float2(0.f, 0.f);
             if (i < Nb) {
-                const float4 g0 = c.A2[i];
                 if (dir == 0) {
-                    for (int ch = 0; ch < i; ++ch) { const float4 v = c.A1[cidx(ch, i - ch, Nb)]; go.x += v.x; go.y += v.y; }
-                    stop = make_float2(g0.x, g0.y);
+                    for (int ch = 0; ch < i; ++ch) { const float2 v = c.gIL[cidx(ch, i - ch, Nb)]; go.x += v.x; go.y += v.y; }
+                    stop = c.gCL[i];
                 } else {
-                    for (int d = 1; d < Nb - i; ++d) { const float4 v = c.A1[cidx(i, d, Nb)]; go.x += v.z; go.y += v.w; }
-                    stop = make_float2(g0.z, g0.w);
+                    for (int d = 1; d < Nb - i; ++d) { const float2 v = c.gIR[cidx(i, d, Nb)]; go.x += v.x; go.y += v.y; }
+                    stop = c.gCR[i];
                 }
             }
             *reinterpret_cast<float4 *>(gd + i * 8 + dir * 4) = make_float4(go.x, stop.x, go.y, stop.y);  // [dir][val][decision]
@@ -507,28 +534,31 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(mem);
     MaxChart c;
-    c.C4 = reinterpret_cast<float4 *>(mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
-    c.I4 = c.C4 + nc; c.VC = c.I4 + nc;
-    c.VX = reinterpret_cast<float2 *>(c.VC + nc);
+    c.VC = reinterpret_cast<float4 *>(mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
+    c.CL = reinterpret_cast<float2 *>(c.VC + nc);
+    c.CR = c.CL + nc; c.IL = c.CR + nc; c.IR = c.IL + nc; c.VX = c.IR + nc;
     int *queue = reinterpret_cast<int *>(c.VX + nc);  // 2 x (2 Nb + 2) ints
     uint16_t *cw = reinterpret_cast<uint16_t *>(queue + 2 * (2 * Nb + 2));
     c.bp = reinterpret_cast<uint8_t *>(cw + nc + (nc & 1));
     const bool prof = p.prof && b == 0 && tid == 0;
     long long t0c = 0;
     if (prof) t0c = clock64();
+    constexpr bool reg_state = CPT > 0;
 
-    stage_inputs<NT>(p, b, Nb, sdec, cw, c.C4, c.I4);
-    #pragma unroll 1
-    for (int t = Nb + tid; t < nc; t += NT) {
-        c.VC[t] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
-        c.VX[t] = make_float2(NEG_BIG, NEG_BIG);
+    stage_inputs<NT>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    if (!reg_state) {
+#pragma unroll 1
+        for (int t = Nb + tid; t < nc; t += NT) {
+            c.VC[t] = make_float4(NEG_BIG, NEG_BIG, NEG_BIG, NEG_BIG);
+            c.VX[t] = make_float2(NEG_BIG, NEG_BIG);
+        }
+#pragma unroll 1
+        for (int t = tid; t < nc * 6; t += NT) c.bp[t] = 255;
     }
-    #pragma unroll 1
-    for (int t = tid; t < nc * 6; t += NT) c.bp[t] = 255;
     // outputs that the back-trace only dots with ones are zero-filled up front
     if (p.arcs) {
         float2 *z = reinterpret_cast<float2 *>(p.arcs + (size_t)b * N * N * 2);
-        #pragma unroll 1
+#pragma unroll 1
         for (int t = tid; t < N * N; t += NT) z[t] = make_float2(0.f, 0.f);
     }
     if (p.vgdec) for (int t = tid; t < N * 8; t += NT) p.vgdec[(size_t)b * N * 8 + t] = 0.f;
@@ -536,91 +566,97 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
     __syncthreads();
     if (prof) p.prof[4] = clock64() - t0c;
 
-    if (CPT > 0 && nc - Nb <= CPT * NT) {
+    if (reg_state) {
         viterbi_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
     } else {
-    #pragma unroll 1
-    for (int s = 0; s <= len; ++s) {
-        if (s >= 1) {
-            // phase A(s): the new term of CL is split r - i = w - s, of CR split r - i - 1 = s - 1
-            const int whi = min(2 * s - 1, len);
-            const int c0 = dbase(s, Nb), c1 = dbase(whi + 1, Nb);
-            #pragma unroll 1
-            for (int cc = c0 + tid; cc < c1; cc += NT) {
-                const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                const float l3 = c.C4[cidx(i, w - s, Nb)].y;
-                const float4 i3 = c.I4[cidx(j - s, s, Nb)];
-                const float4 i4 = c.I4[cidx(i, s, Nb)];
-                const float r4 = c.C4[cidx(i + s, w - s, Nb)].w;
-                float4 v = c.VC[cc];
-                uint8_t *bp = c.bp + cc * 6;
-                int a0 = bp[2], a1 = bp[3], a2 = bp[4], a3 = bp[5];
-                amax1(v.x, a0, __fadd_rn(l3, i3.x), w - s);
-                amax1(v.y, a1, __fadd_rn(l3, i3.y), w - s);
-                amax1(v.z, a2, __fadd_rn(i4.z, r4), s - 1);
-                amax1(v.w, a3, __fadd_rn(i4.w, r4), s - 1);
-                bp[2] = (uint8_t)a0; bp[3] = (uint8_t)a1; bp[4] = (uint8_t)a2; bp[5] = (uint8_t)a3;
-                if (w == s) {
-                    if (i == 0 && w != len) { v.z = p.mask_zero; v.w = p.mask_zero; }
-                    c.C4[cc] = v;
-                } else {
-                    c.VC[cc] = v;
-                }
-            }
-            __syncthreads();
-        }
-        if (s == len) break;
-        {
-            const int ihi = min(2 * s + 1, len), chi = min(2 * s, len);
-            const int i0 = dbase(s + 1, Nb), nI = dbase(ihi + 1, Nb) - i0;
-            const int nC = chi >= s + 1 ? dbase(chi + 1, Nb) - i0 : 0;
-            #pragma unroll 1
-            for (int t = tid; t < nI + nC; t += NT) {
-                if (t < nI) {
-                    const int cc = i0 + t;
+#pragma unroll 1
+        for (int s = 0; s <= len; ++s) {
+            const int Ds = dbase(s, Nb);
+            if (s >= 1) {
+                // phase A(s): the new term of CL is split r - i = w - s, of CR split r - i - 1 = s - 1
+                const int whi = min(2 * s - 1, len);
+                const int c1 = dbase(whi + 1, Nb);
+#pragma unroll 1
+                for (int cc = Ds + tid; cc < c1; cc += NT) {
                     const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                    const float4 la = c.C4[cidx(i, s, Nb)], ra = c.C4[cidx(i + s + 1, w - 1 - s, Nb)];
-                    float2 v = c.VX[cc];
-                    uint8_t *bp = c.bp + cc * 6;
-                    int a0 = bp[0], a1 = bp[1];
-                    amax1(v.x, a0, __fadd_rn(la.w, ra.x), s);  // split r - i = s
-                    amax1(v.y, a1, __fadd_rn(la.z, ra.y), s);
-                    if (w - 1 - s != s) {
-                        const float4 lb = c.C4[cidx(i, w - 1 - s, Nb)], rb = c.C4[cidx(j - s, s, Nb)];
-                        amax1(v.x, a0, __fadd_rn(lb.w, rb.x), w - 1 - s);
-                        amax1(v.y, a1, __fadd_rn(lb.z, rb.y), w - 1 - s);
-                    }
-                    bp[0] = (uint8_t)a0; bp[1] = (uint8_t)a1;
-                    if (w == s + 1) {
-                        const float4 arc = c.I4[cc];
-                        c.I4[cc] = make_float4(__fadd_rn(v.x, arc.x), __fadd_rn(v.x, arc.y), __fadd_rn(v.y, arc.z), __fadd_rn(v.y, arc.w));
-                    } else {
-                        c.VX[cc] = v;
-                    }
-                } else {
-                    const int cc = i0 + (t - nI);
-                    const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                    const float l3 = c.C4[cidx(i, s, Nb)].y;
-                    const float4 i3 = c.I4[cidx(i + s, w - s, Nb)];
-                    const float4 i4 = c.I4[cidx(i, w - s, Nb)];
-                    const float r4 = c.C4[cidx(j - s, s, Nb)].w;
+                    const int Dd = dbase(w - s, Nb);
+                    const float l3 = c.CL[Dd + i].y;
+                    const float2 i3 = c.IL[Ds + j - s];
+                    const float2 i4 = c.IR[Ds + i];
+                    const float r4 = c.CR[Dd + i + s].y;
                     float4 v = c.VC[cc];
                     uint8_t *bp = c.bp + cc * 6;
                     int a0 = bp[2], a1 = bp[3], a2 = bp[4], a3 = bp[5];
-                    amax1(v.x, a0, __fadd_rn(l3, i3.x), s);          // CL split r - i = s
-                    amax1(v.y, a1, __fadd_rn(l3, i3.y), s);
-                    amax1(v.z, a2, __fadd_rn(i4.z, r4), w - s - 1);  // CR split r - i - 1, r = j - s
-                    amax1(v.w, a3, __fadd_rn(i4.w, r4), w - s - 1);
+                    amax1(v.x, a0, __fadd_rn(l3, i3.x), w - s);
+                    amax1(v.y, a1, __fadd_rn(l3, i3.y), w - s);
+                    amax1(v.z, a2, __fadd_rn(i4.x, r4), s - 1);
+                    amax1(v.w, a3, __fadd_rn(i4.y, r4), s - 1);
                     bp[2] = (uint8_t)a0; bp[3] = (uint8_t)a1; bp[4] = (uint8_t)a2; bp[5] = (uint8_t)a3;
-                    c.VC[cc] = v;
+                    if (w == s) {
+                        if (i == 0 && w != len) { v.z = p.mask_zero; v.w = p.mask_zero; }
+                        c.CL[cc] = make_float2(v.x, v.y);
+                        c.CR[cc] = make_float2(v.z, v.w);
+                    } else {
+                        c.VC[cc] = v;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
+            if (s == len) break;
+            {
+                const int ihi = min(2 * s + 1, len), chi = min(2 * s, len);
+                const int i0 = dbase(s + 1, Nb), nI = dbase(ihi + 1, Nb) - i0;
+                const int nC = chi >= s + 1 ? dbase(chi + 1, Nb) - i0 : 0;
+#pragma unroll 1
+                for (int t = tid; t < nI + nC; t += NT) {
+                    if (t < nI) {
+                        const int cc = i0 + t;
+                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+                        const int De = dbase(w - 1 - s, Nb);
+                        const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
+                        float2 v = c.VX[cc];
+                        uint8_t *bp = c.bp + cc * 6;
+                        int a0 = bp[0], a1 = bp[1];
+                        amax1(v.x, a0, __fadd_rn(la.y, ra.x), s);  // split r - i = s
+                        amax1(v.y, a1, __fadd_rn(la.x, ra.y), s);
+                        if (w - 1 - s != s) {
+                            const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                            amax1(v.x, a0, __fadd_rn(lb.y, rb.x), w - 1 - s);
+                            amax1(v.y, a1, __fadd_rn(lb.x, rb.y), w - 1 - s);
+                        }
+                        bp[0] = (uint8_t)a0; bp[1] = (uint8_t)a1;
+                        if (w == s + 1) {
+                            const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                            c.IL[cc] = make_float2(__fadd_rn(v.x, arcl.x), __fadd_rn(v.x, arcl.y));
+                            c.IR[cc] = make_float2(__fadd_rn(v.y, arcr.x), __fadd_rn(v.y, arcr.y));
+                        } else {
+                            c.VX[cc] = v;
+                        }
+                    } else {
+                        const int cc = i0 + (t - nI);
+                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+                        const int Dd = dbase(w - s, Nb);
+                        const float l3 = c.CL[Ds + i].y;
+                        const float2 i3 = c.IL[Dd + i + s];
+                        const float2 i4 = c.IR[Dd + i];
+                        const float r4 = c.CR[Ds + j - s].y;
+                        float4 v = c.VC[cc];
+                        uint8_t *bp = c.bp + cc * 6;
+                        int a0 = bp[2], a1 = bp[3], a2 = bp[4], a3 = bp[5];
+                        amax1(v.x, a0, __fadd_rn(l3, i3.x), s);          // CL split r - i = s
+                        amax1(v.y, a1, __fadd_rn(l3, i3.y), s);
+                        amax1(v.z, a2, __fadd_rn(i4.x, r4), w - s - 1);  // CR split r - i - 1, r = j - s
+                        amax1(v.w, a3, __fadd_rn(i4.y, r4), w - s - 1);
+                        bp[2] = (uint8_t)a0; bp[3] = (uint8_t)a1; bp[4] = (uint8_t)a2; bp[5] = (uint8_t)a3;
+                        c.VC[cc] = v;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
-    }
     if (prof) p.prof[5] = clock64() - t0c;
-    if (tid == 0) p.best[b] = c.C4[cidx(0, len, Nb)].w;
+    if (tid == 0) p.best[b] = c.CR[cidx(0, len, Nb)].y;
 
     // back-trace: breadth-first over the derivation, one warp, two children per expanded item
     if (tid < 32 && (p.heads || p.arcs || p.vgdec)) {
@@ -703,10 +739,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
     }
 }
 
-size_t frontier_bytes(int cap, int passes) {
+size_t frontier_bytes(int cap, int passes, bool reg_state) {
     const size_t nc = ncells(cap), dec = ((size_t)cap * 8 * 4 + 15) & ~(size_t)15;
     size_t s = 0;
-    if (passes & 1) s = dec + nc * 80 + nc * 2 + 16;
+    if (passes & 1) s = dec + nc * (reg_state ? 72 : 88) + nc * 2 + 16;
     if (passes & 2) {
         const size_t m = dec + nc * 56 + (size_t)(2 * (2 * cap + 2)) * 4 + (nc + 1) * 2 + nc * 6 + 16;
         s = m > s ? m : s;
@@ -716,13 +752,13 @@ size_t frontier_bytes(int cap, int passes) {
 
 }  // namespace
 
-bool dmv_frontier_fits(int cap, int passes, int smem_optin) { return cap <= 256 && frontier_bytes(cap, passes) <= (size_t)smem_optin; }
+bool dmv_frontier_fits(int cap, int passes, int smem_optin) { return cap <= 256 && frontier_bytes(cap, passes, false) <= (size_t)smem_optin; }
 
 cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, cudaStream_t st) {
-    const size_t smem = frontier_bytes(cap, passes);
     const int total = a.B * a.npass;
     a.smem_n = cap;
-    auto go = [&](auto kern, int nt) -> cudaError_t {
+    auto go = [&](auto kern, int nt, bool regs) -> cudaError_t {
+        const size_t smem = frontier_bytes(cap, passes, regs);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -739,17 +775,17 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
     static const int env_smem_acc = [] { const char *v = getenv("VLGAE_FRONTIER_SMEM_ACC"); return v && *v ? atoi(v) : -1; }();
     if (env_smem_acc >= 0) reg_state = env_smem_acc == 0;
     const int cells = reg_state ? ncells(cap) - cap : (1 << 30);
-    if (threads <= 64) return cells <= 128 ? go(dmv_frontier_kernel<64, 2>, 64) : go(dmv_frontier_kernel<64, 0>, 64);
-    if (threads <= 128) return cells <= 256 ? go(dmv_frontier_kernel<128, 2>, 128) : go(dmv_frontier_kernel<128, 0>, 128);
+    if (threads <= 64) return cells <= 128 ? go(dmv_frontier_kernel<64, 2>, 64, true) : go(dmv_frontier_kernel<64, 0>, 64, false);
+    if (threads <= 128) return cells <= 256 ? go(dmv_frontier_kernel<128, 2>, 128, true) : go(dmv_frontier_kernel<128, 0>, 128, false);
     if (threads <= 256) {
-        if (cells <= 512) return go(dmv_frontier_kernel<256, 2>, 256);
-        return cells <= 1024 ? go(dmv_frontier_kernel<256, 4>, 256) : go(dmv_frontier_kernel<256, 0>, 256);
+        if (cells <= 512) return go(dmv_frontier_kernel<256, 2>, 256, true);
+        return cells <= 1024 ? go(dmv_frontier_kernel<256, 4>, 256, true) : go(dmv_frontier_kernel<256, 0>, 256, false);
     }
     if (threads <= 512) {
-        if (cells <= 512) return go(dmv_frontier_kernel<512, 1>, 512);
-        return cells <= 1024 ? go(dmv_frontier_kernel<512, 2>, 512) : go(dmv_frontier_kernel<512, 0>, 512);
+        if (cells <= 512) return go(dmv_frontier_kernel<512, 1>, 512, true);
+        return cells <= 1024 ? go(dmv_frontier_kernel<512, 2>, 512, true) : go(dmv_frontier_kernel<512, 0>, 512, false);
     }
-    return cells <= 1024 ? go(dmv_frontier_kernel<1024, 1>, 1024) : go(dmv_frontier_kernel<1024, 0>, 1024);
+    return cells <= 1024 ? go(dmv_frontier_kernel<1024, 1>, 1024, true) : go(dmv_frontier_kernel<1024, 0>, 1024, false);
 }
 
 }  // namespace vlgae
