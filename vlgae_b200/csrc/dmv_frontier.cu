@@ -126,18 +126,22 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-// register-resident variants: thread t owns the target cells Nb + t + k NT (k < CPT) for the whole sweep and keeps
-// their running state in registers -- no cell decode, no accumulator load / store, no task loop per phase.
+// register-resident variants: thread t < H owns the target cells Nb + t + k H (k < CPT, H = cells / CPT rounded up) for
+// the whole sweep and keeps their running state in registers -- no cell decode, no accumulator load / store, no task
+// loop per phase.  The stride is H, not the block size: cells are ordered by width and a phase's band of widths
+// (s .. 2s+1) never holds more than ~Nb^2 / 6 < H cells (CPT = 2), so a thread's two cells are never active in the same
+// phase and the two visits never serialise on the phase's critical path.
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CPT>
 __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
     const int tid = threadIdx.x, nc = ncells(Nb);
+    const int H = (nc - Nb + CPT - 1) / CPT;
     int ow[CPT], oi[CPT];
     float ax[CPT][4], al[CPT][4], ar[CPT][4];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int cc = Nb + tid + k * NT;
-        const int e = cc < nc ? (int)cw[cc] : 0;
+        const int cc = Nb + tid + k * H;
+        const int e = (tid < H && cc < nc) ? (int)cw[cc] : 0;
         ow[k] = e >> 8; oi[k] = e & 255;  // width 0 = no cell: never inside a band
 #pragma unroll
         for (int q = 0; q < 4; ++q) { ax[k][q] = (q & 1) ? 0.f : NEG_BIG; al[k][q] = ax[k][q]; ar[k][q] = ax[k][q]; }
@@ -161,7 +165,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     lse1(ar[k][0], ar[k][1], i4.x + r4);
                     lse1(ar[k][2], ar[k][3], i4.y + r4);
                     if (w == s) {
-                        const int cc = Nb + tid + k * NT;
+                        const int cc = Nb + tid + k * H;
                         float2 vr = make_float2(lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
                         if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);  // single-root mask, dmv.py:63
                         c.CL[cc] = make_float2(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]));
@@ -189,7 +193,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     lse1(ax[k][2], ax[k][3], la.x + ra.y);
                 }
                 if (w == s + 1) {
-                    const int cc = Nb + tid + k * NT;
+                    const int cc = Nb + tid + k * H;
                     const float xl = lse_fin(ax[k][0], ax[k][1]), xr = lse_fin(ax[k][2], ax[k][3]);
                     const float2 arcl = c.IL[cc], arcr = c.IR[cc];
                     c.IL[cc] = make_float2(xl + arcl.x, xl + arcl.y);
@@ -216,13 +220,14 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
 template <int NT, int CPT>
 __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
     const int tid = threadIdx.x, nc = ncells(Nb);
+    const int H = (nc - Nb + CPT - 1) / CPT;
     int ow[CPT], oi[CPT];
     float vx[CPT][2], vc[CPT][4];
     int bx[CPT][2], bc[CPT][4];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) {
-        const int cc = Nb + tid + k * NT;
-        const int e = cc < nc ? (int)cw[cc] : 0;
+        const int cc = Nb + tid + k * H;
+        const int e = (tid < H && cc < nc) ? (int)cw[cc] : 0;
         ow[k] = e >> 8; oi[k] = e & 255;
         vx[k][0] = vx[k][1] = NEG_BIG; bx[k][0] = bx[k][1] = 255;
 #pragma unroll
@@ -246,7 +251,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     amax1(vc[k][2], bc[k][2], __fadd_rn(i4.x, r4), s - 1);   // CR split r - i - 1, r = i + s
                     amax1(vc[k][3], bc[k][3], __fadd_rn(i4.y, r4), s - 1);
                     if (w == s) {
-                        const int cc = Nb + tid + k * NT;
+                        const int cc = Nb + tid + k * H;
                         float2 vr = make_float2(vc[k][2], vc[k][3]);
                         if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);
                         c.CL[cc] = make_float2(vc[k][0], vc[k][1]);
@@ -273,7 +278,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     amax1(vx[k][1], bx[k][1], __fadd_rn(lb.x, rb.y), w - 1 - s);
                 }
                 if (w == s + 1) {
-                    const int cc = Nb + tid + k * NT;
+                    const int cc = Nb + tid + k * H;
                     const float2 arcl = c.IL[cc], arcr = c.IR[cc];
                     c.IL[cc] = make_float2(__fadd_rn(vx[k][0], arcl.x), __fadd_rn(vx[k][0], arcl.y));
                     c.IR[cc] = make_float2(__fadd_rn(vx[k][1], arcr.x), __fadd_rn(vx[k][1], arcr.y));
@@ -445,7 +450,9 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
         // every array.  All accumulator words of a task are distinct and are loaded BEFORE the first store (with
         // interleaved read-modify-writes every load has to stay behind the previous store: possible aliasing).
         const int np = Nb - w;
-        const unsigned rw = (1u << 20) / (unsigned)np + 1u;  // t / np == (t * rw) >> 20 for t < 4096
+        // t / np == (t * rw) >> 20 needs rw * np >= 2^20 and t * (rw * np - 2^20) < 2^20; the float quotient is within 1
+        // of floor(2^20 / np), so +2 keeps the first and 3 np * t <= 3 * 75 * 1406 the second (no integer division)
+        const unsigned rw = __float2uint_rz(__fdividef(1048576.0f, (float)np)) + 2u;
         const int pb = dbase(w, Nb);
         // phase A'(w): complete parents of width w (steps 3, 4 transposed)
 #pragma unroll 1
