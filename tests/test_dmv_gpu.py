@@ -280,6 +280,42 @@ def test_host_buffer_entry_point(dev):
     np.testing.assert_array_equal(heads, oheads)
 
 
+@pytest.mark.parametrize("B,n,ragged", [(16, 12, False), (128, 40, True), (300, 9, True)])
+def test_host_entry_point_pinned_zero_copy(dev, B, n, ragged):
+    """Pinned host buffers take the zero-copy path (the kernel reads / writes host memory itself and the log CTA of a
+    sentence hands the staged inputs to its max CTA); results must equal the device-pointer entry point bit for bit.
+    Called three times on the same buffers: the hand-off flags are epoch-numbered, not reset."""
+    from vlgae_b200 import ops
+    from vlgae_b200._lib import check, lib
+
+    md, ma, L = synth(B, n, 11)
+    if ragged:
+        rng = np.random.default_rng(B)
+        L = np.sort(rng.integers(1, n + 1, size=B))[::-1].astype(np.int64).copy()
+    N = md.shape[1]
+    h = {k: torch.from_numpy(v).pin_memory() for k, v in (("md", md), ("ma", ma), ("L", L))}
+    out = {"Z": torch.zeros(B).pin_memory(), "best": torch.zeros(B).pin_memory(), "gdec": torch.zeros(md.shape).pin_memory(),
+           "gatt": torch.zeros(ma.shape).pin_memory(), "heads": torch.zeros(B, N, dtype=torch.int64).pin_memory()}
+    ref = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev))
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for v in out.values():
+            v.fill_(-7)
+        check(lib().vlgae_dmv_parse_host(h["md"].data_ptr(), h["ma"].data_ptr(), h["L"].data_ptr(), B, N, -1e12,
+                                         out["Z"].data_ptr(), out["gdec"].data_ptr(), out["gatt"].data_ptr(),
+                                         out["best"].data_ptr(), out["heads"].data_ptr(), None), "parse_host")
+        np.testing.assert_array_equal(out["Z"].numpy(), ref.Z.cpu().numpy())
+        np.testing.assert_array_equal(out["best"].numpy(), ref.best.cpu().numpy())
+        np.testing.assert_array_equal(out["heads"].numpy(), ref.heads.cpu().numpy())
+        np.testing.assert_array_equal(out["gatt"].numpy(), ref.gattach.cpu().numpy())
+        np.testing.assert_array_equal(out["gdec"].numpy(), ref.gdec.cpu().numpy())
+    oZ, _, ogatt = oracle.dmv_log(md, ma, L)
+    _, oheads, _, _ = oracle.dmv_viterbi(md, ma, L)
+    np.testing.assert_allclose(out["Z"].numpy(), oZ, rtol=Z_RTOL)
+    assert_marginals(out["gatt"].numpy(), ogatt, oZ)
+    np.testing.assert_array_equal(out["heads"].numpy(), oheads)
+
+
 @pytest.mark.parametrize("name", ["deptree_rand", "deptree_mbr", "deptree_ties"])
 def test_dependency_crf_golden(golden, dev, name):
     """DependencyCRF (MBR decoding path, ldndmv.py:294-299) against the reference's golden vectors."""

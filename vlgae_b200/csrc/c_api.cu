@@ -116,6 +116,62 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nd = (size_t)B * N * 8, na = (size_t)B * N * N * 2;
     const size_t ws = vlgae_dmv_workspace_bytes(B, N);
+    // Zero-copy path: when every host buffer is pinned (cudaHostAlloc / cudaHostRegister -- what torch's pin_memory()
+    // gives), the kernel reads the potentials from and writes the results to host memory itself.  Each CTA pulls its
+    // own sentence over PCIe when it starts and pushes its marginals when it ends, so the transfers of the short
+    // sentences hide behind the chart sweeps of the long ones, and the eight per-call copies (each a few us of fixed
+    // cost) disappear: cfg2 182 us -> see DESIGN.md.  Pageable buffers take the staged path below.
+    static const bool env_zero_copy = [] { const char *v = getenv("VLGAE_ZERO_COPY"); return !(v && v[0] == '0'); }();
+    if (env_zero_copy && ws == 0) {
+        const void *hp[8] = {dec_host, attach_host, lengths_host, Z_host, gdec_host, gattach_host, best_host, heads_host};
+        void *dp[8];
+        bool pinned = true;
+        for (int k = 0; k < 8 && pinned; ++k) {
+            dp[k] = nullptr;
+            if (!hp[k]) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                pinned = false;
+            } else {
+                dp[k] = at.devicePointer;
+            }
+        }
+        // best and Z are required by the kernels: fall through to the staged path if the caller did not ask for them
+        if (pinned && dp[3] && dp[6]) {
+            const bool want_grad = gdec_host || gattach_host;
+            // device scratch through which the log CTA of a sentence hands the staged inputs to the max CTA
+            // (DmvArgs::share): every input byte crosses PCIe once instead of twice
+            static thread_local unsigned char *share = nullptr;
+            static thread_local size_t share_bytes = 0;
+            static thread_local unsigned epoch = 0;
+            const int stride = N * 8 + 4 * (N * (N + 1) / 2);
+            const size_t need = (size_t)B * stride * 4 + (size_t)B * 4 + 64;
+            if (share_bytes < need) {
+                if (share) { cudaStreamSynchronize(st); cudaFree(share); share = nullptr; share_bytes = 0; }
+                cudaError_t ea = cudaMalloc((void **)&share, need);
+                if (ea != cudaSuccess) return cuda_fail(ea, "cudaMalloc");
+                ea = cudaMemsetAsync(share, 0, need, st);
+                if (ea != cudaSuccess) return cuda_fail(ea, "cudaMemset");
+                share_bytes = need;
+                epoch = 0;
+            }
+            vlgae::DmvArgs a;
+            memset(&a, 0, sizeof(a));
+            a.dec = (const float *)dp[0]; a.attach = (const float *)dp[1]; a.lengths = (const int64_t *)dp[2];
+            a.B = B; a.N = N; a.mask_zero = mask_zero;
+            a.Z = (float *)dp[3]; a.gdec = want_grad ? (float *)dp[4] : nullptr; a.gattach = want_grad ? (float *)dp[5] : nullptr;
+            a.best = (float *)dp[6]; a.heads = (int64_t *)dp[7];
+            a.share = (float *)share;
+            a.share_flag = (unsigned *)(share + (((size_t)B * stride * 4 + 15) & ~(size_t)15));
+            a.share_epoch = ++epoch;
+            a.share_stride = stride;
+            rc = run_dmv(a, 3, nullptr, 0, stream);
+            if (rc) return rc;
+            cudaError_t es = cudaStreamSynchronize(st);
+            return es == cudaSuccess ? VLGAE_OK : cuda_fail(es, "sync");
+        }
+    }
     // one device arena: dec | attach | gdec | gattach | Z | best | lengths | heads | workspace
     const size_t fl = nd + na + nd + na + 2 * (size_t)B;
     const size_t bytes = ((fl * 4 + 15) & ~(size_t)15) + (size_t)B * 8 + (size_t)B * N * 8 + 256 + ws;

@@ -95,14 +95,37 @@ __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
 
 // stage dec, width-0 complete items (STOP decisions, dmv.py:39-40) and the arc scores attach + dec[GO]
 // (formed first in fp32, exactly as dmv.py:36-37 does).  dec index = dir*4 + val*2 + decision.
-template <int NT>
+// MODE 0: plain; 1: also publish the staged values in p.share (log CTA); 2: take them from p.share (max CTA)
+template <int NT, int MODE>
 __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, float *sdec, uint16_t *cw, float2 *CL, float2 *CR,
                                              float2 *IL, float2 *IR) {
     const int tid = threadIdx.x, N = p.N;
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
+    float *sh_dec = nullptr;
+    float2 *sh_il = nullptr, *sh_ir = nullptr;
+    if (MODE != 0) {
+        sh_dec = p.share + (size_t)b * p.share_stride;
+        sh_il = reinterpret_cast<float2 *>(sh_dec + N * 8);
+        sh_ir = sh_il + ncells(N);
+    }
+    if (MODE == 2) {
+        if (tid == 0) {
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.share_flag + b) : "memory");
+                if (v != p.share_epoch) __nanosleep(100);
+            } while (v != p.share_epoch);
+        }
+        __syncthreads();
+        dec = sh_dec;
+    }
 #pragma unroll 1
-    for (int t = tid; t < Nb * 8; t += NT) sdec[t] = dec[t];
+    for (int t = tid; t < Nb * 8; t += NT) {
+        const float v = MODE == 2 ? __ldcg(dec + t) : dec[t];
+        sdec[t] = v;
+        if (MODE == 1) sh_dec[t] = v;
+    }
 #pragma unroll 1
     for (int d = tid; d < Nb; d += NT) {  // cell -> (width, left end)
         const int base = dbase(d, Nb);
@@ -114,14 +137,35 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         CL[i] = make_float2(sdec[i * 8 + 1], sdec[i * 8 + 3]);
         CR[i] = make_float2(sdec[i * 8 + 5], sdec[i * 8 + 7]);
     }
-    const int nc = ncells(Nb);
+    if (MODE == 2) {
+        const int nc = ncells(Nb);
 #pragma unroll 1
-    for (int c = Nb + tid; c < nc; c += NT) {
-        const int w = cw[c] >> 8, i = cw[c] & 255, j = i + w;
-        const float2 al = *reinterpret_cast<const float2 *>(attach + ((size_t)j * N + i) * 2);  // arc j -> i
-        const float2 ar = *reinterpret_cast<const float2 *>(attach + ((size_t)i * N + j) * 2);  // arc i -> j
-        IL[c] = make_float2(__fadd_rn(al.x, sdec[j * 8 + 0]), __fadd_rn(al.y, sdec[j * 8 + 2]));
-        IR[c] = make_float2(__fadd_rn(ar.x, sdec[i * 8 + 4]), __fadd_rn(ar.y, sdec[i * 8 + 6]));
+        for (int c = Nb + tid; c < nc; c += NT) { IL[c] = __ldcg(sh_il + c); IR[c] = __ldcg(sh_ir + c); }
+        return;
+    }
+    // arc scores in the order they lie in memory (row h: Nb contiguous float2), so that the reads coalesce -- they may
+    // come straight from pinned host memory over PCIe (vlgae_dmv_parse_host)
+#pragma unroll 1
+    for (int t = tid; t < Nb * Nb; t += NT) {
+        const int h = t / Nb, ch = t - h * Nb;
+        if (h == ch) continue;
+        const float2 a = *reinterpret_cast<const float2 *>(attach + ((size_t)h * N + ch) * 2);
+        if (ch < h) {
+            const float2 v = make_float2(__fadd_rn(a.x, sdec[h * 8 + 0]), __fadd_rn(a.y, sdec[h * 8 + 2]));
+            const int c = cidx(ch, h - ch, Nb);
+            IL[c] = v;
+            if (MODE == 1) sh_il[c] = v;
+        } else {
+            const float2 v = make_float2(__fadd_rn(a.x, sdec[h * 8 + 4]), __fadd_rn(a.y, sdec[h * 8 + 6]));
+            const int c = cidx(h, ch - h, Nb);
+            IR[c] = v;
+            if (MODE == 1) sh_ir[c] = v;
+        }
+    }
+    if (MODE == 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.share_flag + b), "r"(p.share_epoch) : "memory");
     }
 }
 
@@ -331,7 +375,8 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
     if (prof) t0c = clock64();
     constexpr bool reg_state = CPT > 0;  // the launcher picks CPT so that the sentence's cells fit (cap - 1 words)
 
-    stage_inputs<NT>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    if (p.share) stage_inputs<NT, 1>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    else stage_inputs<NT, 0>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
     if (!reg_state) {
         const float4 init = make_float4(NEG_BIG, 0.f, NEG_BIG, 0.f);
 #pragma unroll 1
@@ -552,7 +597,8 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
     if (prof) t0c = clock64();
     constexpr bool reg_state = CPT > 0;
 
-    stage_inputs<NT>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    if (p.share) stage_inputs<NT, 2>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    else stage_inputs<NT, 0>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
     if (!reg_state) {
 #pragma unroll 1
         for (int t = Nb + tid; t < nc; t += NT) {
@@ -766,18 +812,31 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
     a.smem_n = cap;
     auto go = [&](auto kern, int nt, bool regs) -> cudaError_t {
         const size_t smem = frontier_bytes(cap, passes, regs);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
+        // the attribute / occupancy queries cost ~10 us of host time per call: remember them per (variant, shared memory)
+        struct Cached { const void *fn; size_t smem; int occ, dev; };
+        static thread_local Cached cache[32];
+        static thread_local int ncache = 0;
+        int occ = 0, dev = 0;
+        cudaGetDevice(&dev);
+        for (int k = 0; k < ncache; ++k)
+            if (cache[k].fn == (const void *)kern && cache[k].smem == smem && cache[k].dev == dev) occ = cache[k].occ;
+        if (occ == 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem);
+            if (e != cudaSuccess) return e;
+            if (occ < 1) occ = 1;
+            // the attribute is sticky and only ever has to grow: keep one entry per kernel at its largest size
+            int slot = -1;
+            for (int k = 0; k < ncache; ++k) if (cache[k].fn == (const void *)kern && cache[k].dev == dev) slot = k;
+            if (slot < 0 && ncache < 32) slot = ncache++;
+            if (slot >= 0) cache[slot] = Cached{(const void *)kern, smem, occ, dev};
+        }
         int grid = sm_count * occ;
         if (grid > total) grid = total;
         kern<<<grid, nt, smem, st>>>(a);
         return cudaGetLastError();
     };
-    // cells per thread of the register-resident sweeps (0 = running state in shared memory, any chart size)
     // running state in registers (thread owns <= 4 target cells for the whole sweep) or in shared memory (any size)
     static const int env_smem_acc = [] { const char *v = getenv("VLGAE_FRONTIER_SMEM_ACC"); return v && *v ? atoi(v) : -1; }();
     if (env_smem_acc >= 0) reg_state = env_smem_acc == 0;

@@ -35,6 +35,13 @@ struct DmvArgs {
     int threads;       // CTA size (96, 192, 384); 0 = choose from N
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
     int tpl;           // split points per lane before a span is shared between lanes (1..32, power of 2); 0 = auto
+    // frontier kernel, both passes in one launch, inputs in pinned HOST memory: the log CTA of a sentence republishes
+    // what it staged (dec, arc scores) in device memory and the max CTA of the same sentence takes it from there, so
+    // every input byte crosses PCIe once.  share_flag[b] == share_epoch once sentence b is published.
+    float *share;            // [B][share_stride] or null
+    unsigned *share_flag;    // [B]
+    unsigned share_epoch;
+    int share_stride;        // floats per sentence: N * 8 + 4 * ncells(N)
 };
 
 // passes bitmask: 1 = log semiring, 2 = max semiring
