@@ -116,9 +116,11 @@ int vlgae_dmv_parse(const float *dec, const float *attach, const int64_t *length
                     float *vgdec, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
- * Same as vlgae_dmv_parse but with HOST buffers: copies inputs to the device, runs, copies the
- * results back and synchronises `stream` before returning (the end-to-end call a non-torch
- * embedder would make).  Any output pointer may be NULL.
+ * Same as vlgae_dmv_parse but with HOST buffers; synchronises `stream` before returning (the
+ * end-to-end call a non-torch embedder would make).  Any output pointer may be NULL.
+ * Pinned buffers (cudaHostAlloc / cudaHostRegister, torch pin_memory()) are read and written by
+ * the kernel directly over PCIe -- no staging copies; pageable buffers are staged through a
+ * grow-only device arena owned by the calling host thread.  VLGAE_ZERO_COPY=0 forces staging.
  */
 int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
                          float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
