@@ -79,3 +79,41 @@ def test_reduced_and_drop_in_signature(golden, dev):
     att.rename(None)[0, 0, 0, 0] = 1.0  # writable, not aliased
     red = gather_logit_reduced_impl(None, {}, vis, txt, None)
     np.testing.assert_allclose(red.cpu().numpy(), g["reduced"], rtol=1e-4, atol=2e-3)
+
+
+def test_gradients_match_reference_formula(dev):
+    """The reference's attmap is differentiable (einsum + masked_fill_, joint.py:413-418); so is the replacement."""
+    from vlgae_b200.alignment import gather_logit_reduced, gather_logit_simple
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    A, V, B, Q, D = 3, 150, 4, 20, 96
+    vis = torch.randn(A, V, D, generator=g, device=dev)
+    txt = torch.randn(B, Q, D, generator=g, device=dev)
+    vm = torch.rand(A, V, generator=g, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g, device=dev) > 0.2
+    marg = torch.rand(B, Q, generator=g, device=dev) + 0.1
+    w = torch.randn(B, A, Q, V, generator=g, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def reference(v, t):
+        att = torch.einsum("avd,bqd->baqv", v, t)
+        att = att.masked_fill(~vm[None, :, None, :], -1e20).masked_fill(~tm[:, None, :, None], -1e20)
+        return att
+
+    v1, t1 = vis.clone().requires_grad_(), txt.clone().requires_grad_()
+    v2, t2 = vis.clone().requires_grad_(), txt.clone().requires_grad_()
+    keep = vm[None, :, None, :] & tm[:, None, :, None]
+    (gather_logit_simple(v1, vm, t1, tm, named=False) * w * keep).sum().backward()
+    (reference(v2, t2) * w * keep).sum().backward()
+    np.testing.assert_allclose(v1.grad.cpu().numpy(), v2.grad.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(t1.grad.cpu().numpy(), t2.grad.cpu().numpy(), rtol=1e-4, atol=1e-3)
+    # the reduced form (max over V, marginal-weighted mean over Q) back-propagates through the same node
+    v3, t3 = vis.clone().requires_grad_(), txt.clone().requires_grad_()
+    v4, t4 = vis.clone().requires_grad_(), txt.clone().requires_grad_()
+    gather_logit_reduced(v3, vm, t3, tm, marg).sum().backward()
+    att = reference(v4, t4)
+    (torch.sum(att.max(dim=-1).values * marg.unsqueeze(1), dim=-1) / marg.sum(1, keepdim=True)).sum().backward()
+    np.testing.assert_allclose(v3.grad.cpu().numpy(), v4.grad.cpu().numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(t3.grad.cpu().numpy(), t4.grad.cpu().numpy(), rtol=1e-3, atol=1e-3)
+    # no graph is built when nothing requires grad
+    assert not gather_logit_simple(vis, vm, txt, tm, named=False).requires_grad

@@ -36,8 +36,66 @@ def _workspace(dev, nbytes):
     return ws
 
 
+def _launch(vf, vm, tf, tm, split, neg, pad_rows):
+    """One kernel call on prepared tensors (fp32 contiguous features, uint8 masks) -> [B, A, Q, V] (padded-row view)."""
+    dev = vf.device
+    A, V, D = vf.shape
+    B, Q, _ = tf.shape
+    ldv = (V + 7) // 8 * 8 if pad_rows else V
+    out = torch.empty((B, A, Q, ldv), dtype=torch.float32, device=dev)
+    need = lib().vlgae_align_workspace_bytes(A, V, B, Q, D)
+    if need == 0 and out.numel() > 0:
+        raise VlgaeError(f"gather_logit: unsupported shape (D = {D} > 128?)")
+    ws = _workspace(dev, max(need, 1))
+    with torch.cuda.device(dev):
+        check(lib().vlgae_align_logits(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D,
+                                       float(neg), int(split), out.data_ptr(), ldv, ws.data_ptr(), ws.numel(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits")
+    return out[..., :V] if ldv != V else out
+
+
+class _AlignLogits(torch.autograd.Function):
+    """The reference's attmap is an autograd node (einsum + two masked_fill_, joint.py:413-418): the grounding losses
+    back-propagate through it into both encoders.  Forward = the tcgen05 kernel; backward = the two transposed
+    contractions with the masks folded into the operands (a masked entry was overwritten, so it passes no gradient):
+        d vis[a,v,:] = m_v[a,v] * sum_{b,q} g[b,a,q,v] * (m_q[b,q] txt[b,q,:])
+        d txt[b,q,:] = m_q[b,q] * sum_{a,v} g[b,a,q,v] * (m_v[a,v] vis[a,v,:])
+    run as fp32 library GEMMs for now (hand-written transposed kernels are listed under DESIGN.md "Next")."""
+
+    @staticmethod
+    def forward(ctx, vis_feat, txt_feat, vm, tm, split, neg, pad_rows):
+        vf = vis_feat.detach().to(torch.float32).contiguous()
+        tf = txt_feat.detach().to(torch.float32).contiguous()
+        ctx.save_for_backward(vf, tf, vm, tm)
+        ctx.in_dtypes = (vis_feat.dtype, txt_feat.dtype)
+        return _launch(vf, vm, tf, tm, split, neg, pad_rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        vf, tf, vm, tm = ctx.saved_tensors
+        mv, mq = vm.to(torch.float32), tm.to(torch.float32)
+        g = g.to(torch.float32)
+        B, A, Q, V = g.shape
+        gv = gt = None
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            if ctx.needs_input_grad[0]:
+                # [A, V, B*Q] x [B*Q, D]
+                gv = torch.matmul(g.permute(1, 3, 0, 2).reshape(A, V, B * Q), (tf * mq.unsqueeze(-1)).reshape(B * Q, -1))
+                gv = (gv * mv.unsqueeze(-1)).to(ctx.in_dtypes[0])
+            if ctx.needs_input_grad[1]:
+                # [B, Q, A*V] x [A*V, D]
+                gt = torch.matmul(g.permute(0, 2, 1, 3).reshape(B, Q, A * V), (vf * mv.unsqueeze(-1)).reshape(A * V, -1))
+                gt = (gt * mq.unsqueeze(-1)).to(ctx.in_dtypes[1])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        return gv, gt, None, None, None, None, None
+
+
 def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=-INF, named=True, pad_rows=True):
-    """attmap [B, A, Q, V] = <txt[b,q,:], vis[a,v,:]> with both masks applied (joint.py:406-419).
+    """attmap [B, A, Q, V] = <txt[b,q,:], vis[a,v,:]> with both masks applied (joint.py:406-419); differentiable with
+    respect to both feature tensors, like the reference's einsum.
 
     pad_rows: allocate rows of ``ceil(V / 8) * 8`` floats and return the ``[..., :V]`` view (same shape, dtype and
     values; last-dim stride 1, not contiguous).  Every consumer in joint.py indexes / reduces / sorts, none calls
@@ -52,22 +110,13 @@ def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=
     B, Q, D2 = txt_feat.shape
     if D != D2 or tuple(vis_mask.shape) != (A, V) or tuple(txt_mask.shape) != (B, Q):
         raise VlgaeError("gather_logit: vis [A,V,D], vis_mask [A,V], txt [B,Q,D], txt_mask [B,Q] expected")
-    vf = vis_feat.detach().to(torch.float32).contiguous()
-    tf = txt_feat.detach().to(torch.float32).contiguous()
     vm = vis_mask.to(torch.bool).contiguous().view(torch.uint8)
     tm = txt_mask.to(torch.bool).contiguous().view(torch.uint8)
-    ldv = (V + 7) // 8 * 8 if pad_rows else V
-    out = torch.empty((B, A, Q, ldv), dtype=torch.float32, device=dev)
-    need = lib().vlgae_align_workspace_bytes(A, V, B, Q, D)
-    if need == 0 and out.numel() > 0:
-        raise VlgaeError(f"gather_logit: unsupported shape (D = {D} > 128?)")
-    ws = _workspace(dev, max(need, 1))
-    with torch.cuda.device(dev):
-        check(lib().vlgae_align_logits(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D,
-                                       float(neg), int(split), out.data_ptr(), ldv, ws.data_ptr(), ws.numel(),
-                                       torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits")
-    if ldv != V:
-        out = out[..., :V]
+    if torch.is_grad_enabled() and (vis_feat.requires_grad or txt_feat.requires_grad):
+        out = _AlignLogits.apply(vis_feat, txt_feat, vm, tm, split, neg, pad_rows)
+    else:
+        out = _launch(vis_feat.detach().to(torch.float32).contiguous(), vm,
+                      txt_feat.detach().to(torch.float32).contiguous(), tm, split, neg, pad_rows)
     if named:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
