@@ -163,6 +163,21 @@ int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, con
                        const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
                        float *out, int out_row_stride, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Maximum of the alignment scores over the factors, without materialising the [B][A][Q][V] tensor.
+ * Replaces the first half of  gather_logit_reduced   src/model/joint.py:421-432
+ *   (attmap = gather_logit_simple(...); maxatt = attmap.max(dim=-1).values):
+ *   maxv[b][a][q] = max_v out[b][a][q][v]   with out as defined for vlgae_align_logits (masks included), bit-identical
+ *                   to the maximum of the materialised tensor;
+ *   argv[b][a][q] = the smallest v that attains it (int32; may be NULL) -- the index the backward of max routes to.
+ * The same tcgen05 pipeline; the epilogue reduces each 128-factor tile per query row and merges tiles with atomicMax.
+ * workspace: vlgae_align_reduce_workspace_bytes(A, V, B, Q, D) bytes.
+ */
+size_t vlgae_align_reduce_workspace_bytes(int A, int V, int B, int Q, int D);
+int vlgae_align_max_over_factors(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                                 const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill,
+                                 int split, float *maxv, int *argv, void *workspace, size_t workspace_bytes, void *stream);
+
 /* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
 int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);
 

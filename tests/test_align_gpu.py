@@ -117,3 +117,35 @@ def test_gradients_match_reference_formula(dev):
     np.testing.assert_allclose(t3.grad.cpu().numpy(), t4.grad.cpu().numpy(), rtol=1e-3, atol=1e-3)
     # no graph is built when nothing requires grad
     assert not gather_logit_simple(vis, vm, txt, tm, named=False).requires_grad
+
+
+@pytest.mark.parametrize("A,V,B,Q,D", [(2, 1369, 3, 82, 128), (3, 129, 2, 130, 128), (5, 300, 7, 33, 100), (2, 40, 2, 1, 8),
+                                       (9, 700, 20, 50, 64)])
+def test_max_over_factors_equals_max_of_materialised(dev, A, V, B, Q, D):
+    """The fused epilogue (no [B,A,Q,V] tensor) gives bit for bit the max over V of the materialised logits, and the
+    arg-max it reports attains that max at the smallest factor index."""
+    from vlgae_b200.alignment import gather_logit_simple, max_over_factors
+
+    g = torch.Generator(device=dev).manual_seed(A * 100 + Q)
+    vis = torch.randn(A, V, D, generator=g, device=dev)
+    txt = torch.randn(B, Q, D, generator=g, device=dev)
+    vm = torch.rand(A, V, generator=g, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g, device=dev) > 0.2
+    vm[0, :] = False  # an image without any valid factor: every max is the fill value
+    for split in (3, 1):
+        att = gather_logit_simple(vis, vm, txt, tm, split=split, named=False)
+        maxv, argv = max_over_factors(vis, vm, txt, tm, split=split)
+        ref = att.max(dim=-1)
+        assert torch.equal(maxv, ref.values)
+        picked = att.gather(-1, argv.long().unsqueeze(-1)).squeeze(-1)
+        assert torch.equal(picked, ref.values)
+        first = (att == ref.values.unsqueeze(-1)).int().argmax(dim=-1)   # first index attaining the maximum
+        keep = tm.view(B, 1, Q).expand(B, A, Q)
+        assert torch.equal(argv.long()[keep], first[keep])
+    # against the oracle (fp32 einsum + masks) within the split-bf16 error model
+    want = oracle.gather_logit_simple(vis.cpu().numpy(), vm.cpu().numpy(), txt.cpu().numpy(), tm.cpu().numpy()).max(-1)
+    got = max_over_factors(vis, vm, txt, tm)[0].cpu().numpy()
+    masked = want == -1e20
+    assert ((got == -1e20) == masked).all()
+    scale = float(vis.norm(dim=-1).max() * txt.norm(dim=-1).max())
+    assert np.abs(got - want)[~masked].max(initial=0.0) <= scale * 2.0 ** -15

@@ -8,7 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from vlgae_b200.alignment import gather_logit_simple  # noqa: E402
+from vlgae_b200.alignment import gather_logit_reduced, gather_logit_simple, max_over_factors  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--A", type=int, default=128)
@@ -48,6 +48,25 @@ for split, pad in (((3, True),) if args.quick else ((3, True), (3, False), (1, T
     ms = e0.elapsed_time(e1) / args.iters
     print(f"split={split} pad_rows={pad}: {ms:.3f} ms  {out_bytes / ms / 1e6:.0f} GB/s written  {flops * (3 if split == 3 else 1) / ms / 1e9:.0f} "
           f"TFLOP/s issued (bf16)  [{args.B}x{args.A}x{args.Q}x{args.V}, out {out_bytes / 2**30:.2f} GiB]")
+def timed(fn, iters=args.iters):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+marg = torch.rand(args.B, args.Q, generator=g, device=dev) + 0.1
+ms_fused = timed(lambda: max_over_factors(vis, vm, txt, tm))
+ms_mat = timed(lambda: gather_logit_simple(vis, vm, txt, tm, named=False).max(dim=-1).values)
+print(f"max over V, fused epilogue (no [B,A,Q,V] tensor): {ms_fused:.3f} ms  {flops * 3 / ms_fused / 1e9:.0f} TFLOP/s issued;  "
+      f"materialise + torch max: {ms_mat:.3f} ms")
+print(f"gather_logit_reduced end to end: {timed(lambda: gather_logit_reduced(vis, vm, txt, tm, marg)):.3f} ms")
 if args.quick:
     sys.exit(0)
 # reference arithmetic for context: fp32 einsum + 2 masked fills (what joint.py:413-418 runs on the GPU)

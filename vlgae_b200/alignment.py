@@ -124,10 +124,76 @@ def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=
     return out
 
 
+def max_over_factors(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=-INF, want_argmax=True):
+    """(maxatt [B, A, Q], argmax_v [B, A, Q] int32) of the alignment logits without materialising them
+    (vlgae_align_max_over_factors); maxatt is bit-identical to ``gather_logit_simple(...).max(-1).values``."""
+    vf, vm, tf, tm = map(_plain, (vis_feat, vis_mask, txt_feat, txt_mask))
+    dev = vf.device
+    if dev.type != "cuda":
+        raise VlgaeError("vlgae_b200.alignment needs CUDA tensors (there is no CPU fallback)")
+    A, V, D = vf.shape
+    B, Q, D2 = tf.shape
+    if D != D2 or tuple(vm.shape) != (A, V) or tuple(tm.shape) != (B, Q):
+        raise VlgaeError("gather_logit: vis [A,V,D], vis_mask [A,V], txt [B,Q,D], txt_mask [B,Q] expected")
+    vf = vf.detach().to(torch.float32).contiguous()
+    tf = tf.detach().to(torch.float32).contiguous()
+    vm = vm.to(torch.bool).contiguous().view(torch.uint8)
+    tm = tm.to(torch.bool).contiguous().view(torch.uint8)
+    maxv = torch.empty((B, A, Q), dtype=torch.float32, device=dev)
+    argv = torch.empty((B, A, Q), dtype=torch.int32, device=dev) if want_argmax else None
+    need = lib().vlgae_align_reduce_workspace_bytes(A, V, B, Q, D)
+    if need == 0 and maxv.numel() > 0:
+        raise VlgaeError(f"gather_logit: unsupported shape (D = {D} > 128?)")
+    ws = _workspace(dev, max(need, 1))
+    with torch.cuda.device(dev):
+        check(lib().vlgae_align_max_over_factors(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D,
+                                                 float(neg), int(split), maxv.data_ptr(),
+                                                 argv.data_ptr() if argv is not None else None, ws.data_ptr(), ws.numel(),
+                                                 torch.cuda.current_stream(dev).cuda_stream),
+              "vlgae_align_max_over_factors")
+    return maxv, argv
+
+
+class _MaxOverFactors(torch.autograd.Function):
+    """max over V of the alignment logits as one autograd node.  torch's backward of ``attmap.max(-1)`` routes the
+    gradient of (b, a, q) to the single arg-max factor; through the einsum that is
+        d txt[b,q,:] += g[b,a,q] * vis[a, argv[b,a,q], :]        d vis[a, argv[b,a,q], :] += g[b,a,q] * txt[b,q,:]
+    and nothing where the arg-max entry was a masked one (masked_fill_ cut the graph there)."""
+
+    @staticmethod
+    def forward(ctx, vis_feat, txt_feat, vis_mask, txt_mask, split, neg):
+        maxv, argv = max_over_factors(vis_feat, vis_mask, txt_feat, txt_mask, split=split, neg=neg)
+        ctx.save_for_backward(vis_feat.detach(), txt_feat.detach(), vis_mask, txt_mask, argv)
+        ctx.mark_non_differentiable(argv)
+        return maxv, argv
+
+    @staticmethod
+    def backward(ctx, g, _g_arg):
+        vis, txt, vm, tm, argv = ctx.saved_tensors
+        B, A, Q = g.shape
+        V, D = vis.shape[1], vis.shape[2]
+        arg = argv.long()
+        a_idx = torch.arange(A, device=g.device).view(1, A, 1).expand(B, A, Q)
+        keep = vm.bool()[a_idx, arg] & tm.bool().view(B, 1, Q)
+        g = (g * keep).to(torch.float32)
+        gv = gt = None
+        if ctx.needs_input_grad[1]:
+            sel = vis.to(torch.float32)[a_idx, arg]                       # [B, A, Q, D]
+            gt = torch.einsum("baq,baqd->bqd", g, sel).to(txt.dtype)
+        if ctx.needs_input_grad[0]:
+            src = (g.unsqueeze(-1) * txt.to(torch.float32).unsqueeze(1)).reshape(-1, D)   # [B*A*Q, D]
+            flat = (a_idx * V + arg).reshape(-1)
+            gv = torch.zeros(A * V, D, dtype=torch.float32, device=g.device).index_add_(0, flat, src)
+            gv = gv.view(A, V, D).to(vis.dtype)
+        return gv, gt, None, None, None, None
+
+
 def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, *, split=3):
-    """max over V, marginal-weighted mean over Q -> [B, A] (joint.py:421-432)."""
-    att = gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, split=split, named=False)
-    maxatt = att.max(dim=-1).values
+    """max over V, marginal-weighted mean over Q -> [B, A] (joint.py:421-432).  The [B, A, Q, V] tensor is never
+    written: the kernel's epilogue reduces over the factors; differentiable w.r.t. both feature tensors and the
+    marginal, like the reference."""
+    vis_feat, vis_mask, txt_feat, txt_mask = map(_plain, (vis_feat, vis_mask, txt_feat, txt_mask))
+    maxatt, _ = _MaxOverFactors.apply(vis_feat, txt_feat, vis_mask, txt_mask, split, -INF)
     tm = _plain(txt_marginal)
     return torch.sum(maxatt * tm.unsqueeze(1), dim=-1) / tm.sum(1, keepdim=True)
 

@@ -221,8 +221,13 @@ struct AlignSmem {
 //   A CTA keeps TWO image tiles (256 factors) resident and runs every caption tile against both (TS-form MMA, operand A
 //   from tensor memory): with one tile the kernel streams as many caption bytes L2 -> SM as it writes, and the L2
 //   slices, which carry the reads, the writes and the write-back together, are what saturates.
-template <int KB, bool BULK>
+// MODE 0: direct stores (rows not 16-byte aligned)   1: staged tile + bulk TMA stores   2: no [B,A,Q,V] output at all --
+// the epilogue reduces every query row to its maximum over the factors (and the arg-max) and merges the v-tiles with a
+// 64-bit atomicMax (gather_logit_reduced, joint.py:421-432: the 7.4 GB tensor is never materialised)
+template <int KB, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
+    constexpr bool BULK = MODE >= 1;      // a staged [query][128 factors] tile per epilogue team
+    constexpr bool REDUCE = MODE == 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nq = p.nq, S = p.stages, NB = p.out_bufs;
     const uint32_t chunk_b = (uint32_t)nq * 128u;         // one (part, k-block) chunk of a caption tile
@@ -478,7 +483,42 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(neg);
                         }
-                        {
+                        if constexpr (REDUCE) {
+                            // transpose through the staged tile, then one warp per query row: each lane takes 4
+                            // consecutive factors (one LDS.128), REDUX gives the row maximum, the lowest lane that holds
+                            // it gives the first arg-max (torch.max's tie rule); v-tiles merge by atomicMax on
+                            // (ordered value bits << 32 | ~v), so equal values keep the smaller factor index
+                            float *tile_out = s_out + (size_t)team * out_tile_floats;
+                            named_bar(1 + team, 32 * kTeamWarps);  // the previous tile's rows have been reduced
+#pragma unroll
+                            for (int k = 0; k < MAXCH; ++k) {
+                                const int c0 = half * 16 + k * 4 * kEpiWarps;
+                                float *slot = tile_out + (size_t)c0 * TILE_M + quad * 32 + lane;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < q_lim) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                            }
+                            named_bar(1 + team, 32 * kTeamWarps);
+                            unsigned long long *dst = p.red + ((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M;
+                            const uint32_t vbase = (uint32_t)((vt0 + t) * TILE_M + lane * 4);
+                            for (int q = tw; q < q_lim; q += kTeamWarps) {
+                                const uint32_t w32 = q < 32 ? mb_cur.x : (q < 64 ? mb_cur.y : (q < 96 ? mb_cur.z : mb_cur.w));
+                                if (!((w32 >> (q & 31)) & 1u)) continue;  // masked query: stays at the initial key
+                                const float4 x = *reinterpret_cast<const float4 *>(tile_out + (size_t)q * TILE_M + lane * 4);
+                                float m = x.x;
+                                uint32_t vi = 0;
+                                if (x.y > m) { m = x.y; vi = 1; }
+                                if (x.z > m) { m = x.z; vi = 2; }
+                                if (x.w > m) { m = x.w; vi = 3; }
+                                const uint32_t bits = __float_as_uint(m);
+                                const uint32_t key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);  // order-preserving
+                                const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+                                const int src = __ffs(__ballot_sync(0xffffffffu, key == kmax)) - 1;
+                                const uint32_t vwin = __shfl_sync(0xffffffffu, vbase + vi, src);
+                                if (lane == 0)
+                                    atomicMax(dst + q, ((unsigned long long)kmax << 32) | (unsigned long long)(0xffffffffu - vwin));
+                            }
+                        } else {
                             // The tile is staged in shared memory ([query][128 factors] fp32) and written with one
                             // 512 B bulk copy (TMA) per query row: a row segment reaches L2 as one contiguous write and
                             // the warps spend 1 instruction per 4 B on shared memory only. NB tiles alternate, so the
@@ -517,7 +557,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                 }
             }
         }
-        if (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (BULK && !REDUCE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -559,9 +599,10 @@ size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
     return pl.vis_packed_bytes + pl.txt_packed_bytes + ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
 }
 
-cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
-                         int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
-                         cudaStream_t st) {
+// mode 0 / 1: materialise the logits in `out`; mode 2: reduce over the factors into `red` (packed, zero-initialised here)
+static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask,
+                                     int A, int V, int B, int Q, int D, float neg, int split, float *out, int ldv,
+                                     unsigned long long *red, void *workspace, cudaStream_t st) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
     const AlignPlan pl = align_plan(A, V, B, Q, D);
@@ -586,10 +627,12 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
     a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;
     a.out = out; a.ldv = ldv; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.neg = neg; a.split = split == 1 ? 1 : 3;
+    a.red = red;
     { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }  // measurement aids, see the kernel
     a.prof = dmv_profile_buffer();
+    const bool reduce = red != nullptr;
     // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
-    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = (bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0); }
+    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || ((bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0)); }
     // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
     size_t slot_bytes = (size_t)2 * pl.KB * pl.nq * 128;
     if (slot_bytes < (size_t)CHUNK_A) slot_bytes = CHUNK_A;
@@ -618,8 +661,53 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
         kern<<<grid, kThreads, smem_bytes, st>>>(a);
         return cudaGetLastError();
     };
-    if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, true>) : launch(align_gemm_kernel<1, false>);
-    return a.bulk ? launch(align_gemm_kernel<2, true>) : launch(align_gemm_kernel<2, false>);
+    if (reduce) {
+        e = cudaMemsetAsync(red, 0, (size_t)A * B * Q * sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
+    }
+    if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, 1>) : launch(align_gemm_kernel<1, 0>);
+    return a.bulk ? launch(align_gemm_kernel<2, 1>) : launch(align_gemm_kernel<2, 0>);
+}
+
+cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                         int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
+                         cudaStream_t st) {
+    return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, out, ldv, nullptr, workspace, st);
+}
+
+// packed (ordered max bits << 32 | ~argmax) -> max value / first arg-max; untouched (masked query) -> neg / 0
+__global__ void align_unpack_kernel(const unsigned long long *red, size_t n, float neg, float *maxv, int *argv) {
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = red[t];
+        float m = neg;
+        int a = 0;
+        if (k != 0ull) {
+            const uint32_t key = (uint32_t)(k >> 32);
+            m = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+            a = (int)(0xffffffffu - (uint32_t)k);
+        }
+        maxv[t] = m;
+        if (argv) argv[t] = a;
+    }
+}
+
+size_t align_reduce_bytes(int A, int B, int Q) { return (size_t)A * B * Q * sizeof(unsigned long long) + 256; }
+
+cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                                int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
+                                cudaStream_t st) {
+    // workspace = [align_workspace_bytes][packed keys]
+    const size_t off = (align_workspace_bytes(A, V, B, Q, D) + 255) & ~(size_t)255;
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(
+        ((uintptr_t)(reinterpret_cast<uint8_t *>(workspace) + off) + 255) & ~(uintptr_t)255);
+    cudaError_t e = launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, nullptr, 0, red, workspace, st);
+    if (e != cudaSuccess) return e;
+    const size_t n = (size_t)A * B * Q;
+    int grid = (int)((n + 255) / 256);
+    if (grid > g_align_sm * 8) grid = g_align_sm * 8;
+    align_unpack_kernel<<<grid, 256, 0, st>>>(red, n, neg, maxv, argv);
+    return cudaGetLastError();
 }
 
 }  // namespace vlgae

@@ -18,6 +18,7 @@ struct AlignArgs {
     int BCH, stages, out_bufs, out_rows, teams, split, debug, bulk;
     uint32_t slot_bytes;
     float neg;
+    unsigned long long *red;  // MODE 2: [B][A][Q] packed (ordered max bits << 32 | ~argmax), zero-initialised
     long long *prof;  // debug: per CTA 8 counters of the MMA warp (clocks waiting for captions / accumulators / issuing)
 };
 
@@ -32,5 +33,11 @@ size_t align_workspace_bytes(int A, int V, int B, int Q, int D);
 cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
                          int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
                          cudaStream_t st);
+// max over the factors without materialising the logits: maxv [B][A][Q] fp32, argv [B][A][Q] int32 (first arg-max;
+// masked queries: neg / 0).  Workspace: align_workspace_bytes + align_reduce_bytes.
+size_t align_reduce_bytes(int A, int B, int Q);
+cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                                int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
+                                cudaStream_t st);
 
 }  // namespace vlgae

@@ -266,6 +266,28 @@ int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, con
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align launch");
 }
 
+size_t vlgae_align_reduce_workspace_bytes(int A, int V, int B, int Q, int D) {
+    const size_t base = vlgae_align_workspace_bytes(A, V, B, Q, D);
+    if (base == 0) return 0;
+    return ((base + 255) & ~(size_t)255) + 256 + vlgae::align_reduce_bytes(A, B, Q);
+}
+
+int vlgae_align_max_over_factors(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                                 const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill,
+                                 int split, float *maxv, int *argv, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!vis_feat || !vis_mask || !txt_feat || !txt_mask || !maxv) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (A < 0 || V < 0 || B < 0 || Q < 0) return fail(VLGAE_E_INVALID, "%s", "negative extent");
+    if (D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "D must be in [1, 128]");
+    if (split != 1 && split != 3) return fail(VLGAE_E_INVALID, "%s", "split must be 1 or 3");
+    if (A == 0 || B == 0 || Q == 0) return VLGAE_OK;
+    if (V == 0) return fail(VLGAE_E_INVALID, "%s", "max over an empty factor axis");
+    const size_t need = vlgae_align_reduce_workspace_bytes(A, V, B, Q, D);
+    if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "alignment workspace too small");
+    cudaError_t e = vlgae::launch_align_reduce(vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D, neg_fill, split, maxv,
+                                               argv, workspace, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align reduce launch");
+}
+
 static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
     if (!ms_host || !ops_host || iters < 1) return fail(VLGAE_E_INVALID, "%s", "bad microbench arguments");
     cudaStream_t st = (cudaStream_t)stream;
