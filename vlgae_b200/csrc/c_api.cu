@@ -4,6 +4,10 @@
 #include <string.h>
 
 #include "../../include/vlgae_b200.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "align_kernels.cuh"
 #include "deptree_kernels.cuh"
 #include "dmv_kernels.cuh"
@@ -114,6 +118,7 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     if (rc) return rc;
     if (B == 0) return VLGAE_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    const auto t_enter = std::chrono::steady_clock::now();
     const size_t nd = (size_t)B * N * 8, na = (size_t)B * N * N * 2;
     const size_t ws = vlgae_dmv_workspace_bytes(B, N);
     // Zero-copy path: when every host buffer is pinned (cudaHostAlloc / cudaHostRegister -- what torch's pin_memory()
@@ -166,9 +171,18 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             a.share_flag = (unsigned *)(share + (((size_t)B * stride * 4 + 15) & ~(size_t)15));
             a.share_epoch = ++epoch;
             a.share_stride = stride;
+            static const bool trace = getenv("VLGAE_E2E_TRACE") != nullptr;  // host-side breakdown of the call (debug)
+            const auto t_launch = std::chrono::steady_clock::now();
             rc = run_dmv(a, 3, nullptr, 0, stream);
             if (rc) return rc;
+            const auto t_issued = std::chrono::steady_clock::now();
             cudaError_t es = cudaStreamSynchronize(st);
+            if (trace) {
+                const auto t_end = std::chrono::steady_clock::now();
+                auto us = [](auto d) { return std::chrono::duration<double, std::micro>(d).count(); };
+                fprintf(stderr, "[vlgae] parse_host: prepare %.1f us, launch %.1f us, wait %.1f us\n", us(t_launch - t_enter),
+                        us(t_issued - t_launch), us(t_end - t_issued));
+            }
             return es == cudaSuccess ? VLGAE_OK : cuda_fail(es, "sync");
         }
     }
