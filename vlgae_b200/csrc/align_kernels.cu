@@ -240,7 +240,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     float *s_out = reinterpret_cast<float *>(smem + (size_t)S * slot_bytes);
     const size_t out_tile_floats = (size_t)p.out_rows * TILE_M;  // rows = min(nq, Q): the queries a tile can hold
     float *s_neg = s_out + (size_t)NB * out_tile_floats;  // BULK: one row of -INF, the source of masked query rows
-    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + (size_t)S * slot_bytes + (BULK ? (size_t)NB * p.out_rows * 512 + 512 : 0));
+    // REDUCE: running (ordered max bits << 32 | ~arg-max) per (team, caption of the chunk, query); 0 = nothing seen yet
+    unsigned long long *s_run = reinterpret_cast<unsigned long long *>(s_neg + TILE_M);
+    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + (size_t)S * slot_bytes + (BULK ? (size_t)NB * p.out_rows * 512 + 512 : 0) +
+                                                  (REDUCE ? (size_t)p.run_bytes : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -256,6 +259,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         s_neg[threadIdx.x - 64] = p.neg;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (REDUCE)
+        for (int t = threadIdx.x; t < (int)(p.run_bytes / 8); t += kThreads) s_run[t] = 0ull;
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // the swizzled tile images need 1024-byte alignment
     tc_fence_before();
     __syncthreads();
@@ -265,15 +270,23 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     constexpr uint32_t NACC = MAX_ACC;
 
     // work items: (a, group of PAIR v-tiles, chunk of captions) -- full groups first, the odd last v-tiles after them, so
-    // that the static round-robin deal stays balanced; tiles inside an item: (b, q-tile, v-tile of the group)
+    // that the static round-robin deal stays balanced; tiles inside an item: (b, q-tile, v-tile of the group).
+    // REDUCE: an item is (a, chunk of captions) and walks ALL v-tile groups of the image as sub-steps, so the running row
+    // maxima of the chunk stay in this CTA's shared memory (no global atomics, results written once at the end).
     const int VT = p.VT, QT = p.QT, BCH = p.BCH;
     const int VG = VT / PAIR;  // full groups per image
     const int n_full = p.A * VG * BCH;
-    const int n_items = n_full + (VT % PAIR ? p.A * BCH : 0);
+    const int n_items = REDUCE ? p.A * BCH : n_full + (VT % PAIR ? p.A * BCH : 0);
+    const int n_sub = REDUCE ? (VT + PAIR - 1) / PAIR : 1;
     const int b_per = (p.B + BCH - 1) / BCH;
-    auto decode = [&](int item, int &a, int &vt0, int &ntv, int &b0, int &b1) {
+    auto decode = [&](int item, int sub, int &a, int &vt0, int &ntv, int &b0, int &b1) {
         int bc;
-        if (item < n_full) {
+        if (REDUCE) {
+            a = item / BCH;
+            bc = item - a * BCH;
+            vt0 = sub * PAIR;
+            ntv = min(PAIR, VT - vt0);
+        } else if (item < n_full) {
             a = item / (VG * BCH);
             const int rem = item - a * VG * BCH;
             bc = rem / VG;  // v-tile group fastest: neighbouring CTAs write neighbouring segments of the same rows
@@ -295,9 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t s = 0, s_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+            for (int sub = 0; sub < n_sub; ++sub) {
                 int a, vt0, ntv, b0, b1;
-                decode(item, a, vt0, ntv, b0, b1);
+                decode(item, sub, a, vt0, ntv, b0, b1);
                 for (int t = 0; t < ntv; ++t) {  // image tiles: 2*KB chunks of 16 KB, `cps` per slot
                     const uint8_t *src = p.vis_packed + ((size_t)a * VT + vt0 + t) * (size_t)(2 * KB * CHUNK_A);
                     for (int c = 0; c < 2 * KB; c += cps) {
@@ -335,9 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
             uint32_t s = 0, s_phase = 0, acc = 0, acc_phase = 0;
             long long t_ring = 0, t_acc = 0, t_vis = 0;
             const long long t_begin = clock64();
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x)
+            for (int sub = 0; sub < n_sub; ++sub) {
                 int a, vt0, ntv, b0, b1;
-                decode(item, a, vt0, ntv, b0, b1);
+                decode(item, sub, a, vt0, ntv, b0, b1);
                 const long long tv0 = clock64();
                 // Image tiles -> tensor memory once per work item. tcgen05.cp executes in issue order behind the MMAs
                 // of the previous item, which still read the old tiles. With operand A in tensor memory the MMAs read
@@ -412,9 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
         constexpr int MAXCH = 8 / (kEpiWarps / 4);       // 16-query chunks of one warp per tile
         const int T = p.teams;                           // 1: team 0 serves both accumulators (one staging tile fits)
         uint32_t gcount = 0;
-        for (int item = blockIdx.x; team < T && item < n_items; item += gridDim.x) {
+        for (int item = blockIdx.x; team < T && item < n_items; item += gridDim.x)
+        for (int sub = 0; sub < n_sub; ++sub) {
             int a, vt0, ntv, b0, b1;
-            decode(item, a, vt0, ntv, b0, b1);
+            decode(item, sub, a, vt0, ntv, b0, b1);
             bool v_ok_t[PAIR], v_keep_t[PAIR];
 #pragma unroll
             for (int t = 0; t < PAIR; ++t) {
@@ -499,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                     if (c0 + j < q_lim) slot[j * TILE_M] = __uint_as_float(r[k][j]);
                             }
                             named_bar(1 + team, 32 * kTeamWarps);
-                            unsigned long long *dst = p.red + ((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE_M;
+                            unsigned long long *dst = s_run + ((size_t)team * b_per + (b - b0)) * p.Q + (size_t)qt * TILE_M;
                             const uint32_t vbase = (uint32_t)((vt0 + t) * TILE_M + lane * 4);
                             for (int q = tw; q < q_lim; q += kTeamWarps) {
                                 const uint32_t w32 = q < 32 ? mb_cur.x : (q < 64 ? mb_cur.y : (q < 96 ? mb_cur.z : mb_cur.w));
@@ -515,8 +531,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                 const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
                                 const int src = __ffs(__ballot_sync(0xffffffffu, key == kmax)) - 1;
                                 const uint32_t vwin = __shfl_sync(0xffffffffu, vbase + vi, src);
-                                if (lane == 0)
-                                    atomicMax(dst + q, ((unsigned long long)kmax << 32) | (unsigned long long)(0xffffffffu - vwin));
+                                if (lane == 0) {  // row q of this team's copy belongs to this warp alone: plain update
+                                    const unsigned long long k = ((unsigned long long)kmax << 32) | (unsigned long long)(0xffffffffu - vwin);
+                                    if (k > dst[q]) dst[q] = k;
+                                }
                             }
                         } else {
                             // The tile is staged in shared memory ([query][128 factors] fp32) and written with one
@@ -555,6 +573,33 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                         }
                     }
                 }
+            }
+            if (REDUCE && sub == n_sub - 1) {
+                // every v-tile of the image has been seen for this chunk of captions: merge the teams' copies, unpack and
+                // write max / arg-max once (masked queries were never touched: fill value, index 0)
+                named_bar(3, 32 * kTeamWarps * T);
+                const int e_tid = (warp - 2) * 32 + lane, e_n = 32 * kTeamWarps * T, cnt = (b1 - b0) * p.Q;
+                for (int e = e_tid; e < cnt; e += e_n) {
+                    const int bb = e / p.Q, q = e - bb * p.Q;
+                    unsigned long long k = s_run[(size_t)bb * p.Q + q];
+                    s_run[(size_t)bb * p.Q + q] = 0ull;
+                    if (T == 2) {
+                        const unsigned long long k1 = s_run[((size_t)b_per + bb) * p.Q + q];
+                        s_run[((size_t)b_per + bb) * p.Q + q] = 0ull;
+                        k = k1 > k ? k1 : k;
+                    }
+                    float m = p.neg;
+                    int arg = 0;
+                    if (k != 0ull) {
+                        const uint32_t key = (uint32_t)(k >> 32);
+                        m = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+                        arg = (int)(0xffffffffu - (uint32_t)k);
+                    }
+                    const size_t o = ((size_t)(b0 + bb) * p.A + a) * p.Q + q;
+                    p.maxv[o] = m;
+                    if (p.argv) p.argv[o] = arg;
+                }
+                named_bar(3, 32 * kTeamWarps * T);
             }
         }
         if (BULK && !REDUCE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -602,7 +647,7 @@ size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
 // mode 0 / 1: materialise the logits in `out`; mode 2: reduce over the factors into `red` (packed, zero-initialised here)
 static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask,
                                      int A, int V, int B, int Q, int D, float neg, int split, float *out, int ldv,
-                                     unsigned long long *red, void *workspace, cudaStream_t st) {
+                                     float *maxv, int *argv, void *workspace, cudaStream_t st) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
     const AlignPlan pl = align_plan(A, V, B, Q, D);
@@ -627,31 +672,43 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;
     a.out = out; a.ldv = ldv; a.A = A; a.V = V; a.B = B; a.Q = Q; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.neg = neg; a.split = split == 1 ? 1 : 3;
-    a.red = red;
     { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }  // measurement aids, see the kernel
     a.prof = dmv_profile_buffer();
-    const bool reduce = red != nullptr;
+    const bool reduce = maxv != nullptr;
+    a.maxv = maxv; a.argv = argv;
     // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
     { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || ((bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0)); }
     // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
     size_t slot_bytes = (size_t)2 * pl.KB * pl.nq * 128;
     if (slot_bytes < (size_t)CHUNK_A) slot_bytes = CHUNK_A;
     const int out_rows = Q < pl.nq ? Q : pl.nq;
-    const size_t out_tile_bytes = (size_t)out_rows * 512, fixed = sizeof(AlignSmem) + 64 + 512;
+    // REDUCE: captions per work item bounded by the running-maxima arrays (2 teams x b_per x Q x 8 B <= 24 KB)
+    int bch = 1, b_per = B;
+    size_t run_bytes = 0;
+    if (reduce) {
+        int bmax = (int)(24576 / ((size_t)16 * Q));
+        if (bmax < 1) bmax = 1;
+        bch = (B + bmax - 1) / bmax;
+        while ((long long)A * bch < 6LL * g_align_sm && bch < B) ++bch;
+        b_per = (B + bch - 1) / bch;
+        run_bytes = ((size_t)2 * b_per * Q * 8 + 15) & ~(size_t)15;
+    }
+    const size_t out_tile_bytes = (size_t)out_rows * 512, fixed = sizeof(AlignSmem) + 64 + 512 + run_bytes;
     int out_bufs = a.bulk ? 2 : 0;
     if (out_bufs == 2 && ((size_t)g_align_smem - fixed - 2 * out_tile_bytes) / slot_bytes < 2) out_bufs = 1;
     int stages = (int)(((size_t)g_align_smem - fixed - out_bufs * out_tile_bytes) / slot_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return cudaErrorInvalidValue;
     a.stages = stages; a.out_bufs = out_bufs; a.slot_bytes = (uint32_t)slot_bytes;
-    a.teams = a.bulk ? out_bufs : kTeams; a.out_rows = out_rows;
-    const size_t smem_bytes = (size_t)stages * slot_bytes + out_bufs * out_tile_bytes + 512 + sizeof(AlignSmem) + 64;
+    a.teams = a.bulk ? out_bufs : kTeams; a.out_rows = out_rows; a.run_bytes = (uint32_t)run_bytes;
+    const size_t smem_bytes = (size_t)stages * slot_bytes + out_bufs * out_tile_bytes + 512 + run_bytes + sizeof(AlignSmem) + 64;
     // Work items are dealt round-robin to the persistent CTAs: split the captions of one (image, v-tile pair) into
     // chunks until every CTA gets >= 16 items, so the uneven last round costs a few per cent at most.
-    const long long groups = (long long)A * ((pl.VT + 1) / 2);
-    int bch = 1;
-    while (groups * bch < 16LL * g_align_sm && bch < B) bch <<= 1;
-    if (bch > B) bch = B;
+    const long long groups = reduce ? (long long)A : (long long)A * ((pl.VT + 1) / 2);
+    if (!reduce) {
+        while (groups * bch < 16LL * g_align_sm && bch < B) bch <<= 1;
+        if (bch > B) bch = B;
+    }
     a.BCH = bch;
     int grid = g_align_sm;
     if (grid > groups * bch) grid = (int)(groups * bch);
@@ -661,11 +718,7 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
         kern<<<grid, kThreads, smem_bytes, st>>>(a);
         return cudaGetLastError();
     };
-    if (reduce) {
-        e = cudaMemsetAsync(red, 0, (size_t)A * B * Q * sizeof(unsigned long long), st);
-        if (e != cudaSuccess) return e;
-        return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
-    }
+    if (reduce) return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
     if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, 1>) : launch(align_gemm_kernel<1, 0>);
     return a.bulk ? launch(align_gemm_kernel<2, 1>) : launch(align_gemm_kernel<2, 0>);
 }
@@ -673,41 +726,15 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
 cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
                          int V, int B, int Q, int D, float neg, int split, float *out, int ldv, void *workspace,
                          cudaStream_t st) {
-    return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, out, ldv, nullptr, workspace, st);
+    return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, out, ldv, nullptr, nullptr, workspace, st);
 }
 
-// packed (ordered max bits << 32 | ~argmax) -> max value / first arg-max; untouched (masked query) -> neg / 0
-__global__ void align_unpack_kernel(const unsigned long long *red, size_t n, float neg, float *maxv, int *argv) {
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = red[t];
-        float m = neg;
-        int a = 0;
-        if (k != 0ull) {
-            const uint32_t key = (uint32_t)(k >> 32);
-            m = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
-            a = (int)(0xffffffffu - (uint32_t)k);
-        }
-        maxv[t] = m;
-        if (argv) argv[t] = a;
-    }
-}
-
-size_t align_reduce_bytes(int A, int B, int Q) { return (size_t)A * B * Q * sizeof(unsigned long long) + 256; }
+size_t align_reduce_bytes(int, int, int) { return 0; }  // the running maxima live in shared memory
 
 cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
                                 int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
                                 cudaStream_t st) {
-    // workspace = [align_workspace_bytes][packed keys]
-    const size_t off = (align_workspace_bytes(A, V, B, Q, D) + 255) & ~(size_t)255;
-    unsigned long long *red = reinterpret_cast<unsigned long long *>(
-        ((uintptr_t)(reinterpret_cast<uint8_t *>(workspace) + off) + 255) & ~(uintptr_t)255);
-    cudaError_t e = launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, nullptr, 0, red, workspace, st);
-    if (e != cudaSuccess) return e;
-    const size_t n = (size_t)A * B * Q;
-    int grid = (int)((n + 255) / 256);
-    if (grid > g_align_sm * 8) grid = g_align_sm * 8;
-    align_unpack_kernel<<<grid, 256, 0, st>>>(red, n, neg, maxv, argv);
-    return cudaGetLastError();
+    return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, nullptr, 0, maxv, argv, workspace, st);
 }
 
 }  // namespace vlgae

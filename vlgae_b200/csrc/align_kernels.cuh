@@ -18,7 +18,9 @@ struct AlignArgs {
     int BCH, stages, out_bufs, out_rows, teams, split, debug, bulk;
     uint32_t slot_bytes;
     float neg;
-    unsigned long long *red;  // MODE 2: [B][A][Q] packed (ordered max bits << 32 | ~argmax), zero-initialised
+    float *maxv;  // MODE 2: [B][A][Q] max over the factors
+    int *argv;    // MODE 2: [B][A][Q] first arg-max, or null
+    uint32_t run_bytes;  // MODE 2: shared memory of the running maxima
     long long *prof;  // debug: per CTA 8 counters of the MMA warp (clocks waiting for captions / accumulators / issuing)
 };
 
