@@ -68,7 +68,7 @@ const char *vlgae_last_error(void) { return g_err; }
 size_t vlgae_dmv_workspace_bytes(int B, int N) {
     if (B <= 0 || N < 1 || N > VLGAE_DMV_MAX_N) return 0;
     if (vlgae::dmv_fits_smem(N, 3)) return 0;
-    return (size_t)vlgae::dmv_grid_for_workspace(B) * vlgae::dmv_chart_bytes(N, 3);
+    return (size_t)vlgae::dmv_grid_for_workspace(B) * vlgae::dmv_ws_slice_bytes(N, 3);
 }
 
 int vlgae_dmv_inside_outside(const float *dec, const float *attach, const int64_t *lengths, int B, int N,

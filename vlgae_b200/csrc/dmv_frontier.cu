@@ -349,13 +349,20 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
 // ---------------------------------------------------------------------------------------------
 // log semiring: inside + outside for one sentence
 // ---------------------------------------------------------------------------------------------
+// `small` = shared memory for dec and the cell table; `chart` = the chart arrays, in shared memory right behind them
+// (null) or, for sentences whose chart does not fit, in this CTA's slice of the global workspace (L2-resident).
+__device__ __forceinline__ unsigned char *chart_base(unsigned char *small, unsigned char *chart, int Nb) {
+    return chart ? chart : small + ((((size_t)Nb * 8 * 4 + 15) & ~(size_t)15) + (((size_t)ncells(Nb) * 2 + 15) & ~(size_t)15));
+}
+
 template <int NT, int CPT>
-__device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
+__device__ void log_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
-    float *sdec = reinterpret_cast<float *>(mem);
+    float *sdec = reinterpret_cast<float *>(small);
+    uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     LogChart c;
-    unsigned char *base = mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15);
+    unsigned char *base = chart_base(small, chart, Nb);
     if (CPT > 0) {  // running state in registers: only the 32 B of gradients per cell
         c.A0 = c.A1 = c.A2 = nullptr;
         c.gCL = reinterpret_cast<float2 *>(base); c.gCR = c.gCL + nc; c.gIL = c.gCR + nc; c.gIR = c.gIL + nc;
@@ -368,7 +375,6 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
         c.CL = reinterpret_cast<float2 *>(c.A2 + nc);
     }
     c.CR = c.CL + nc; c.IL = c.CR + nc; c.IR = c.IL + nc; c.X = c.IR + nc;
-    uint16_t *cw = reinterpret_cast<uint16_t *>(c.X + nc);
     const bool want_grad = (p.gdec != nullptr) || (p.gattach != nullptr);
     const bool prof = p.prof && b == 0 && tid == 0;
     long long t0c = 0;
@@ -581,17 +587,17 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *mem) {
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
 template <int NT, int CPT>
-__device__ void max_pass(const DmvArgs &p, int b, unsigned char *mem) {
+__device__ void max_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
-    float *sdec = reinterpret_cast<float *>(mem);
+    float *sdec = reinterpret_cast<float *>(small);
+    uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     MaxChart c;
-    c.VC = reinterpret_cast<float4 *>(mem + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
+    c.VC = reinterpret_cast<float4 *>(chart_base(small, chart, Nb));
     c.CL = reinterpret_cast<float2 *>(c.VC + nc);
     c.CR = c.CL + nc; c.IL = c.CR + nc; c.IR = c.IL + nc; c.VX = c.IR + nc;
     int *queue = reinterpret_cast<int *>(c.VX + nc);  // 2 x (2 Nb + 2) ints
-    uint16_t *cw = reinterpret_cast<uint16_t *>(queue + 2 * (2 * Nb + 2));
-    c.bp = reinterpret_cast<uint8_t *>(cw + nc + (nc & 1));
+    c.bp = reinterpret_cast<uint8_t *>(queue + 2 * (2 * Nb + 2));
     const bool prof = p.prof && b == 0 && tid == 0;
     long long t0c = 0;
     if (prof) t0c = clock64();
@@ -787,31 +793,43 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
             const int len = clamp_len(p, b);
             if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         }
-        if (which == 0) log_pass<NT, CPT>(p, b, smem_raw);
-        else max_pass<NT, CPT>(p, b, smem_raw);
+        unsigned char *chart = p.workspace ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
+        if (which == 0) log_pass<NT, CPT>(p, b, smem_raw, chart);
+        else max_pass<NT, CPT>(p, b, smem_raw, chart);
     }
 }
 
-size_t frontier_bytes(int cap, int passes, bool reg_state) {
-    const size_t nc = ncells(cap), dec = ((size_t)cap * 8 * 4 + 15) & ~(size_t)15;
+size_t frontier_small_bytes(int cap) {  // dec + cell table: always shared memory
+    return ((((size_t)cap * 8 * 4 + 15) & ~(size_t)15) + (((size_t)ncells(cap) * 2 + 15) & ~(size_t)15));
+}
+size_t frontier_chart_only_bytes(int cap, int passes, bool reg_state) {
+    const size_t nc = ncells(cap);
     size_t s = 0;
-    if (passes & 1) s = dec + nc * (reg_state ? 72 : 88) + nc * 2 + 16;
+    if (passes & 1) s = nc * (reg_state ? 72 : 88) + 16;
     if (passes & 2) {
-        const size_t m = dec + nc * 56 + (size_t)(2 * (2 * cap + 2)) * 4 + (nc + 1) * 2 + nc * 6 + 16;
+        const size_t m = nc * 56 + (size_t)(2 * (2 * cap + 2)) * 4 + nc * 6 + 16;
         s = m > s ? m : s;
     }
-    return (s + 255) & ~(size_t)255;
+    return s;
+}
+size_t frontier_bytes(int cap, int passes, bool reg_state) {
+    return (frontier_small_bytes(cap) + frontier_chart_only_bytes(cap, passes, reg_state) + 255) & ~(size_t)255;
 }
 
 }  // namespace
 
 bool dmv_frontier_fits(int cap, int passes, int smem_optin) { return cap <= 256 && frontier_bytes(cap, passes, false) <= (size_t)smem_optin; }
+size_t dmv_frontier_chart_bytes(int N, int passes) { return (frontier_chart_only_bytes(N, passes, false) + 255) & ~(size_t)255; }
 
-cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, cudaStream_t st) {
+cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, int max_grid,
+                                cudaStream_t st) {
+    // a.workspace != null: the chart lives in the CTA's slice of the workspace (stride a.ws_stride, max_grid slices)
     const int total = a.B * a.npass;
+    const bool global_chart = a.workspace != nullptr;
+    if (global_chart) reg_state = false;
     a.smem_n = cap;
     auto go = [&](auto kern, int nt, bool regs) -> cudaError_t {
-        const size_t smem = frontier_bytes(cap, passes, regs);
+        const size_t smem = global_chart ? ((frontier_small_bytes(cap) + 255) & ~(size_t)255) : frontier_bytes(cap, passes, regs);
         // the attribute / occupancy queries cost ~10 us of host time per call: remember them per (variant, shared memory)
         struct Cached { const void *fn; size_t smem; int occ, dev; };
         static thread_local Cached cache[32];
@@ -834,6 +852,7 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
         }
         int grid = sm_count * occ;
         if (grid > total) grid = total;
+        if (global_chart && grid > max_grid) grid = max_grid;
         kern<<<grid, nt, smem, st>>>(a);
         return cudaGetLastError();
     };

@@ -912,6 +912,11 @@ static cudaError_t device_info() {
     return cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 }
 
+size_t dmv_ws_slice_bytes(int N, int passes) {
+    const size_t a = dmv_chart_bytes(N, passes), b = dmv_frontier_chart_bytes(N, passes);
+    return a > b ? a : b;
+}
+
 size_t dmv_chart_bytes(int N, int passes /*1 log, 2 max, 3 both*/) {
     size_t s = 0;
     if (passes & 1) s = log_chart_bytes(N);
@@ -969,18 +974,28 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads
     // the role-split kernel below, which also covers the long sentences whose chart lives in global memory.
     static const int env_role = [] { const char *v = getenv("VLGAE_DMV_KERNEL"); return v && v[0] == 'r' ? 1 : 0; }();
     static const int env_ft = env_int("VLGAE_FRONTIER_THREADS", 0);
-    if (!env_role && g_tune_gmax == 0 && g_tune_threads == 0 && a.threads == 0 && dmv_frontier_fits(cap, passes, g_smem_optin)) {
+    const bool fits = dmv_frontier_fits(cap, passes, g_smem_optin);
+    // (a chart that fits the role kernel's shared-memory layout but not the frontier's comes without a workspace)
+    if (!env_role && g_tune_gmax == 0 && g_tune_threads == 0 && a.threads == 0 && cap <= 256 && (fits || a.workspace)) {
+        DmvArgs f = a;
         // Latency regime (every work item resident at once): many threads, running state in registers.  Throughput
         // regime: small CTAs with the state in shared memory (idle warps skip a phase entirely) -- measured on B200:
         // COCO-like bulk 806 us vs 1126, 512 x 16 words 31 us vs 58; 40-word charts prefer 256 threads / registers.
+        // Charts beyond shared memory (N > ~72): same kernel, chart arrays in the CTA's workspace slice (L2-resident).
         const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count;
         int ft;
         bool reg_state;
-        if (resident) { ft = cap <= 24 ? 256 : 512; reg_state = true; }
+        if (!fits) { ft = env_int("VLGAE_FRONTIER_BIG_THREADS", 1024); reg_state = false; }
+        else if (resident) { ft = cap <= 24 ? 256 : 512; reg_state = true; }
         else if (cap <= 33) { ft = cap <= 12 ? 64 : 128; reg_state = false; }
         else { ft = 256; reg_state = true; }
         if (env_ft > 0) ft = env_ft;
-        return launch_dmv_frontier(a, passes, cap, ft, reg_state, g_sm_count, st);
+        if (fits) { f.workspace = nullptr; f.ws_stride = 0; }
+        else {
+            if (!f.workspace) return cudaErrorInvalidValue;
+            f.ws_stride = dmv_ws_slice_bytes(a.N, 3);
+        }
+        return launch_dmv_frontier(f, passes, cap, ft, reg_state, g_sm_count, dmv_grid_for_workspace(a.B), st);
     }
     // CTA = 3 roles x LPR lanes with LPR >= cap - 1 (every width is one round); a tuning request can only widen it
     const int need = cap <= 33 ? 96 : (cap <= 65 ? 192 : (cap <= 129 ? 384 : 768));

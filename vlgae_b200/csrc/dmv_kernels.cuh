@@ -54,7 +54,10 @@ long long *dmv_profile_buffer();  // nullptr unless a debug buffer was registere
 cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st);
 // frontier schedule (dmv_frontier.cu): chart in shared memory only; `cap` = chart positions the launch is sized for
 bool dmv_frontier_fits(int cap, int passes, int smem_optin);
-cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, cudaStream_t st);
+size_t dmv_frontier_chart_bytes(int N, int passes);  // per-CTA workspace slice when the chart is in global memory
+cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, int max_grid,
+                                cudaStream_t st);
+size_t dmv_ws_slice_bytes(int N, int passes);  // what vlgae_dmv_workspace_bytes reserves per CTA (either schedule)
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);
 cudaError_t launch_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, cudaStream_t st);
