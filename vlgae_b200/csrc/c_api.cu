@@ -239,9 +239,18 @@ int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "scale_rows launch");
 }
 
+// DependencyCRF runs on the DMV kernels (see deptree_kernels.cu): workspace = dec | attach2 | g2 | DMV workspace.
+static size_t deptree_dmv_bytes(int B, int N, size_t *o_att, size_t *o_g2, size_t *o_ws) {
+    const size_t dec = (((size_t)B * N * 8 * 4) + 255) & ~(size_t)255, att = (((size_t)B * N * N * 2 * 4) + 255) & ~(size_t)255;
+    if (o_att) *o_att = dec;
+    if (o_g2) *o_g2 = dec + att;
+    if (o_ws) *o_ws = dec + 2 * att;
+    return dec + 2 * att + vlgae_dmv_workspace_bytes(B, N) + 256;
+}
+
 size_t vlgae_deptree_workspace_bytes(int B, int N) {
     if (B <= 0 || N < 1 || N > VLGAE_DMV_MAX_N) return 0;
-    return (size_t)B * vlgae::deptree_ws_stride(N);
+    return deptree_dmv_bytes(B, N, nullptr, nullptr, nullptr);
 }
 
 int vlgae_deptree(const float *arc, const int64_t *lengths, int B, int N, float fill, float mask_zero, int semiring,
@@ -252,11 +261,32 @@ int vlgae_deptree(const float *arc, const int64_t *lengths, int B, int N, float 
     if (B == 0) return VLGAE_OK;
     if (!workspace || workspace_bytes < vlgae_deptree_workspace_bytes(B, N))
         return fail(VLGAE_E_WORKSPACE, "%s", "deptree workspace too small");
-    vlgae::DepTreeArgs a;
-    a.arc = arc; a.lengths = lengths; a.B = B; a.N = N; a.fill = fill; a.mask_zero = mask_zero;
-    a.out = out; a.marg = marginals; a.heads = heads; a.workspace = workspace; a.ws_stride = vlgae::deptree_ws_stride(N);
-    cudaError_t e = vlgae::launch_deptree(a, semiring, (cudaStream_t)stream);
-    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "deptree launch");
+    (void)fill;  // positions beyond lengths[b] never enter the chart: every sentence is swept at its own length
+    size_t o_att, o_g2, o_ws;
+    deptree_dmv_bytes(B, N, &o_att, &o_g2, &o_ws);
+    unsigned char *w = reinterpret_cast<unsigned char *>(workspace);
+    float *dec = reinterpret_cast<float *>(w), *att = reinterpret_cast<float *>(w + o_att), *g2 = reinterpret_cast<float *>(w + o_g2);
+    void *dws = reinterpret_cast<void *>(((uintptr_t)(w + o_ws) + 255) & ~(uintptr_t)255);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = vlgae::launch_deptree_expand(arc, B, N, att, dec, st);
+    if (e != cudaSuccess) return cuda_fail(e, "deptree expand");
+    vlgae::DmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dec = dec; a.attach = att; a.lengths = lengths; a.B = B; a.N = N; a.mask_zero = mask_zero;
+    int rc;
+    if (semiring == 0) {
+        a.Z = out; a.gattach = marginals ? g2 : nullptr;
+        rc = run_dmv(a, 1, dws, vlgae_dmv_workspace_bytes(B, N), stream);
+    } else {
+        a.best = out; a.heads = heads; a.arcs = marginals ? g2 : nullptr;
+        rc = run_dmv(a, 2, dws, vlgae_dmv_workspace_bytes(B, N), stream);
+    }
+    if (rc) return rc;
+    if (marginals) {
+        e = vlgae::launch_deptree_collapse(g2, B, N, marginals, st);
+        if (e != cudaSuccess) return cuda_fail(e, "deptree collapse");
+    }
+    return VLGAE_OK;
 }
 
 size_t vlgae_align_workspace_bytes(int A, int V, int B, int Q, int D) {

@@ -1,4 +1,4 @@
-// deptree_kernels.cuh -- internal interface of the arc-factored (MBR) chart kernel.
+// deptree_kernels.cuh -- helpers that map the arc-factored (MBR) chart onto the DMV kernels.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -6,19 +6,8 @@
 
 namespace vlgae {
 
-struct DepTreeArgs {
-    const float *arc;        // [B][N][N] (head, child)
-    const int64_t *lengths;  // [B]
-    int B, N;
-    float fill, mask_zero;
-    float *out;      // [B]
-    float *marg;     // [B][N][N] or null
-    int64_t *heads;  // [B][N] or null
-    void *workspace;
-    size_t ws_stride;
-};
-
-size_t deptree_ws_stride(int N);
-cudaError_t launch_deptree(const DepTreeArgs &a, int semiring, cudaStream_t st);
+// attach2 [B][N][N][2] = (arc, arc), dec [B][N][8] = 0;  marg [B][N][N] = g2[..., 0] + g2[..., 1]
+cudaError_t launch_deptree_expand(const float *arc, int B, int N, float *attach2, float *dec, cudaStream_t st);
+cudaError_t launch_deptree_collapse(const float *g2, int B, int N, float *marg, cudaStream_t st);
 
 }  // namespace vlgae
