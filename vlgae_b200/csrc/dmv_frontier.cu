@@ -137,12 +137,11 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         CL[i] = make_float2(sdec[i * 8 + 1], sdec[i * 8 + 3]);
         CR[i] = make_float2(sdec[i * 8 + 5], sdec[i * 8 + 7]);
     }
-    if (MODE == 2) {
+    if constexpr (MODE == 2) {
         const int nc = ncells(Nb);
 #pragma unroll 1
         for (int c = Nb + tid; c < nc; c += NT) { IL[c] = __ldcg(sh_il + c); IR[c] = __ldcg(sh_ir + c); }
-        return;
-    }
+    } else {
     // arc scores in the order they lie in memory (row h: Nb contiguous float2), so that the reads coalesce -- they may
     // come straight from pinned host memory over PCIe (vlgae_dmv_parse_host)
 #pragma unroll 1
@@ -166,6 +165,7 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         __threadfence();
         __syncthreads();
         if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.share_flag + b), "r"(p.share_epoch) : "memory");
+    }
     }
 }
 

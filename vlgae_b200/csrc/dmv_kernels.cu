@@ -68,19 +68,6 @@ __host__ __device__ inline int ncells(int Nb) { return Nb * (Nb + 1) / 2; }
 __device__ __forceinline__ int dbase(int d, int Nb) { return d * Nb - ((d * (d - 1)) >> 1); }
 __device__ __forceinline__ int cidx(int lo, int d, int Nb) { return dbase(d, Nb) + lo; }
 
-// Index streams over the split point.  fwd: cell (lo, d0 + k g); bwd: cell (lo0 + k g, d0 - k g).
-// Successive differences of the diagonal-major index are linear in k, so each step is two integer adds.
-struct Stream {
-    int idx, step, dec;
-    __device__ __forceinline__ void fwd(int lo, int d, int g, int Nb) {
-        idx = cidx(lo, d, Nb); step = g * Nb - g * d - ((g * (g - 1)) >> 1); dec = g * g;
-    }
-    __device__ __forceinline__ void bwd(int lo, int d, int g, int Nb) {
-        idx = cidx(lo, d, Nb); step = -g * Nb + g * d - ((g * (g + 1)) >> 1) + g; dec = g * g;
-    }
-    __device__ __forceinline__ void next() { idx += step; step -= dec; }
-};
-
 __device__ __forceinline__ int ceil_log2(int x) { return x <= 1 ? 0 : 32 - __clz(x - 1); }
 
 // log2 of the lanes per span for width w: the smallest power of two that leaves every lane at most 2^tpl_log2 split
@@ -518,7 +505,7 @@ __device__ void log_pass(const DmvArgs &p, int b, void *mem, float *sdec, unsign
     __syncthreads();
 
     if (prof) p.prof[0] = clock64() - t0c;
-    Lane ln;
+    Lane ln{};
     ln.init<NT>(p, lgtab, Nb);
     if (ln.role == 0) inside_sweep<NT, 0>(c, ln, Nb, len, p.mask_zero, want_grad);
     else if (ln.role == 1) inside_sweep<NT, 1>(c, ln, Nb, len, p.mask_zero, want_grad);
@@ -709,7 +696,7 @@ __device__ void max_pass(const DmvArgs &p, int b, void *mem, float *sdec, unsign
     __syncthreads();
 
     if (prof) p.prof[4] = clock64() - t0c;
-    Lane ln;
+    Lane ln{};
     ln.init<NT>(p, lgtab, Nb);
     ProfAcc pa;
 #ifdef VLGAE_PROF_DETAIL
@@ -988,7 +975,8 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads
         if (!fits) { ft = env_int("VLGAE_FRONTIER_BIG_THREADS", 1024); reg_state = false; }
         else if (resident) { ft = cap <= 24 ? 256 : 512; reg_state = true; }
         else if (cap <= 33) { ft = cap <= 12 ? 64 : 128; reg_state = false; }
-        else { ft = 256; reg_state = true; }
+        else if (cap <= 45) { ft = 256; reg_state = true; }   // <= 1024 cells: 4 per thread in registers
+        else { ft = 512; reg_state = false; }                 // one CTA per SM: more threads (n = 64: 907 vs 1039 us)
         if (env_ft > 0) ft = env_ft;
         if (fits) { f.workspace = nullptr; f.ws_stride = 0; }
         else {
