@@ -351,18 +351,22 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
 // ---------------------------------------------------------------------------------------------
 // `small` = shared memory for dec and the cell table; `chart` = the chart arrays, in shared memory right behind them
 // (null) or, for sentences whose chart does not fit, in this CTA's slice of the global workspace (L2-resident).
+// (GC is a template parameter so that the shared-memory case keeps its address space at compile time: through one generic
+// pointer every chart access became a generic load / store and the cfg2 launch went from 56 to 60 us)
+template <bool GC>
 __device__ __forceinline__ unsigned char *chart_base(unsigned char *small, unsigned char *chart, int Nb) {
-    return chart ? chart : small + ((((size_t)Nb * 8 * 4 + 15) & ~(size_t)15) + (((size_t)ncells(Nb) * 2 + 15) & ~(size_t)15));
+    if (GC) return chart;
+    return small + ((((size_t)Nb * 8 * 4 + 15) & ~(size_t)15) + (((size_t)ncells(Nb) * 2 + 15) & ~(size_t)15));
 }
 
-template <int NT, int CPT>
+template <int NT, int CPT, bool GC>
 __device__ void log_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     LogChart c;
-    unsigned char *base = chart_base(small, chart, Nb);
+    unsigned char *base = chart_base<GC>(small, chart, Nb);
     if (CPT > 0) {  // running state in registers: only the 32 B of gradients per cell
         c.A0 = c.A1 = c.A2 = nullptr;
         c.gCL = reinterpret_cast<float2 *>(base); c.gCR = c.gCL + nc; c.gIL = c.gCR + nc; c.gIR = c.gIL + nc;
@@ -586,14 +590,14 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *small, unsigned
 // items of the back-trace: kind (0 CR, 1 CL, 2 IR, 3 IL) | v << 2 | lo << 3 | hi << 12
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
-template <int NT, int CPT>
+template <int NT, int CPT, bool GC>
 __device__ void max_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
     const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     MaxChart c;
-    c.VC = reinterpret_cast<float4 *>(chart_base(small, chart, Nb));
+    c.VC = reinterpret_cast<float4 *>(chart_base<GC>(small, chart, Nb));
     c.CL = reinterpret_cast<float2 *>(c.VC + nc);
     c.CR = c.CL + nc; c.IL = c.CR + nc; c.IR = c.IL + nc; c.VX = c.IR + nc;
     int *queue = reinterpret_cast<int *>(c.VX + nc);  // 2 x (2 Nb + 2) ints
@@ -778,7 +782,7 @@ __device__ void max_pass(const DmvArgs &p, int b, unsigned char *small, unsigned
 // ---------------------------------------------------------------------------------------------
 // kernel: persistent CTAs stride over (sentence, semiring) work items (same placement rule as dmv_kernels.cu)
 // ---------------------------------------------------------------------------------------------
-template <int NT, int CPT>
+template <int NT, int CPT, bool GC = false>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 6 : (NT == 64 ? 12 : 1)))) dmv_frontier_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.B * p.npass;
@@ -793,9 +797,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
             const int len = clamp_len(p, b);
             if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         }
-        unsigned char *chart = p.workspace ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
-        if (which == 0) log_pass<NT, CPT>(p, b, smem_raw, chart);
-        else max_pass<NT, CPT>(p, b, smem_raw, chart);
+        unsigned char *chart = GC ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
+        if (which == 0) log_pass<NT, CPT, GC>(p, b, smem_raw, chart);
+        else max_pass<NT, CPT, GC>(p, b, smem_raw, chart);
     }
 }
 
@@ -860,6 +864,7 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
     static const int env_smem_acc = [] { const char *v = getenv("VLGAE_FRONTIER_SMEM_ACC"); return v && *v ? atoi(v) : -1; }();
     if (env_smem_acc >= 0) reg_state = env_smem_acc == 0;
     const int cells = reg_state ? ncells(cap) - cap : (1 << 30);
+    if (global_chart) return threads <= 512 ? go(dmv_frontier_kernel<512, 0, true>, 512, false) : go(dmv_frontier_kernel<1024, 0, true>, 1024, false);
     if (threads <= 64) return cells <= 128 ? go(dmv_frontier_kernel<64, 2>, 64, true) : go(dmv_frontier_kernel<64, 0>, 64, false);
     if (threads <= 128) return cells <= 256 ? go(dmv_frontier_kernel<128, 2>, 128, true) : go(dmv_frontier_kernel<128, 0>, 128, false);
     if (threads <= 256) {
