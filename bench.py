@@ -283,7 +283,7 @@ def alignment_leg(dev, iters=10):
                     "rows padded to 8 floats", "ms": ms, "captions_per_s": B / (ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu capture, profiles/r1_align_kernel.txt)
-                     "traffic": 7.657e9, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
+                     "traffic": 7.61e9, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
                      "kernel": "align_gemm_kernel (+ align_pack_kernel x2)"},
         "tensor_tflops_issued": 3 * 2.0 * A * B * Q * V * D / (ms * 1e-3) / 1e12,
         "parity": {"mask_pattern_equal": bool(((got == -1e20) == masked).all()), "max_abs_err_vs_fp32_oracle": err},
