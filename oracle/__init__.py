@@ -171,3 +171,14 @@ def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, n
     maxatt = att.max(-1)
     tm = _f32(txt_marginal)
     return (maxatt * tm[:, None, :]).sum(-1) / tm.sum(1, keepdims=True)
+
+
+def word_factor_attention(vis_feat, txt_feat, vis_mid):
+    """``softmax_v(<txt[b,q,:], vis[b,v,:]>) @ vis_mid[b]`` (joint.py:668-673; the caller drops ROOT with ``[:, 1:]``
+    before and adds the residual + LayerNorm after)."""
+    vis_feat, txt_feat, vis_mid = _f32(vis_feat), _f32(txt_feat), _f32(vis_mid)
+    s = np.einsum("bvd,bqd->bqv", vis_feat, txt_feat)
+    s = s - s.max(-1, keepdims=True)
+    p = np.exp(s)
+    p /= p.sum(-1, keepdims=True)
+    return np.einsum("bqv,bvh->bqh", p, vis_mid)

@@ -149,3 +149,17 @@ def test_max_over_factors_equals_max_of_materialised(dev, A, V, B, Q, D):
     assert ((got == -1e20) == masked).all()
     scale = float(vis.norm(dim=-1).max() * txt.norm(dim=-1).max())
     assert np.abs(got - want)[~masked].max(initial=0.0) <= scale * 2.0 ** -15
+
+
+def test_word_factor_attention(dev):
+    """Row a10 (joint.py:668-673): library GEMMs + softmax, checked against the numpy restatement."""
+    from vlgae_b200.alignment import word_factor_attention
+
+    g = torch.Generator(device=dev).manual_seed(5)
+    vis = torch.randn(4, 300, 128, generator=g, device=dev) * 0.3
+    txt = torch.randn(4, 12, 128, generator=g, device=dev) * 0.3
+    mid = torch.randn(4, 300, 256, generator=g, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    got = word_factor_attention(vis, txt, mid).cpu().numpy()
+    want = oracle.word_factor_attention(vis.cpu().numpy(), txt.cpu().numpy(), mid.cpu().numpy())
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)

@@ -198,6 +198,17 @@ def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, *
     return torch.sum(maxatt * tm.unsqueeze(1), dim=-1) / tm.sum(1, keepdim=True)
 
 
+def word_factor_attention(vis_feat, txt_feat, vis_mid):
+    """Per-sample word -> factor attention of ``DependencyBoxRel._forward`` (joint.py:668-673):
+    ``softmax_v(<txt[b,q,:], vis[b,v,:]>) @ vis_mid[b]`` -> [B, Q, H].  Two plain batched GEMMs and a softmax (0.3 % of the
+    alignment contraction's flops at the cfg2 shape): run as library calls, differentiable through torch."""
+    vis_feat, txt_feat, vis_mid = map(_plain, (vis_feat, txt_feat, vis_mid))
+    if vis_feat.device.type != "cuda":
+        raise VlgaeError("vlgae_b200.alignment needs CUDA tensors (there is no CPU fallback)")
+    att = torch.bmm(txt_feat, vis_feat.transpose(1, 2)).softmax(2)
+    return torch.bmm(att, vis_mid)
+
+
 # ---- drop-in methods for the reference's implementation-group registry -------------------------------------------
 def gather_logit_simple_impl(self, inputs, vis, txt, vp):
     vis_feat, vis_mask, _ = vis
