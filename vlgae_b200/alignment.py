@@ -80,13 +80,18 @@ class _AlignLogits(torch.autograd.Function):
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
+            # batched GEMMs over strided views of g -- no permuted copy of the 7.4 GB gradient is ever made
             if ctx.needs_input_grad[0]:
-                # [A, V, B*Q] x [B*Q, D]
-                gv = torch.matmul(g.permute(1, 3, 0, 2).reshape(A, V, B * Q), (tf * mq.unsqueeze(-1)).reshape(B * Q, -1))
+                tfm = tf * mq.unsqueeze(-1)                                   # [B, Q, D]
+                gv = torch.zeros(A, V, vf.shape[2], dtype=torch.float32, device=g.device)
+                for b in range(B):                                            # batch = a: [V, Q] x [Q, D]
+                    gv.baddbmm_(g[b].transpose(1, 2), tfm[b].unsqueeze(0).expand(A, -1, -1))
                 gv = (gv * mv.unsqueeze(-1)).to(ctx.in_dtypes[0])
             if ctx.needs_input_grad[1]:
-                # [B, Q, A*V] x [A*V, D]
-                gt = torch.matmul(g.permute(0, 2, 1, 3).reshape(B, Q, A * V), (vf * mv.unsqueeze(-1)).reshape(A * V, -1))
+                vfm = vf * mv.unsqueeze(-1)                                   # [A, V, D]
+                gt = torch.zeros(B, Q, vf.shape[2], dtype=torch.float32, device=g.device)
+                for a in range(A):                                            # batch = b: [Q, V] x [V, D]
+                    gt.baddbmm_(g[:, a], vfm[a].unsqueeze(0).expand(B, -1, -1))
                 gt = (gt * mq.unsqueeze(-1)).to(ctx.in_dtypes[1])
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
