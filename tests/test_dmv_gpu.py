@@ -221,11 +221,23 @@ def test_empty_and_single_word(dev):
 
 @pytest.mark.parametrize("B,n", [(12, 64), (6, 100), (4, 128)])
 def test_long_sentences(dev, B, n):
-    """n = 64 stays in shared memory (256 threads); n >= 100 uses the global-workspace charts."""
+    """n = 64 stays in shared memory; n >= 100 uses the global-workspace charts (frontier kernel, chart in L2)."""
     g = torch.Generator().manual_seed(n)
     L = torch.randint(n // 2, n + 1, (B,), generator=g)
     L[0] = n
     check_all(*synth(B, n, 40 + n, L), dev)
+
+
+@pytest.mark.parametrize("B,n,seed", [(3, 44, 1), (5, 45, 2), (4, 46, 3), (300, 46, 4), (3, 49, 5), (2, 71, 6), (2, 72, 7),
+                                      (2, 73, 8), (40, 24, 9), (600, 25, 10), (700, 12, 11), (1200, 13, 12), (260, 33, 13)])
+def test_launch_variant_boundaries(dev, B, n, seed):
+    """Sizes that sit on the boundaries of the frontier kernel's launch variants: cells per thread in registers (<= 1024
+    cells: n <= 44), running state in shared memory, 64/128/256/512-thread CTAs, resident vs strided work items, and the
+    chart moving from shared memory to the global workspace (n >= 72).  Ragged lengths, everything against the oracle."""
+    g = torch.Generator().manual_seed(100 + seed)
+    L = torch.randint(1, n + 1, (B,), generator=g).sort(descending=True).values
+    L[0] = n
+    check_all(*synth(B, n, 60 + seed, L), dev)
 
 
 def test_cfg3_sweep_small(dev):
