@@ -164,6 +164,19 @@ int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, con
                        float *out, int out_row_stride, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * Backward of vlgae_align_logits: the reference's attmap is an autograd node (einsum + masked_fill_, joint.py:413-418).
+ *   grad_out [B][A][Q][grad_row_stride] (>= V) = d loss / d out;  masked entries pass no gradient:
+ *   grad_txt[b][q][:] = txt_mask[b][q] * sum_{a,v} grad_out[b][a][q][v] * vis_mask[a][v] * vis_feat[a][v][:]
+ *   grad_vis[a][v][:] = vis_mask[a][v] * sum_{b,q} grad_out[b][a][q][v] * txt_mask[b][q] * txt_feat[b][q][:]
+ * Either output may be NULL.  tcgen05 kernels streaming grad_out once each (converted to split bf16 on the fly).
+ * workspace: vlgae_align_workspace_bytes(A, V, B, Q, D) bytes.
+ */
+int vlgae_align_logits_backward(const float *grad_out, int grad_row_stride, const float *vis_feat,
+                                const unsigned char *vis_mask, const float *txt_feat, const unsigned char *txt_mask, int A,
+                                int V, int B, int Q, int D, int split, float *grad_vis, float *grad_txt, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
+/*
  * Maximum of the alignment scores over the factors, without materialising the [B][A][Q][V] tensor.
  * Replaces the first half of  gather_logit_reduced   src/model/joint.py:421-432
  *   (attmap = gather_logit_simple(...); maxatt = attmap.max(dim=-1).values):

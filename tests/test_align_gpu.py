@@ -163,3 +163,37 @@ def test_word_factor_attention(dev):
     got = word_factor_attention(vis, txt, mid).cpu().numpy()
     want = oracle.word_factor_attention(vis.cpu().numpy(), txt.cpu().numpy(), mid.cpu().numpy())
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("A,V,B,Q,D,pad", [(2, 150, 3, 20, 128, False), (3, 300, 4, 82, 128, True), (2, 129, 2, 130, 64, False),
+                                           (2, 40, 2, 5, 8, True), (5, 1369, 6, 82, 128, True)])
+def test_backward_kernels_against_fp64(dev, A, V, B, Q, D, pad):
+    """vlgae_align_logits_backward (tcgen05, split bf16) against the two transposed contractions in fp64, with the masks
+    folded in; `pad` passes the upstream gradient with padded rows (stride > V), as autograd does for the padded output."""
+    from vlgae_b200._lib import check, lib
+
+    g_ = torch.Generator(device=dev).manual_seed(A * 7 + Q)
+    vis = torch.randn(A, V, D, generator=g_, device=dev)
+    txt = torch.randn(B, Q, D, generator=g_, device=dev)
+    vm = torch.rand(A, V, generator=g_, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g_, device=dev) > 0.2
+    ld = (V + 7) // 8 * 8 if pad else V
+    gfull = torch.randn(B, A, Q, ld, generator=g_, device=dev)
+    g = gfull[..., :V]
+    gv = torch.full((A, V, D), 7.0, device=dev)
+    gt = torch.full((B, Q, D), 7.0, device=dev)
+    ws = torch.empty(lib().vlgae_align_workspace_bytes(A, V, B, Q, D), dtype=torch.uint8, device=dev)
+    vmu, tmu = vm.view(torch.uint8), tm.view(torch.uint8)
+    check(lib().vlgae_align_logits_backward(gfull.data_ptr(), ld, vis.data_ptr(), vmu.data_ptr(), txt.data_ptr(), tmu.data_ptr(),
+                                            A, V, B, Q, D, 3, gv.data_ptr(), gt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "bwd")
+    torch.cuda.synchronize()
+    gm = (g * vm[None, :, None, :] * tm[:, None, :, None]).double()
+    rv = torch.einsum("baqv,bqd->avd", gm, txt.double())
+    rt = torch.einsum("baqv,avd->bqd", gm, vis.double())
+    # error model of a split-bf16 product summed over K terms: 2^-16 per product, random-walk accumulation
+    tol_v = 2.0 ** -14 * float(g.abs().max() * txt.abs().max()) * (B * Q) ** 0.5
+    tol_t = 2.0 ** -14 * float(g.abs().max() * vis.abs().max()) * (A * V) ** 0.5
+    assert float((gv.double() - rv).abs().max()) <= tol_v
+    assert float((gt.double() - rt).abs().max()) <= tol_t
+    assert (gv[~vm] == 0).all() and (gt[~tm] == 0).all()   # masked rows receive exact zeros

@@ -36,6 +36,8 @@ PROTOTYPES = {
     "vlgae_align_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vlgae_align_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                    c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "vlgae_align_logits_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                            c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlgae_align_reduce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vlgae_align_max_over_factors": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                              c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

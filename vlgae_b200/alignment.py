@@ -57,10 +57,10 @@ def _launch(vf, vm, tf, tm, split, neg, pad_rows):
 class _AlignLogits(torch.autograd.Function):
     """The reference's attmap is an autograd node (einsum + two masked_fill_, joint.py:413-418): the grounding losses
     back-propagate through it into both encoders.  Forward = the tcgen05 kernel; backward = the two transposed
-    contractions with the masks folded into the operands (a masked entry was overwritten, so it passes no gradient):
+    contractions, also on tcgen05 (vlgae_align_logits_backward, csrc/align_bwd_kernels.cu), with the masks folded in (a
+    masked entry was overwritten, so it passes no gradient):
         d vis[a,v,:] = m_v[a,v] * sum_{b,q} g[b,a,q,v] * (m_q[b,q] txt[b,q,:])
-        d txt[b,q,:] = m_q[b,q] * sum_{a,v} g[b,a,q,v] * (m_v[a,v] vis[a,v,:])
-    run as fp32 library GEMMs for now (hand-written transposed kernels are listed under DESIGN.md "Next")."""
+        d txt[b,q,:] = m_q[b,q] * sum_{a,v} g[b,a,q,v] * (m_v[a,v] vis[a,v,:])"""
 
     @staticmethod
     def forward(ctx, vis_feat, txt_feat, vm, tm, split, neg, pad_rows):
@@ -68,33 +68,32 @@ class _AlignLogits(torch.autograd.Function):
         tf = txt_feat.detach().to(torch.float32).contiguous()
         ctx.save_for_backward(vf, tf, vm, tm)
         ctx.in_dtypes = (vis_feat.dtype, txt_feat.dtype)
+        ctx.split = int(split)
         return _launch(vf, vm, tf, tm, split, neg, pad_rows)
 
     @staticmethod
     def backward(ctx, g):
         vf, tf, vm, tm = ctx.saved_tensors
-        mv, mq = vm.to(torch.float32), tm.to(torch.float32)
-        g = g.to(torch.float32)
         B, A, Q, V = g.shape
-        gv = gt = None
-        tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            # batched GEMMs over strided views of g -- no permuted copy of the 7.4 GB gradient is ever made
-            if ctx.needs_input_grad[0]:
-                tfm = tf * mq.unsqueeze(-1)                                   # [B, Q, D]
-                gv = torch.zeros(A, V, vf.shape[2], dtype=torch.float32, device=g.device)
-                for b in range(B):                                            # batch = a: [V, Q] x [Q, D]
-                    gv.baddbmm_(g[b].transpose(1, 2), tfm[b].unsqueeze(0).expand(A, -1, -1))
-                gv = (gv * mv.unsqueeze(-1)).to(ctx.in_dtypes[0])
-            if ctx.needs_input_grad[1]:
-                vfm = vf * mv.unsqueeze(-1)                                   # [A, V, D]
-                gt = torch.zeros(B, Q, vf.shape[2], dtype=torch.float32, device=g.device)
-                for a in range(A):                                            # batch = b: [Q, V] x [V, D]
-                    gt.baddbmm_(g[:, a], vfm[a].unsqueeze(0).expand(B, -1, -1))
-                gt = (gt * mq.unsqueeze(-1)).to(ctx.in_dtypes[1])
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = tf32
+        D = vf.shape[2]
+        dev = g.device
+        g = g.to(torch.float32)
+        if g.stride(-1) != 1 or g.stride(2) < V or g.stride(1) != Q * g.stride(2) or g.stride(0) != A * Q * g.stride(2):
+            g = g.contiguous()  # rows may be padded (stride >= V); anything else is made dense
+        gv = torch.empty((A, V, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        gt = torch.empty((B, Q, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        ws = _workspace(dev, max(lib().vlgae_align_workspace_bytes(A, V, B, Q, D), 1))
+        with torch.cuda.device(dev):
+            check(lib().vlgae_align_logits_backward(g.data_ptr(), g.stride(2), vf.data_ptr(), vm.data_ptr(), tf.data_ptr(),
+                                                    tm.data_ptr(), A, V, B, Q, D, ctx.split,
+                                                    gv.data_ptr() if gv is not None else None,
+                                                    gt.data_ptr() if gt is not None else None, ws.data_ptr(), ws.numel(),
+                                                    torch.cuda.current_stream(dev).cuda_stream),
+                  "vlgae_align_logits_backward")
+        if gv is not None:
+            gv = gv.to(ctx.in_dtypes[0])
+        if gt is not None:
+            gt = gt.to(ctx.in_dtypes[1])
         return gv, gt, None, None, None, None, None
 
 

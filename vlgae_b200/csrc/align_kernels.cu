@@ -644,7 +644,28 @@ size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
     return pl.vis_packed_bytes + pl.txt_packed_bytes + ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
 }
 
-// mode 0 / 1: materialise the logits in `out`; mode 2: reduce over the factors into `red` (packed, zero-initialised here)
+// pack both operands (bf16 hi / lo, swizzled tile images) + the caption mask bits into the workspace:
+//   [vis tiles][caption tiles][mask bits]   (shared by the forward and the backward kernels)
+cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
+                                void *workspace, cudaStream_t st) {
+    cudaError_t e = align_device_info();
+    if (e != cudaSuccess) return e;
+    const AlignPlan pl = align_plan(A, V, B, Q, D);
+    uint8_t *ws = reinterpret_cast<uint8_t *>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    uint8_t *vis_packed = ws;
+    uint8_t *txt_packed = vis_packed + pl.vis_packed_bytes;
+    uint32_t *maskbits = reinterpret_cast<uint32_t *>(txt_packed + pl.txt_packed_bytes);
+    const size_t nv = (size_t)A * pl.VT * TILE_M * pl.KB * 8, nt = (size_t)B * pl.QT * TILE_M * pl.KB * 8;
+    int gv = (int)((nv + 255) / 256), gt = (int)((nt + 255) / 256);
+    const int cap = g_align_sm * 16;
+    if (gv > cap) gv = cap;
+    if (gt > cap) gt = cap;
+    align_pack_kernel<<<gv, 256, 0, st>>>(vis, nullptr, A, V, D, pl.KB, TILE_M, pl.tile_bytes, pl.VT, vis_packed, nullptr);
+    align_pack_kernel<<<gt, 256, 0, st>>>(txt, txt_mask, B, Q, D, pl.KB, TILE_M, pl.tile_bytes, pl.QT, txt_packed, maskbits);
+    return cudaGetLastError();
+}
+
+// mode 0 / 1: materialise the logits in `out`; mode 2: reduce over the factors (maxv / argv)
 static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask,
                                      int A, int V, int B, int Q, int D, float neg, int split, float *out, int ldv,
                                      float *maxv, int *argv, void *workspace, cudaStream_t st) {
@@ -656,17 +677,8 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     uint8_t *txt_packed = vis_packed + pl.vis_packed_bytes;
     uint32_t *maskbits = reinterpret_cast<uint32_t *>(txt_packed + pl.txt_packed_bytes);
 
-    {   // pack both operands (bf16 hi / lo, swizzled tile images)
-        const size_t nv = (size_t)A * pl.VT * TILE_M * pl.KB * 8, nt = (size_t)B * pl.QT * TILE_M * pl.KB * 8;
-        int gv = (int)((nv + 255) / 256), gt = (int)((nt + 255) / 256);
-        const int cap = g_align_sm * 16;
-        if (gv > cap) gv = cap;
-        if (gt > cap) gt = cap;
-        align_pack_kernel<<<gv, 256, 0, st>>>(vis, nullptr, A, V, D, pl.KB, TILE_M, pl.tile_bytes, pl.VT, vis_packed, nullptr);
-        align_pack_kernel<<<gt, 256, 0, st>>>(txt, txt_mask, B, Q, D, pl.KB, TILE_M, pl.tile_bytes, pl.QT, txt_packed, maskbits);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
+    e = align_pack_operands(vis, txt, txt_mask, A, V, B, Q, D, workspace, st);
+    if (e != cudaSuccess) return e;
 
     AlignArgs a{};
     a.vis_packed = vis_packed; a.txt_packed = txt_packed; a.txt_maskbits = maskbits; a.vis_mask = vis_mask;

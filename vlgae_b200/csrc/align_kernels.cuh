@@ -38,6 +38,13 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
 // max over the factors without materialising the logits: maxv [B][A][Q] fp32, argv [B][A][Q] int32 (first arg-max;
 // masked queries: neg / 0).  Workspace: align_workspace_bytes + align_reduce_bytes.
 size_t align_reduce_bytes(int A, int B, int Q);
+cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
+                                void *workspace, cudaStream_t st);
+// backward of the logits (align_bwd_kernels.cu): g [B][A][Q][ldg]; grad_vis [A][V][D] and / or grad_txt [B][Q][D] (null = skip);
+// workspace: align_workspace_bytes
+cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, const uint8_t *vis_mask, const float *txt,
+                                  const uint8_t *txt_mask, int A, int V, int B, int Q, int D, int split, float *grad_vis,
+                                  float *grad_txt, void *workspace, cudaStream_t st);
 cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
                                 int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
                                 cudaStream_t st);

@@ -310,6 +310,23 @@ int vlgae_align_logits(const float *vis_feat, const unsigned char *vis_mask, con
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align launch");
 }
 
+int vlgae_align_logits_backward(const float *grad_out, int grad_row_stride, const float *vis_feat,
+                                const unsigned char *vis_mask, const float *txt_feat, const unsigned char *txt_mask, int A,
+                                int V, int B, int Q, int D, int split, float *grad_vis, float *grad_txt, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    if (!grad_out || !vis_feat || !vis_mask || !txt_feat || !txt_mask) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (A < 0 || V < 0 || B < 0 || Q < 0) return fail(VLGAE_E_INVALID, "%s", "negative extent");
+    if (D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "D must be in [1, 128]");
+    if (split != 1 && split != 3) return fail(VLGAE_E_INVALID, "%s", "split must be 1 or 3");
+    if (grad_row_stride < V) return fail(VLGAE_E_INVALID, "%s", "grad_row_stride must be >= V");
+    if (A == 0 || V == 0 || B == 0 || Q == 0 || (!grad_vis && !grad_txt)) return VLGAE_OK;
+    const size_t need = vlgae::align_workspace_bytes(A, V, B, Q, D);
+    if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "alignment workspace too small");
+    cudaError_t e = vlgae::launch_align_backward(grad_out, grad_row_stride, vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q,
+                                                 D, split, grad_vis, grad_txt, workspace, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align backward launch");
+}
+
 size_t vlgae_align_reduce_workspace_bytes(int A, int V, int B, int Q, int D) {
     const size_t base = vlgae_align_workspace_bytes(A, V, B, Q, D);
     if (base == 0) return 0;
