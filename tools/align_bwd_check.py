@@ -40,10 +40,30 @@ for A, V, B, Q, D in shapes:
         print(f"A={A} V={V} B={B} Q={Q} D={D}: |d_vis err| {float((gv - rv).abs().max()):.3e} (scale {float(rv.abs().max()):.1f})  "
               f"|d_txt err| {float((gt - rt).abs().max()):.3e} (scale {float(rt.abs().max()):.1f})")
     else:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(3):
-            run()
-        b.record()
-        torch.cuda.synchronize()
-        print(f"A={A} V={V} B={B} Q={Q} D={D}: backward (both gradients) {a.elapsed_time(b) / 3:.3f} ms")
+        def timed(pv, pt):
+            def f():
+                check(lib().vlgae_align_logits_backward(g.data_ptr(), V, vis.data_ptr(), vmu.data_ptr(), txt.data_ptr(),
+                                                        tmu.data_ptr(), A, V, B, Q, D, int(os.environ.get("SPLIT", "3")), pv, pt, ws.data_ptr(), ws.numel(),
+                                                        torch.cuda.current_stream().cuda_stream), "bwd")
+            f()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                f()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / 3
+        import ctypes
+        prof = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+        lib().vlgae_dmv_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+        for name, pv, pt in (("d_txt", None, gt.data_ptr()), ("d_vis", gv.data_ptr(), None)):
+            prof.zero_()
+            timed(pv, pt)
+            pr = prof.view(148, 8).double().cpu()
+            pr = pr[pr[:, 0] > 0]
+            tot = pr[:, 0].mean().item()
+            print(f"  {name}: MMA warp {tot:.0f} clk per launch; waiting for the operand tile {100 * pr[:, 1].mean().item() / tot:.0f} %, "
+                  f"for the converted g image {100 * pr[:, 2].mean().item() / tot:.0f} %")
+        lib().vlgae_dmv_set_profile_buffer(ctypes.c_void_p(0))
+        print(f"A={A} V={V} B={B} Q={Q} D={D}: d_txt {timed(None, gt.data_ptr()):.3f} ms, d_vis {timed(gv.data_ptr(), None):.3f} ms, "
+              f"both {timed(gv.data_ptr(), gt.data_ptr()):.3f} ms  (gradient: {g.numel() * 4 / 2**30:.2f} GiB)")

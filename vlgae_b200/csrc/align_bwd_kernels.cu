@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include "align_kernels.cuh"
+#include "dmv_kernels.cuh"
 
 namespace vlgae {
 namespace {
@@ -121,6 +122,7 @@ struct BwdArgs {
     float *out;                    // KIND 0: d txt [B][Q][D]; KIND 1: d vis [A][V][D]
     int ldg, A, V, B, Q, D, KB, VT, QT, nq, split;
     int stages;                    // 2, or 1 when two stages do not fit (Q tiles of 128 queries with D = 128)
+    long long *prof;               // debug: per CTA clocks of the MMA warp (total, waiting for the operand tile, for the g image)
 };
 
 // KIND 0: item = (b, qt), steps = (a, vt);  KIND 1: item = (a, vt), steps = (b, qt)
@@ -178,12 +180,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
         // ===================== MMA issuer (converged warp, elect.sync) =====================
         const uint32_t idesc = KIND == 0 ? idesc_bf16(TILE, nq, true, false) : idesc_bf16(TILE, 64 * KB, true, true);
         uint32_t s = 0, ph = 0, it = 0;
+        long long t_op = 0, t_g = 0;
+        const long long t_begin = clock64();
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             mbar_wait(&sb->acc_empty, (it & 1) ^ 1);
             tc_fence_after();
             for (int step = 0; step < n_steps; ++step) {
+                const long long t0 = clock64();
                 mbar_wait(&sb->op_full[s], ph);
+                const long long t1 = clock64();
                 mbar_wait(&sb->g_full[s], ph);
+                t_op += t1 - t0;
+                t_g += clock64() - t1;
                 tc_fence_after();
                 const uint32_t op = smem_u32(smem + (size_t)s * stage_bytes), gi = op + op_alloc;
                 // hi*hi + lo*hi + hi*lo   (operand tile parts: chunk part * KB + block; g image parts: chunk part * 2 + block)
@@ -217,55 +225,70 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
             }
             tc_commit_elect(&sb->acc_full);
         }
+        if (p.prof && lane == 0) {
+            long long *o = p.prof + (size_t)blockIdx.x * 8;
+            o[0] = clock64() - t_begin; o[1] = t_op; o[2] = t_g;
+        }
     } else {
         // ===================== converters (all 16 warps) + epilogue (the first 4) =====================
         const int cw = warp - 2;
         uint32_t s = 0, ph = 0, it = 0;
+        constexpr int kRows = TILE / kConvWarps;  // rows per warp (nq <= 128)
+        // Loads of one step: this warp's rows q = cw + 16 r of the [queries x 128 factors] tile; a lane owns the factor pairs
+        // (64 j + 2 lane, + 1), j = 0, 1, so that hi and lo leave as ONE packed bf16x2 store each.  The other side's mask is
+        // folded in here (KIND 0: m_v per column, KIND 1: m_q per row); out-of-range elements are zero.  All loads of a step
+        // are issued together and one step ahead of their conversion: the tile comes cold from HBM.
+        auto load_step = [&](int item, int step, float (&x)[kRows][4]) {
+            int a, vt, b, qt;
+            if (KIND == 0) { b = item / p.QT; qt = item - b * p.QT; a = step / p.VT; vt = step - a * p.VT; }
+            else { a = item / p.VT; vt = item - a * p.VT; b = step / p.QT; qt = step - b * p.QT; }
+            const int q_lim = min(TILE, p.Q - qt * TILE);
+            bool colk[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int v = vt * TILE + 64 * (c >> 1) + 2 * lane + (c & 1);
+                colk[c] = v < p.V && (KIND == 1 || p.vis_mask[(size_t)a * p.V + v] != 0);
+            }
+            const float *gsrc = p.g + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE) * p.ldg + (size_t)vt * TILE + 2 * lane;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int q = cw + r * kConvWarps;
+                const bool rowk = q < q_lim && (KIND == 0 || p.txt_mask[(size_t)b * p.Q + qt * TILE + q] != 0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    x[r][c] = (rowk && colk[c]) ? __ldcs(gsrc + (size_t)q * p.ldg + 64 * (c >> 1) + (c & 1)) : 0.f;
+            }
+        };
+        // byte offset of this lane's pair inside a 128-byte row of the swizzled image: 16-byte unit (lane >> 2) ^ (q & 7),
+        // and q & 7 == cw & 7 for every row of this warp (rows are 16 apart)
+        const uint32_t lane_off = (uint32_t)((((lane >> 2) ^ (cw & 7)) << 4) + (lane & 3) * 4 + cw * 128);
+        float x[kRows][4], xn[kRows][4];
+        if ((int)blockIdx.x < n_items) load_step(blockIdx.x, 0, x);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             for (int step = 0; step < n_steps; ++step) {
-                int a, vt, b, qt;
-                if (KIND == 0) { b = item / p.QT; qt = item - b * p.QT; a = step / p.VT; vt = step - a * p.VT; }
-                else { a = item / p.VT; vt = item - a * p.VT; b = step / p.QT; qt = step - b * p.QT; }
-                const int q_lim = min(TILE, p.Q - qt * TILE);
-                // per-lane factor columns v = lane + 32 j and their mask (KIND 0 folds m_v into g, KIND 1 folds m_q)
-                float colw[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int v = vt * TILE + lane + 32 * j;
-                    colw[j] = v < p.V ? (KIND == 0 ? (p.vis_mask[(size_t)a * p.V + v] ? 1.f : 0.f) : 1.f) : -1.f;  // -1: out of range
-                }
-                // all loads of this warp's rows are issued first (and before the wait for the shared-memory slot): the tile
-                // comes cold from HBM, one row at a time would pay the DRAM latency kRows times per step
-                constexpr int kRows = TILE / kConvWarps;  // rows per warp (nq <= 128)
-                const float *gsrc = p.g + (((size_t)b * p.A + a) * p.Q + (size_t)qt * TILE) * p.ldg + (size_t)vt * TILE + lane;
-                float x[kRows][4];
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) {
-                    const int q = cw + r * kConvWarps;
-                    float roww = 0.f;
-                    if (q < q_lim) roww = KIND == 1 ? (p.txt_mask[(size_t)b * p.Q + qt * TILE + q] ? 1.f : 0.f) : 1.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        x[r][j] = (roww != 0.f && colw[j] > 0.f) ? __ldcs(gsrc + (size_t)q * p.ldg + 32 * j) : 0.f;
-                }
+                // the next step's tile (possibly the next item's first) is requested before this one is converted
+                if (step + 1 < n_steps) load_step(item, step + 1, xn);
+                else if (item + (int)gridDim.x < n_items) load_step(item + gridDim.x, 0, xn);
                 mbar_wait(&sb->empty[s], ph ^ 1);
-                uint8_t *gi = smem + (size_t)s * stage_bytes + op_alloc;
+                uint8_t *gi = smem + (size_t)s * stage_bytes + op_alloc + lane_off;
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
-                    const int q = cw + r * kConvWarps;
-                    if (q < nq) {
+                    if (cw + r * kConvWarps < nq) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(x[r][j]);
-                            const __nv_bfloat16 l = __float2bfloat16_rn(x[r][j] - __bfloat162float(h));
-                            const int vv = lane + 32 * (j & 1);  // column inside the 64-factor block j >> 1
-                            const uint32_t off = (uint32_t)(j >> 1) * chunk_g + (uint32_t)q * 128u +
-                                                 (uint32_t)((((vv >> 3) ^ (q & 7)) << 4) + (vv & 7) * 2);
-                            *reinterpret_cast<__nv_bfloat16 *>(gi + off) = h;
-                            *reinterpret_cast<__nv_bfloat16 *>(gi + 2u * chunk_g + off) = l;
+                        for (int j = 0; j < 2; ++j) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(x[r][2 * j], x[r][2 * j + 1]);
+                            const float2 hf = __bfloat1622float2(h);
+                            const __nv_bfloat162 l = __floats2bfloat162_rn(x[r][2 * j] - hf.x, x[r][2 * j + 1] - hf.y);
+                            uint8_t *dst = gi + (uint32_t)j * chunk_g + (uint32_t)(r * kConvWarps) * 128u;
+                            *reinterpret_cast<__nv_bfloat162 *>(dst) = h;
+                            *reinterpret_cast<__nv_bfloat162 *>(dst + 2u * chunk_g) = l;
                         }
                     }
                 }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) x[r][c] = xn[r][c];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sb->g_full[s]);
@@ -337,6 +360,7 @@ cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, con
     a.g = g; a.ldg = ldg; a.vis_mask = vis_mask; a.txt_mask = txt_mask;
     a.A = A; a.V = V; a.B = B; a.Q = Q; a.D = D; a.KB = pl.KB; a.VT = pl.VT; a.QT = pl.QT; a.nq = pl.nq;
     a.split = split == 1 ? 1 : 3;
+    a.prof = dmv_profile_buffer();
     const size_t g_bytes = (size_t)4 * pl.nq * 128;
     auto run = [&](auto kern, size_t stage, int items) -> cudaError_t {
         const size_t fixed = sizeof(BwdSmem) + 64;
