@@ -273,6 +273,31 @@ def alignment_leg(dev, iters=10):
         tsrc = "MEASURED_PEAKS.json bf16_tflops (measured, burst)"
     except Exception:  # noqa: BLE001
         tpeak, tsrc = 1500.0, "fallback 1.5 PFLOP/s dense bf16 (B200_PROFILING.md)"
+    # backward of the materialised logits (both transposed contractions, tcgen05): upstream gradient = ones
+    from vlgae_b200._lib import check as _check, lib as _lib
+    gup = torch.ones((B, A, Q, V), dtype=torch.float32, device=dev)
+    gvis, gtxt = torch.empty_like(vis), torch.empty_like(txt)
+    ws = torch.empty(_lib().vlgae_align_workspace_bytes(A, V, B, Q, D), dtype=torch.uint8, device=dev)
+    vmu, tmu = vm.view(torch.uint8), tm.view(torch.uint8)
+
+    def bwd():
+        _check(_lib().vlgae_align_logits_backward(gup.data_ptr(), V, vis.data_ptr(), vmu.data_ptr(), txt.data_ptr(), tmu.data_ptr(),
+                                                  A, V, B, Q, D, 3, gvis.data_ptr(), gtxt.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits_backward")
+    bwd()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        bwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_bwd = e0.elapsed_time(e1) / iters
+    want_t = ((vis * vm.unsqueeze(-1)).sum((0, 1)).unsqueeze(0).unsqueeze(0) * tm.unsqueeze(-1)).cpu()  # g = 1: sum of kept vis rows
+    bwd_err = float((gtxt.cpu() - want_t).abs().max() / want_t.abs().max())
+    del gup
+    backward = {"workload": "vlgae_align_logits_backward (d vis and d txt, gradient streamed once each), same shape",
+                "ms": ms_bwd, "gradient_gb_per_s": 2 * out_bytes / (ms_bwd * 1e-3) / 1e9,
+                "rel_err_d_txt_vs_closed_form": bwd_err}
     reduced = {"workload": "vlgae_align_max_over_factors (max over V in the epilogue; joint.py:421-428), same shape",
                "ms": ms_red, "bit_identical_to_max_of_materialised": bool(torch.equal(maxv, ref_max)),
                "roofline": {"bound": "tensor", "achieved": flops / (ms_red * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
@@ -289,6 +314,7 @@ def alignment_leg(dev, iters=10):
         "parity": {"mask_pattern_equal": bool(((got == -1e20) == masked).all()), "max_abs_err_vs_fp32_oracle": err},
         "gpu_launches_per_call": 3,
         "reduced": reduced,
+        "backward": backward,
     }
 
 
