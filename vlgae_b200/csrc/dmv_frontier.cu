@@ -120,6 +120,20 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         __syncthreads();
         dec = sh_dec;
     }
+    // the first arc scores are requested together with dec, not after it: from host memory each is a PCIe round trip
+    constexpr int kPre = 4;
+    float2 pre[kPre];
+    if (MODE != 2) {
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int t = tid + k * NT;
+            pre[k] = make_float2(0.f, 0.f);
+            if (t < Nb * Nb) {
+                const int h = t / Nb, ch = t - h * Nb;
+                pre[k] = *reinterpret_cast<const float2 *>(attach + ((size_t)h * N + ch) * 2);
+            }
+        }
+    }
 #pragma unroll 1
     for (int t = tid; t < Nb * 8; t += NT) {
         const float v = MODE == 2 ? __ldcg(dec + t) : dec[t];
@@ -145,10 +159,12 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
     // arc scores in the order they lie in memory (row h: Nb contiguous float2), so that the reads coalesce -- they may
     // come straight from pinned host memory over PCIe (vlgae_dmv_parse_host)
 #pragma unroll 1
-    for (int t = tid; t < Nb * Nb; t += NT) {
+    for (int t = tid, k = 0; t < Nb * Nb; t += NT, ++k) {
         const int h = t / Nb, ch = t - h * Nb;
         if (h == ch) continue;
-        const float2 a = *reinterpret_cast<const float2 *>(attach + ((size_t)h * N + ch) * 2);
+        float2 a;
+        if (k < kPre) a = k == 0 ? pre[0] : (k == 1 ? pre[1] : (k == 2 ? pre[2] : pre[3]));
+        else a = *reinterpret_cast<const float2 *>(attach + ((size_t)h * N + ch) * 2);
         if (ch < h) {
             const float2 v = make_float2(__fadd_rn(a.x, sdec[h * 8 + 0]), __fadd_rn(a.y, sdec[h * 8 + 2]));
             const int c = cidx(ch, h - ch, Nb);
@@ -360,9 +376,9 @@ __device__ __forceinline__ unsigned char *chart_base(unsigned char *small, unsig
 }
 
 template <int NT, int CPT, bool GC>
-__device__ void log_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
+__device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
-    const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
+    const int Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     LogChart c;
@@ -591,9 +607,9 @@ __device__ void log_pass(const DmvArgs &p, int b, unsigned char *small, unsigned
 __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return kind | (v << 2) | (lo << 3) | (hi << 12); }
 
 template <int NT, int CPT, bool GC>
-__device__ void max_pass(const DmvArgs &p, int b, unsigned char *small, unsigned char *chart) {
+__device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
     const int tid = threadIdx.x, N = p.N;
-    const int len = clamp_len(p, b), Nb = len + 1, nc = ncells(Nb);
+    const int Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
     MaxChart c;
@@ -793,13 +809,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }
-        {
-            const int len = clamp_len(p, b);
-            if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
-        }
+        const int len = clamp_len(p, b);  // read once: the lengths may live in host memory (one PCIe round trip)
+        if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         unsigned char *chart = GC ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
-        if (which == 0) log_pass<NT, CPT, GC>(p, b, smem_raw, chart);
-        else max_pass<NT, CPT, GC>(p, b, smem_raw, chart);
+        if (which == 0) log_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
+        else max_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
     }
 }
 
