@@ -88,6 +88,16 @@ struct MaxChart {
     uint8_t *bp;  // 6 bytes per cell: XL, XR, CL[HAS], CL[NO], CR[HAS], CR[NO]  (first maximal split)
 };
 
+// NT == 32 is the warp-per-sentence mode: the "block" of a sentence is one warp, its barrier is __syncwarp and its
+// thread index the lane (several sentences share a CTA, each with its own slice of shared memory)
+template <int NT>
+__device__ __forceinline__ void blk_sync() {
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ int blk_tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+
 __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
     int len = (int)p.lengths[b];
     return len < 0 ? 0 : (len > p.N - 1 ? p.N - 1 : len);
@@ -99,7 +109,7 @@ __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
 template <int NT, int MODE>
 __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, float *sdec, uint16_t *cw, float2 *CL, float2 *CR,
                                              float2 *IL, float2 *IR) {
-    const int tid = threadIdx.x, N = p.N;
+    const int tid = blk_tid<NT>(), N = p.N;
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
     float *sh_dec = nullptr;
@@ -117,7 +127,7 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
                 if (v != p.share_epoch) __nanosleep(100);
             } while (v != p.share_epoch);
         }
-        __syncthreads();
+        blk_sync<NT>();
         dec = sh_dec;
     }
     // the first arc scores are requested together with dec, not after it: from host memory each is a PCIe round trip
@@ -145,7 +155,7 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         const int base = dbase(d, Nb);
         for (int lo = 0; lo < Nb - d; ++lo) cw[base + lo] = (uint16_t)((d << 8) | lo);
     }
-    __syncthreads();
+    blk_sync<NT>();
 #pragma unroll 1
     for (int i = tid; i < Nb; i += NT) {
         CL[i] = make_float2(sdec[i * 8 + 1], sdec[i * 8 + 3]);
@@ -179,7 +189,7 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
     }
     if (MODE == 1) {
         __threadfence();
-        __syncthreads();
+        blk_sync<NT>();
         if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.share_flag + b), "r"(p.share_epoch) : "memory");
     }
     }
@@ -194,7 +204,7 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CPT>
 __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
-    const int tid = threadIdx.x, nc = ncells(Nb);
+    const int tid = blk_tid<NT>(), nc = ncells(Nb);
     const int H = (nc - Nb + CPT - 1) / CPT;
     int ow[CPT], oi[CPT];
     float ax[CPT][4], al[CPT][4], ar[CPT][4];
@@ -233,7 +243,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     }
                 }
             }
-            __syncthreads();
+            blk_sync<NT>();
         }
         if (s == len) break;
         // phase B(s): complete items of width s are final
@@ -273,13 +283,13 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                 }
             }
         }
-        __syncthreads();
+        blk_sync<NT>();
     }
 }
 
 template <int NT, int CPT>
 __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
-    const int tid = threadIdx.x, nc = ncells(Nb);
+    const int tid = blk_tid<NT>(), nc = ncells(Nb);
     const int H = (nc - Nb + CPT - 1) / CPT;
     int ow[CPT], oi[CPT];
     float vx[CPT][2], vc[CPT][4];
@@ -321,7 +331,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     }
                 }
             }
-            __syncthreads();
+            blk_sync<NT>();
         }
         if (s == len) break;
 #pragma unroll
@@ -358,7 +368,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                 }
             }
         }
-        __syncthreads();
+        blk_sync<NT>();
     }
 }
 
@@ -377,7 +387,7 @@ __device__ __forceinline__ unsigned char *chart_base(unsigned char *small, unsig
 
 template <int NT, int CPT, bool GC>
 __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
-    const int tid = threadIdx.x, N = p.N;
+    const int tid = blk_tid<NT>(), N = p.N;
     const int Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
@@ -408,7 +418,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
 #pragma unroll 1
         for (int t = Nb + tid; t < nc; t += NT) { c.A0[t] = init; c.A1[t] = init; c.A2[t] = init; }
     }
-    __syncthreads();
+    blk_sync<NT>();
     if (prof) p.prof[0] = clock64() - t0c;
 
     // ---------------- inside ----------------
@@ -446,7 +456,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
                         c.A1[cc] = a1; c.A2[cc] = a2;
                     }
                 }
-                __syncthreads();
+                blk_sync<NT>();
             }
             if (s == len) break;
             // phase B(s): complete items of width s are final
@@ -496,13 +506,13 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
                         c.A1[cc] = a1; c.A2[cc] = a2;
                     }
                 }
-                __syncthreads();
+                blk_sync<NT>();
             }
         }
     }
     if (prof) p.prof[1] = clock64() - t0c;
     if (tid == 0) p.Z[b] = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65
-    if (!want_grad) { __syncthreads(); return; }
+    if (!want_grad) { blk_sync<NT>(); return; }
 
     // ---------------- outside (explicit reverse sweep) ----------------
     {
@@ -510,9 +520,9 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         float4 *g4 = reinterpret_cast<float4 *>(c.gCL);  // gCL, gCR, gIL, gIR are contiguous: 2 nc float4
 #pragma unroll 1
         for (int t = tid; t < 2 * nc; t += NT) g4[t] = z;
-        __syncthreads();
+        blk_sync<NT>();
         if (tid == 0) c.gCR[cidx(0, len, Nb)].y = p.gZ ? p.gZ[b] : 1.f;
-        __syncthreads();
+        blk_sync<NT>();
     }
 #pragma unroll 1
     for (int w = len; w >= 1; --w) {
@@ -549,7 +559,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             c.gIR[cl4] = make_float2(o3.x + q0, o3.y + q1);
             c.gCR[cr4].y = o4 + (q0 + q1);
         }
-        __syncthreads();
+        blk_sync<NT>();
         // phase B'(w): incomplete parents of width w (steps 1, 2 transposed)
 #pragma unroll 1
         for (int t = tid; t < ntask; t += NT) {
@@ -563,7 +573,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             c.gCR[cl] = make_float2(ol.x + pR, ol.y + pL);    // CR[i, r]: .HAS from step 2, .NO from step 1
             c.gCL[cr] = make_float2(orr.x + pL, orr.y + pR);  // CL[r+1, j]: .HAS from step 1, .NO from step 2
         }
-        __syncthreads();
+        blk_sync<NT>();
     }
     if (prof) p.prof[2] = clock64() - t0c;
 
@@ -596,7 +606,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             *reinterpret_cast<float4 *>(gd + i * 8 + dir * 4) = make_float4(go.x, stop.x, go.y, stop.y);  // [dir][val][decision]
         }
     }
-    __syncthreads();
+    blk_sync<NT>();
     if (prof) p.prof[3] = clock64() - t0c;
 }
 
@@ -608,7 +618,7 @@ __device__ __forceinline__ int mk_item(int kind, int v, int lo, int hi) { return
 
 template <int NT, int CPT, bool GC>
 __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
-    const int tid = threadIdx.x, N = p.N;
+    const int tid = blk_tid<NT>(), N = p.N;
     const int Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
     uint16_t *cw = reinterpret_cast<uint16_t *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15));
@@ -642,7 +652,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     }
     if (p.vgdec) for (int t = tid; t < N * 8; t += NT) p.vgdec[(size_t)b * N * 8 + t] = 0.f;
     if (p.heads) for (int t = tid; t < N; t += NT) p.heads[(size_t)b * N + t] = 0;
-    __syncthreads();
+    blk_sync<NT>();
     if (prof) p.prof[4] = clock64() - t0c;
 
     if (reg_state) {
@@ -679,7 +689,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
                         c.VC[cc] = v;
                     }
                 }
-                __syncthreads();
+                blk_sync<NT>();
             }
             if (s == len) break;
             {
@@ -730,7 +740,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
                         c.VC[cc] = v;
                     }
                 }
-                __syncthreads();
+                blk_sync<NT>();
             }
         }
     }
@@ -791,7 +801,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             ncur = nnext;
         }
     }
-    __syncthreads();
+    blk_sync<NT>();
     if (prof) p.prof[6] = clock64() - t0c;
 }
 
@@ -814,6 +824,26 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
         unsigned char *chart = GC ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
         if (which == 0) log_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
         else max_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
+    }
+}
+
+// Warp-per-sentence variant for short sentences in the throughput regime: WPC sentences per CTA, each warp runs the
+// same sweeps with __syncwarp as its barrier (a phase of a 12-word chart has < 32 active cells; a block barrier and 3 idle
+// warps per phase cost more than the work), state in registers (<= CPT cells per lane).
+template <int WPC, int CPT>
+__global__ void __launch_bounds__(32 * WPC, CPT <= 3 ? 6 : 4) dmv_frontier_warp_kernel(DmvArgs p, int slice_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    unsigned char *slice = smem_raw + (size_t)warp * slice_bytes;
+    const int total = p.B * p.npass;
+    for (int item = blockIdx.x * WPC + warp; item < total; item += gridDim.x * WPC) {
+        int b, which;
+        if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
+        else { which = p.first_pass; b = item; }
+        const int len = clamp_len(p, b);
+        if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
+        if (which == 0) log_pass<32, CPT, false>(p, b, len, slice, nullptr);
+        else max_pass<32, CPT, false>(p, b, len, slice, nullptr);
     }
 }
 
@@ -878,6 +908,28 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
     static const int env_smem_acc = [] { const char *v = getenv("VLGAE_FRONTIER_SMEM_ACC"); return v && *v ? atoi(v) : -1; }();
     if (env_smem_acc >= 0) reg_state = env_smem_acc == 0;
     const int cells = reg_state ? ncells(cap) - cap : (1 << 30);
+    if (threads == 32 && !global_chart) {  // warp per sentence, 4 sentences per CTA
+        constexpr int WPC = 4;
+        const int cells = ncells(cap) - cap;
+        if (cells <= 5 * 32) {
+            const size_t slice = (frontier_bytes(cap, passes, true) + 15) & ~(size_t)15;
+            auto gow = [&](auto kern) -> cudaError_t {
+                const size_t smem = slice * WPC;
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                int occ = 0;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * WPC, smem);
+                if (e != cudaSuccess) return e;
+                if (occ < 1) occ = 1;
+                int grid = sm_count * occ, need = (total + WPC - 1) / WPC;
+                if (grid > need) grid = need;
+                kern<<<grid, 32 * WPC, smem, st>>>(a, (int)slice);
+                return cudaGetLastError();
+            };
+            return cells <= 3 * 32 ? gow(dmv_frontier_warp_kernel<WPC, 3>) : gow(dmv_frontier_warp_kernel<WPC, 5>);
+        }
+        threads = 64;
+    }
     if (global_chart) return threads <= 512 ? go(dmv_frontier_kernel<512, 0, true>, 512, false) : go(dmv_frontier_kernel<1024, 0, true>, 1024, false);
     if (threads <= 64) return cells <= 128 ? go(dmv_frontier_kernel<64, 2>, 64, true) : go(dmv_frontier_kernel<64, 0>, 64, false);
     if (threads <= 128) return cells <= 256 ? go(dmv_frontier_kernel<128, 2>, 128, true) : go(dmv_frontier_kernel<128, 0>, 128, false);

@@ -974,7 +974,11 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads
         bool reg_state;
         if (!fits) { ft = env_int("VLGAE_FRONTIER_BIG_THREADS", 1024); reg_state = false; }
         else if (resident) { ft = cap <= 24 ? 256 : 512; reg_state = true; }
-        else if (cap <= 33) { ft = cap <= 12 ? 64 : 128; reg_state = false; }
+        // warp per sentence for short charts; with 5 cells per lane (15-17 positions) a sentence takes longer than in a
+        // 128-thread CTA, so that size only switches inside bulk (length-bucketed) launches (682 vs 714 us)
+        else if (cap <= 14 || (cap <= 17 && a.nb_hi < a.N))  // nb_hi < N: a length bucket of a bulk launch
+            { ft = env_int("VLGAE_FRONTIER_WARP", 1) ? 32 : (cap <= 12 ? 64 : 128); reg_state = false; }
+        else if (cap <= 33) { ft = 128; reg_state = false; }
         else if (cap <= 45) { ft = 256; reg_state = true; }   // <= 1024 cells: 4 per thread in registers
         else { ft = 512; reg_state = false; }                 // one CTA per SM: more threads (n = 64: 907 vs 1039 us)
         if (env_ft > 0) ft = env_ft;
