@@ -292,11 +292,12 @@ def test_host_buffer_entry_point(dev):
     np.testing.assert_array_equal(heads, oheads)
 
 
-@pytest.mark.parametrize("B,n,ragged", [(16, 12, False), (128, 40, True), (300, 9, True)])
+@pytest.mark.parametrize("B,n,ragged", [(16, 12, False), (128, 40, True), (300, 9, True), (5, 79, True)])
 def test_host_entry_point_pinned_zero_copy(dev, B, n, ragged):
     """Pinned host buffers take the zero-copy path (the kernel reads / writes host memory itself and the log CTA of a
     sentence hands the staged inputs to its max CTA); results must equal the device-pointer entry point bit for bit.
-    Called three times on the same buffers: the hand-off flags are epoch-numbered, not reset."""
+    Called three times on the same buffers: the hand-off flags are epoch-numbered, not reset.  n = 79 needs the global
+    chart workspace, so that case exercises the staged (arena) path with pinned buffers."""
     from vlgae_b200 import ops
     from vlgae_b200._lib import check, lib
 
