@@ -25,7 +25,7 @@ tot = sum(d[0] for d in data)
 toti = sum(d[1] for d in data)
 print(f"total samples {tot}  total warp-instructions {toti}")
 stall_keys = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
-for s, ins, line, src, d in sorted(data, reverse=True)[:top]:
+for s, ins, line, src, d in sorted(data, key=lambda r: r[:3], reverse=True)[:top]:
     stalls = sorted(((int(d.get(k, 0) or 0), k[6:]) for k in stall_keys), reverse=True)[:3]
     st = " ".join(f"{k}:{v}" for v, k in stalls if v)
     print(f"{100.0 * s / max(tot, 1):5.1f}%  inst {ins:8d}  L{line:<4d} {src}\n        {st}")
