@@ -122,6 +122,7 @@ struct BwdArgs {
     float *out;                    // KIND 0: d txt [B][Q][D]; KIND 1: d vis [A][V][D]
     int ldg, A, V, B, Q, D, KB, VT, QT, nq, split;
     int stages;                    // 2, or 1 when two stages do not fit (Q tiles of 128 queries with D = 128)
+    int ksplit;                    // work units per item: each reduces a contiguous range of the steps and ADDS its partial
     long long *prof;               // debug: per CTA clocks of the MMA warp (total, waiting for the operand tile, for the g image)
 };
 
@@ -160,13 +161,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
     const int n_items = KIND == 0 ? p.B * p.QT : p.A * p.VT;
     const int n_steps = KIND == 0 ? p.A * p.VT : p.B * p.QT;
     const int NOUT = KIND == 0 ? nq : 64 * KB;   // accumulator columns (MMA N)
+    // A work unit = (item, k-slice): with KS > 1 an item's steps are cut into KS contiguous ranges whose partial results
+    // are added with fp32 atomics (the output is zeroed by the launcher).  That evens out the waves (128 captions on 148
+    // SMs leave 14 % of the machine idle) and shortens the chains of truncating tensor-core accumulations 15-fold.
+    const int KS = p.ksplit, n_units = n_items * KS;
+    auto unit = [&](int u, int &item, int &s0, int &s1) {
+        item = u / KS;
+        const int ks = u - item * KS;
+        s0 = (int)(((long long)ks * n_steps) / KS);
+        s1 = (int)(((long long)(ks + 1) * n_steps) / KS);
+    };
 
     if (warp == 0) {
         // ===================== TMA producer: the packed operand tile of every step =====================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x)
-                for (int step = 0; step < n_steps; ++step) {
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int item, s0, s1;
+                unit(u, item, s0, s1);
+                for (int step = s0; step < s1; ++step) {
                     mbar_wait(&sb->empty[s], ph ^ 1);
                     mbar_expect_tx(&sb->op_full[s], op_bytes);
                     const uint8_t *src = p.op_packed + (size_t)step * (size_t)(2 * KB * CHUNK);
@@ -175,6 +188,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
                         bulk_g2s(dst + (size_t)ch * chunk_op, src + (size_t)ch * CHUNK, chunk_op, &sb->op_full[s]);
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (converged warp, elect.sync) =====================
@@ -182,10 +196,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
         uint32_t s = 0, ph = 0, it = 0;
         long long t_op = 0, t_g = 0;
         const long long t_begin = clock64();
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            int item, s0, s1;
+            unit(u, item, s0, s1);
             mbar_wait(&sb->acc_empty, (it & 1) ^ 1);
             tc_fence_after();
-            for (int step = 0; step < n_steps; ++step) {
+            for (int step = s0; step < s1; ++step) {
                 const long long t0 = clock64();
                 mbar_wait(&sb->op_full[s], ph);
                 const long long t1 = clock64();
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
                         for (int k = 0; k < 8; ++k) {
                             const uint64_t ad = desc_mn_major(a0 + (uint32_t)k * 2048u, chunk_op);
                             const uint64_t bd = desc_k_major(b0 + (uint32_t)(k >> 2) * chunk_g + (uint32_t)(k & 3) * 32u);
-                            tc_mma_ss_elect(tmem_base, ad, bd, idesc, (step | term | k) != 0);
+                            tc_mma_ss_elect(tmem_base, ad, bd, idesc, ((step - s0) | term | k) != 0);
                         }
                     } else {
                         // A = g image, MN-major: M = factors (2 blocks of 64, LBO = one chunk), K = query rows, 16 per MMA
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
                         for (int k = 0; k < nq / 16; ++k) {
                             const uint64_t ad = desc_mn_major(a0 + (uint32_t)k * 2048u, chunk_g);
                             const uint64_t bd = desc_mn_major(b0 + (uint32_t)k * 2048u, chunk_op);
-                            tc_mma_ss_elect(tmem_base, ad, bd, idesc, (step | term | k) != 0);
+                            tc_mma_ss_elect(tmem_base, ad, bd, idesc, ((step - s0) | term | k) != 0);
                         }
                     }
                 }
@@ -263,12 +279,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
         // and q & 7 == cw & 7 for every row of this warp (rows are 16 apart)
         const uint32_t lane_off = (uint32_t)((((lane >> 2) ^ (cw & 7)) << 4) + (lane & 3) * 4 + cw * 128);
         float x[kRows][4], xn[kRows][4];
-        if ((int)blockIdx.x < n_items) load_step(blockIdx.x, 0, x);
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            for (int step = 0; step < n_steps; ++step) {
-                // the next step's tile (possibly the next item's first) is requested before this one is converted
-                if (step + 1 < n_steps) load_step(item, step + 1, xn);
-                else if (item + (int)gridDim.x < n_items) load_step(item + gridDim.x, 0, xn);
+        if ((int)blockIdx.x < n_units) {
+            int item, s0, s1;
+            unit(blockIdx.x, item, s0, s1);
+            load_step(item, s0, x);
+        }
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            int item, s0, s1;
+            unit(u, item, s0, s1);
+            for (int step = s0; step < s1; ++step) {
+                // the next step's tile (possibly the next unit's first) is requested before this one is converted
+                if (step + 1 < s1) load_step(item, step + 1, xn);
+                else if (u + (int)gridDim.x < n_units) {
+                    int item2, t0, t1;
+                    unit(u + gridDim.x, item2, t0, t1);
+                    load_step(item2, t0, xn);
+                }
                 mbar_wait(&sb->empty[s], ph ^ 1);
                 uint8_t *gi = smem + (size_t)s * stage_bytes + op_alloc + lane_off;
 #pragma unroll
@@ -310,7 +336,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
                             const int q = c0 + j;
                             if (q < q_lim && row < p.D) {
                                 const size_t qq = (size_t)b * p.Q + qt * TILE + q;
-                                p.out[qq * p.D + row] = p.txt_mask[qq] ? __uint_as_float(r[j]) : 0.f;
+                                const float val = p.txt_mask[qq] ? __uint_as_float(r[j]) : 0.f;
+                                if (KS > 1) atomicAdd(p.out + qq * p.D + row, val);
+                                else p.out[qq * p.D + row] = val;
                             }
                         }
                     }
@@ -323,7 +351,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) align_bwd_kernel(BwdArgs p) {
                         if (v < p.V) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (c0 + j < p.D) p.out[((size_t)a * p.V + v) * p.D + c0 + j] = keep ? __uint_as_float(r[j]) : 0.f;
+                                if (c0 + j < p.D) {
+                                    const float val = keep ? __uint_as_float(r[j]) : 0.f;
+                                    if (KS > 1) atomicAdd(p.out + ((size_t)a * p.V + v) * p.D + c0 + j, val);
+                                    else p.out[((size_t)a * p.V + v) * p.D + c0 + j] = val;
+                                }
                         }
                     }
                 }
@@ -362,7 +394,24 @@ cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, con
     a.split = split == 1 ? 1 : 3;
     a.prof = dmv_profile_buffer();
     const size_t g_bytes = (size_t)4 * pl.nq * 128;
-    auto run = [&](auto kern, size_t stage, int items) -> cudaError_t {
+    // k-slices per item: the count (<= 16, <= steps) that fills the last wave of persistent CTAs best
+    auto pick_ksplit = [&](int items, int steps) {
+        int best = 1;
+        double best_eff = 0.0;
+        for (int ks = 1; ks <= 16 && ks <= steps; ++ks) {
+            const long long units = (long long)items * ks, waves = (units + sm - 1) / sm;
+            const double eff = (double)units / (double)(waves * sm);
+            if (eff > best_eff + 0.02) { best_eff = eff; best = ks; }
+        }
+        return best;
+    };
+    auto run = [&](auto kern, size_t stage, int items, int steps, float *out, size_t out_elems) -> cudaError_t {
+        a.ksplit = pick_ksplit(items, steps);
+        if (a.ksplit > 1) {
+            cudaError_t err = cudaMemsetAsync(out, 0, out_elems * sizeof(float), st);
+            if (err != cudaSuccess) return err;
+        }
+        items *= a.ksplit;
         const size_t fixed = sizeof(BwdSmem) + 64;
         a.stages = 2 * stage + fixed <= (size_t)smem_max ? 2 : 1;
         const size_t smem = a.stages * stage + fixed;
@@ -374,12 +423,12 @@ cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, con
     };
     if (grad_txt) {
         a.op_packed = vis_packed; a.out = grad_txt;
-        e = run(align_bwd_kernel<0>, (size_t)4 * CHUNK + g_bytes, B * pl.QT);
+        e = run(align_bwd_kernel<0>, (size_t)4 * CHUNK + g_bytes, B * pl.QT, A * pl.VT, grad_txt, (size_t)B * Q * D);
         if (e != cudaSuccess) return e;
     }
     if (grad_vis) {
         a.op_packed = txt_packed; a.out = grad_vis;
-        e = run(align_bwd_kernel<1>, (size_t)2 * pl.KB * pl.nq * 128 + g_bytes, A * pl.VT);
+        e = run(align_bwd_kernel<1>, (size_t)2 * pl.KB * pl.nq * 128 + g_bytes, A * pl.VT, B * pl.QT, grad_vis, (size_t)A * V * D);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
