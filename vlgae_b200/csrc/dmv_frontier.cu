@@ -54,7 +54,8 @@ __device__ __forceinline__ float flog(float x) {
 }
 
 __host__ __device__ inline int ncells(int Nb) { return Nb * (Nb + 1) / 2; }
-__device__ __forceinline__ int dbase(int d, int Nb) { return d * Nb - ((d * (d - 1)) >> 1); }
+// first cell of diagonal d: d Nb - d (d - 1) / 2 = d (2 Nb + 1 - d) / 2  (the product is always even; 2 Nb + 1 is loop-invariant)
+__device__ __forceinline__ int dbase(int d, int Nb) { return (d * (2 * Nb + 1 - d)) >> 1; }
 __device__ __forceinline__ int cidx(int lo, int d, int Nb) { return dbase(d, Nb) + lo; }
 
 // running logsumexp (m, s): value = m + log s
@@ -271,7 +272,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     c.X[cc] = make_float2(xl, xr);
                 }
                 if (w <= 2 * s) {
-                    const int Dd = dbase(w - s, Nb);
+                    const int Dd = De + Nb - (w - 1 - s);   // dbase(w - s)
                     const float l3 = c.CL[Ds + i].y;           // CL[i, i+s].NO
                     const float2 i3 = c.IL[Dd + i + s];        // IL[i+s, j]
                     const float2 i4 = c.IR[Dd + i];            // IR[i, j-s]
@@ -356,7 +357,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     bp[0] = (uint8_t)bx[k][0]; bp[1] = (uint8_t)bx[k][1];
                 }
                 if (w <= 2 * s) {
-                    const int Dd = dbase(w - s, Nb);
+                    const int Dd = De + Nb - (w - 1 - s);   // dbase(w - s)
                     const float l3 = c.CL[Ds + i].y;
                     const float2 i3 = c.IL[Dd + i + s];
                     const float2 i4 = c.IR[Dd + i];
@@ -524,6 +525,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         if (tid == 0) c.gCR[cidx(0, len, Nb)].y = p.gZ ? p.gZ[b] : 1.f;
         blk_sync<NT>();
     }
+    unsigned rw_next = __float2uint_rz(__fdividef(1048576.0f, (float)(Nb - len))) + 2u;
 #pragma unroll 1
     for (int w = len; w >= 1; --w) {
         const int ntask = (Nb - w) * w;
@@ -533,7 +535,9 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         const int np = Nb - w;
         // t / np == (t * rw) >> 20 needs rw * np >= 2^20 and t * (rw * np - 2^20) < 2^20; the float quotient is within 1
         // of floor(2^20 / np), so +2 keeps the first and 3 np * t <= 3 * 75 * 1406 the second (no integer division)
-        const unsigned rw = __float2uint_rz(__fdividef(1048576.0f, (float)np)) + 2u;
+        // (computed one width ahead: the conversion + reciprocal chain stays off the head of the phase)
+        const unsigned rw = rw_next;
+        rw_next = __float2uint_rz(__fdividef(1048576.0f, (float)(np + 1))) + 2u;
         const int pb = dbase(w, Nb);
         // phase A'(w): complete parents of width w (steps 3, 4 transposed)
 #pragma unroll 1
@@ -541,7 +545,8 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             const int a = (int)(((unsigned)t * rw) >> 20), i = t - a * np;
             const float2 gl = c.gCL[pb + i], gr = c.gCR[pb + i], outl = c.CL[pb + i], outr = c.CR[pb + i];
             const int cl3 = cidx(i, a, Nb), cr3 = cidx(i + a, w - a, Nb);
-            const int cl4 = cidx(i, a + 1, Nb), cr4 = cidx(i + a + 1, w - 1 - a, Nb);
+            // dbase(d + 1) - dbase(d) = Nb - d:  cl4 = cidx(i, a + 1), cr4 = cidx(i + a + 1, w - 1 - a)
+            const int cl4 = cl3 + Nb - a, cr4 = cr3 - Nb + w - a;
             const float lv3 = c.CL[cl3].y;
             const float2 rv3 = c.IL[cr3];
             const float2 lv4 = c.IR[cl4];
