@@ -225,7 +225,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 const int w = ow[k], i = oi[k];
-                if (w >= s && w <= 2 * s - 1) {
+                if ((unsigned)(w - s) < (unsigned)s) {  // s <= w <= 2 s - 1
                     const int Dd = dbase(w - s, Nb), j = i + w;
                     const float l3 = c.CL[Dd + i].y;          // CL[i, j-s].NO
                     const float2 i3 = c.IL[Ds + j - s];        // IL[j-s, j]
@@ -251,7 +251,7 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
             const int w = ow[k], i = oi[k];
-            if (w >= s + 1 && w <= 2 * s + 1) {
+            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
                 const int De = dbase(w - 1 - s, Nb), j = i + w;
                 // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
                 const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
@@ -311,7 +311,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
 #pragma unroll
             for (int k = 0; k < CPT; ++k) {
                 const int w = ow[k], i = oi[k];
-                if (w >= s && w <= 2 * s - 1) {
+                if ((unsigned)(w - s) < (unsigned)s) {  // s <= w <= 2 s - 1
                     const int Dd = dbase(w - s, Nb), j = i + w;
                     const float l3 = c.CL[Dd + i].y;
                     const float2 i3 = c.IL[Ds + j - s];
@@ -338,7 +338,7 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
             const int w = ow[k], i = oi[k];
-            if (w >= s + 1 && w <= 2 * s + 1) {
+            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
                 const int De = dbase(w - 1 - s, Nb), j = i + w;
                 const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
                 amax1(vx[k][0], bx[k][0], __fadd_rn(la.y, ra.x), s);
