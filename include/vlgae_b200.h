@@ -57,6 +57,14 @@ const char *vlgae_last_error(void);
 int vlgae_dmv_set_tuning(int gmax, int threads, int tpl);
 
 /*
+ * Schedule of the DMV kernels (process-wide): 0 = automatic (latency regime -> frontier schedule, one thread per
+ * target cell; throughput regime -> gather schedule, lanes stream split points), 1 = frontier, 2 = gather,
+ * 3 = role-split.  A schedule that cannot run a launch (chart beyond shared memory, host-memory hand-off) falls back
+ * to the automatic choice.  Results agree within the documented tolerances (max semiring: bit-exact).
+ */
+int vlgae_dmv_set_schedule(int which);
+
+/*
  * Debug aid: a device buffer of 8 int64; the CTAs of sentence 0 write cumulative SM cycle counts after each phase
  * ([0..3] log pass: staged, inside done, outside done, outputs written; [4..6] max pass: staged, chart done,
  * back-trace done).  NULL disables it (default).

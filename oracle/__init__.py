@@ -56,6 +56,31 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+_REF_DIR = os.path.join(_HERE, "_ref", "torch_struct")
+_ref_mod = None
+
+
+def load_reference():
+    """The UNMODIFIED reference package (src/model/torch_struct), imported in isolation from ``oracle/_ref`` (staged by
+    ``oracle/make_ref.py``) with ``src.setup_inf(1e20)`` emulated (/root/reference/src/__init__.py:113-120).
+    Returns the module, or None when the package has not been staged."""
+    global _ref_mod
+    if _ref_mod is None:
+        init = os.path.join(_REF_DIR, "__init__.py")
+        if not os.path.exists(init):
+            return None
+        import importlib.util
+        import sys
+
+        spec = importlib.util.spec_from_file_location("ref_torch_struct", init, submodule_search_locations=[_REF_DIR])
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["ref_torch_struct"] = m
+        spec.loader.exec_module(m)
+        m.semirings.semirings.NEGINF = -1e20
+        _ref_mod = m
+    return _ref_mod
+
+
 def _p(a, ct):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ct))
 

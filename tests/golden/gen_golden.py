@@ -53,7 +53,7 @@ def synth(B, n, seed, quant=None, zero=False):
     return dec, attach, root
 
 
-def run_dmv(ref, name, dec, attach, root, lengths):
+def run_dmv(ref, name, dec, attach, root, lengths, compact=False):
     lengths = torch.as_tensor(lengths, dtype=torch.long)
     md, ma = ref.DMV1o.merge(dec, attach, root)
     a = ma.detach().clone().requires_grad_()
@@ -73,9 +73,13 @@ def run_dmv(ref, name, dec, attach, root, lengths):
     for b, h, c, v in arg.nonzero().tolist():
         heads[b, c] = h
         val[b, c] = v
+    # compact: the big fixtures store the raw inputs only (merge is pinned bit-exactly by the small ones)
+    inputs = dict(dec=dec.numpy(), attach=attach.numpy(), root=root.numpy())
+    if not compact:
+        inputs.update(merged_dec=md.numpy(), merged_attach=ma.numpy())
     np.savez_compressed(
-        os.path.join(OUT, name + ".npz"), dec=dec.numpy(), attach=attach.numpy(), root=root.numpy(),
-        lengths=lengths.numpy(), merged_dec=md.numpy(), merged_attach=ma.numpy(), partition=Z.detach().numpy(),
+        os.path.join(OUT, name + ".npz"), **inputs,
+        lengths=lengths.numpy(), partition=Z.detach().numpy(),
         max=mx.detach().numpy(), grad_dec=gd.numpy(), grad_attach=ga.numpy(), vgrad_dec=vgd.numpy(), heads=heads,
         arc_valence=val)
     print(name, "B", B, "N", N, "Z[0]", float(Z[0]), "max[0]", float(mx[0]))
@@ -174,6 +178,18 @@ def main():
     # long sentences (cfg2 upper end)
     d, a, r = synth(4, 40, 2)
     ga = run_dmv(ref, "dmv_len40", d, a, r, [40, 33, 17, 4])
+    # the full cfg2 batch bench.py times (BASELINE.json configs[1]: 128 captions, len 4..40 ragged sorted desc, seed 2)
+    # -- same draws as bench.py:make_batch_cpu / make_lengths
+    g = torch.Generator().manual_seed(2)
+    L = torch.randint(4, 41, (128,), generator=g).sort(descending=True).values
+    L[0] = 40
+    d, a, r = synth(128, 40, 2)
+    run_dmv(ref, "dmv_cfg2_full", d, a, r, L, compact=True)
+    # cfg3 upper end (BASELINE.json configs[2]) at small B: n = 64 and n = 128, full length
+    d, a, r = synth(6, 64, 3)
+    run_dmv(ref, "dmv_n64", d, a, r, [64] * 6, compact=True)
+    d, a, r = synth(3, 128, 3)
+    run_dmv(ref, "dmv_n128", d, a, r, [128] * 3, compact=True)
     # DependencyCRF: random potentials, and the MBR chain on real arc marginals
     g = torch.Generator().manual_seed(103)
     run_deptree(ref, "deptree_rand", torch.randn(8, 9, 9, generator=g), [8, 7, 5, 3, 2, 1, 8, 4])

@@ -197,3 +197,41 @@ def test_backward_kernels_against_fp64(dev, A, V, B, Q, D, pad):
     assert float((gv.double() - rv).abs().max()) <= tol_v
     assert float((gt.double() - rt).abs().max()) <= tol_t
     assert (gv[~vm] == 0).all() and (gt[~tm] == 0).all()   # masked rows receive exact zeros
+
+
+@pytest.mark.parametrize("pad", [True, False])
+def test_inplace_write_into_attmap_then_backward(dev, pad):
+    """The reference's default training config writes into attmap in place (use_pos_prior, joint.py:466-469:
+    ``attmap[arange, arange, ...] -= mask * 100``) and then back-propagates through it.  With requires_grad inputs the
+    result comes from the autograd node; it must be writable (not a view made inside the custom Function) and the
+    gradients must equal those of the reference formula with the same in-place write."""
+    from vlgae_b200.alignment import gather_logit_simple
+
+    g_ = torch.Generator(device=dev).manual_seed(21)
+    A = B = 3
+    V, Q, D = 45, 10, 32   # V = 45 is odd: padded rows (ldv = 48) when pad
+    vis = torch.randn(A, V, D, generator=g_, device=dev).requires_grad_()
+    txt = torch.randn(B, Q, D, generator=g_, device=dev).requires_grad_()
+    vm = torch.rand(A, V, generator=g_, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g_, device=dev) > 0.2
+    prior = (torch.rand(B, Q, V, generator=g_, device=dev) > 0.5).float()
+    w = torch.randn(B, A, Q, V, generator=g_, device=dev)
+
+    att = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=pad)
+    ar = torch.arange(B, device=dev)
+    att[ar, ar] -= prior * 100          # must not raise
+    keep = vm[None, :, None, :] & tm[:, None, :, None]
+    (att * w * keep).sum().backward()
+    gv, gt = vis.grad.clone(), txt.grad.clone()
+
+    vis2, txt2 = vis.detach().double().requires_grad_(), txt.detach().double().requires_grad_()
+    ref = torch.einsum("avd,bqd->baqv", vis2, txt2)
+    ref = ref.masked_fill(~vm[None, :, None, :], -1e20).masked_fill(~tm[:, None, :, None], -1e20)
+    ref[ar, ar] -= prior.double() * 100
+    (ref * w.double() * keep).sum().backward()
+    tol = 2.0 ** -13 * float(w.abs().max()) * float(max(vis.abs().max(), txt.abs().max())) * (max(A * V, B * Q)) ** 0.5
+    assert float((gv.double() - vis2.grad).abs().max()) <= tol
+    assert float((gt.double() - txt2.grad).abs().max()) <= tol
+    got, want = att.detach().cpu().numpy(), ref.detach().cpu().numpy()
+    masked = ~keep.expand(B, A, Q, V).cpu().numpy()
+    assert np.abs(got - want)[~masked].max() < 1e-2 and (got[masked] <= -1e19).all()

@@ -14,23 +14,34 @@ pytestmark = pytest.mark.gpu
 Z_RTOL, MARG_ATOL, DEC_ATOL = 1e-4, 1e-5, 4e-5
 
 
-def marg_tol(Z):
-    """Per-sentence absolute tolerance for marginals: BASELINE's 1e-5, widened to two fp32 ulps of |log Z| (relative).
-
-    Chart values of a length-40 sentence are ~ -170, where one fp32 ulp is 1.5e-5: two fp32 implementations that
-    differ in the last bit of ONE cell on the main derivation (they must, unless they replay the reference's exact
-    instruction sequence) differ by that factor in every marginal.  tools/dmv_error_study.py shows exactly this:
-    |gpu - ref| <= 2e-6 except for sentences whose log Z differs by one ulp, and there |gpu - fp64| < |ref - fp64|.
-    """
-    return np.maximum(MARG_ATOL, 2.0 ** -22 * np.abs(np.asarray(Z, dtype=np.float64)))
+def assert_exact(actual, f64, atol=MARG_ATOL):
+    """Plain absolute tolerance against the fp64 evaluation of the same recurrences (oracle, REAL = double).
+    The CUDA log-semiring sweep runs on offset arc scores (chart values O(10) instead of O(-4 len), see
+    csrc/dmv_frontier.cu), so it is expected within ~3e-6 of the exact result at every length tested."""
+    err = np.abs(actual.astype(np.float64) - f64)
+    assert err.max(initial=0.0) <= atol, f"max |gpu - fp64| {err.max():.3e} > {atol:g}"
 
 
-def assert_marginals(actual, desired, Z, scale=1.0):
-    tol = marg_tol(Z).reshape((-1,) + (1,) * (actual.ndim - 1)) * scale
-    err = np.abs(actual.astype(np.float64) - desired)
-    assert (err <= tol).all(), f"max |err| {err.max():.3e}, worst err/tol {(err / tol).max():.2f}"
+def assert_three_way(actual, ref, f64, atol=MARG_ATOL):
+    """Against the reference's own output (golden vectors): BASELINE.json's 1e-5 absolute, no ulp term.  At len >~ 35
+    the reference's fp32 sweep is itself > 1e-5 from the exact result (|ref - fp64| = 1.0e-5 on the cfg2 batch,
+    1.4e-5 at n = 64, 2.0e-5 at n = 128; the C restatement with libm is 1.4e-5 from the reference on cfg2), so a sentence
+    that misses 1e-5 against the reference passes only if the CUDA result is at least as close to the exact (fp64)
+    result as the reference is.  Both errors are part of the failure message."""
+    B = actual.shape[0]
+    a = actual.astype(np.float64).reshape(B, -1)
+    e_gr = np.abs(a - ref.reshape(B, -1)).max(1)
+    e_g64 = np.abs(a - f64.reshape(B, -1)).max(1)
+    e_r64 = np.abs(ref.astype(np.float64).reshape(B, -1) - f64.reshape(B, -1)).max(1)
+    ok = (e_gr <= atol) | (e_g64 <= e_r64)
+    assert ok.all(), (f"|gpu - ref| {e_gr.max():.3e}, |gpu - fp64| {e_g64.max():.3e}, |ref - fp64| {e_r64.max():.3e}; "
+                      f"{(~ok).sum()} of {B} sentences fail both rules")
+    return e_gr.max(), e_g64.max(), e_r64.max()
+
+
 DMV_CASES = ["dmv_tiny_ragged", "dmv_cfg1", "dmv_cfg1_ragged", "dmv_ties_q025", "dmv_ties_q1", "dmv_ties_zero",
-             "dmv_len40"]
+             "dmv_len40", "dmv_cfg2_full", "dmv_n64", "dmv_n128"]
+SCHEDULES = {"auto": 0, "frontier": 1, "gather": 2}
 
 
 @pytest.fixture(scope="module")
@@ -64,11 +75,11 @@ def check_all(md, ma, L, dev, marg_atol=MARG_ATOL):
 
     out = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev), want_arcs=True, want_vgdec=True)
     torch.cuda.synchronize()
-    Z, gdec, gatt = oracle.dmv_log(md, ma, L, trim=True)
+    Z, gdec, gatt = oracle.dmv_log(md, ma, L, trim=True, f64=True)
     best, heads, arcs, vgdec = oracle.dmv_viterbi(md, ma, L, trim=True)
     np.testing.assert_allclose(out.Z.cpu().numpy(), Z, rtol=Z_RTOL)
-    assert_marginals(out.gattach.cpu().numpy(), gatt, Z, marg_atol / MARG_ATOL)
-    assert_marginals(out.gdec.cpu().numpy(), gdec, Z, 4 * marg_atol / MARG_ATOL)
+    assert_exact(out.gattach.cpu().numpy(), gatt, marg_atol)
+    assert_exact(out.gdec.cpu().numpy(), gdec, marg_atol)
     np.testing.assert_array_equal(out.best.cpu().numpy(), best)
     np.testing.assert_array_equal(out.heads.cpu().numpy(), heads)
     np.testing.assert_array_equal(out.arcs.cpu().numpy(), arcs)
@@ -76,17 +87,37 @@ def check_all(md, ma, L, dev, marg_atol=MARG_ATOL):
     return out
 
 
+@pytest.fixture(params=["auto", "frontier", "gather"])
+def schedule(request, dev):
+    """Run a test under each DMV schedule (vlgae_dmv_set_schedule): the automatic choice, the frontier schedule
+    (latency regime) and the gather schedule (throughput regime) must all meet the same parity bar."""
+    from vlgae_b200._lib import check, lib
+
+    check(lib().vlgae_dmv_set_schedule(SCHEDULES[request.param]), "set_schedule")
+    yield request.param
+    check(lib().vlgae_dmv_set_schedule(0), "set_schedule")
+
+
 @pytest.mark.parametrize("name", DMV_CASES)
-def test_golden_reference_vectors(golden, dev, name):
+def test_golden_reference_vectors(golden, dev, schedule, name):
+    """Every fixture recorded from the UNMODIFIED reference (tests/golden/gen_golden.py), incl. the full cfg2 batch bench.py
+    times (B = 128) and the cfg3 upper end (n = 64, 128), under each schedule."""
     from vlgae_b200 import ops
 
     g = golden(name)
-    md, ma, L = _t(g["merged_dec"], dev), _t(g["merged_attach"], dev), _t(g["lengths"], dev)
+    if "merged_dec" in g:
+        hmd, hma = g["merged_dec"], g["merged_attach"]
+    else:  # compact fixtures store the raw inputs; merge is pinned bit-exactly by the small ones
+        hmd, hma = oracle.merge(g["dec"], g["attach"], g["root"])
+    md, ma, L = _t(hmd, dev), _t(hma, dev), _t(g["lengths"], dev)
     Z, gdec, gatt = ops.dmv_inside_outside(md, ma, L)
     best, heads, arcs, vgdec = ops.dmv_viterbi(md, ma, L, want_gdec=True)
+    _, gdec64, gatt64 = oracle.dmv_log(hmd, hma, g["lengths"], trim=True, f64=True)
     np.testing.assert_allclose(Z.cpu().numpy(), g["partition"][:, 0], rtol=Z_RTOL)
-    assert_marginals(gatt.cpu().numpy(), g["grad_attach"], g["partition"][:, 0])
-    assert_marginals(gdec.cpu().numpy(), g["grad_dec"], g["partition"][:, 0], 4)
+    assert_three_way(gatt.cpu().numpy(), g["grad_attach"], gatt64)
+    assert_three_way(gdec.cpu().numpy(), g["grad_dec"], gdec64)
+    if hmd.shape[1] <= 41:  # len <= 40: the north star's plain tolerance against the reference itself
+        np.testing.assert_allclose(gatt.cpu().numpy(), g["grad_attach"], rtol=0, atol=MARG_ATOL)
     np.testing.assert_array_equal(best.cpu().numpy(), g["max"][:, 0])
     np.testing.assert_array_equal(heads.cpu().numpy(), g["heads"])
     np.testing.assert_array_equal(vgdec.cpu().numpy(), g["vgrad_dec"])
@@ -164,11 +195,11 @@ def test_gradient_flows_through_merge(golden, dev):
 
 
 @pytest.mark.parametrize("B,n,seed", [(64, 16, 1), (37, 5, 3), (16, 33, 4), (5, 1, 5), (9, 2, 6)])
-def test_full_length_batches(dev, B, n, seed):
+def test_full_length_batches(dev, schedule, B, n, seed):
     check_all(*synth(B, n, seed), dev)
 
 
-def test_cfg2_shape_ragged_sorted(dev):
+def test_cfg2_shape_ragged_sorted(dev, schedule):
     g = torch.Generator().manual_seed(2)
     L = torch.randint(4, 41, (128,), generator=g).sort(descending=True).values
     L[0] = 40
@@ -181,8 +212,9 @@ def test_cfg2_shape_ragged_sorted(dev):
     np.testing.assert_allclose(out.gdec.cpu().numpy().sum((1, 2, 3, 4)), 3 * L + 1, rtol=1e-4)
 
 
-def test_noise_floor_vs_f64(dev):
-    """The CUDA path is no farther from an fp64 evaluation than the fp32 oracle (= the reference's arithmetic)."""
+def test_noise_floor_vs_f64(dev, schedule):
+    """The CUDA log-semiring sweep (offset arc scores) is closer to the exact result than an fp32 sweep in the
+    reference's arithmetic (the fp32 oracle), by a wide margin at len 40."""
     from vlgae_b200 import ops
 
     md, ma, L = synth(32, 40, 21)
@@ -191,11 +223,11 @@ def test_noise_floor_vs_f64(dev):
     _, _, gpu = ops.dmv_inside_outside(_t(md, dev), _t(ma, dev), _t(L, dev))
     e_gpu = np.abs(gpu.cpu().numpy() - g64).max()
     e_ref = np.abs(g32 - g64).max()
-    assert e_gpu < max(1.5 * e_ref, 1e-5), (e_gpu, e_ref)
+    assert e_gpu < 0.5 * e_ref and e_gpu < 3e-6, (e_gpu, e_ref)
 
 
 @pytest.mark.parametrize("quant", [1.0, 0.5, 0.25])
-def test_tie_stress(dev, quant):
+def test_tie_stress(dev, schedule, quant):
     g = torch.Generator().manual_seed(int(quant * 100))
     L = torch.randint(1, 25, (96,), generator=g)
     L[0] = 24
@@ -214,13 +246,13 @@ def test_all_zero_scores_chain(dev):
     assert arcs[..., 0].sum().item() == 0  # every arc is NOCHILD
 
 
-def test_empty_and_single_word(dev):
+def test_empty_and_single_word(dev, schedule):
     md, ma, _ = synth(4, 6, 9)
     check_all(md, ma, np.array([0, 1, 0, 6]), dev)
 
 
 @pytest.mark.parametrize("B,n", [(12, 64), (6, 100), (4, 128)])
-def test_long_sentences(dev, B, n):
+def test_long_sentences(dev, schedule, B, n):
     """n = 64 stays in shared memory; n >= 100 uses the global-workspace charts (frontier kernel, chart in L2)."""
     g = torch.Generator().manual_seed(n)
     L = torch.randint(n // 2, n + 1, (B,), generator=g)
@@ -230,7 +262,7 @@ def test_long_sentences(dev, B, n):
 
 @pytest.mark.parametrize("B,n,seed", [(3, 44, 1), (5, 45, 2), (4, 46, 3), (300, 46, 4), (3, 49, 5), (2, 71, 6), (2, 72, 7),
                                       (2, 73, 8), (40, 24, 9), (600, 25, 10), (700, 12, 11), (1200, 13, 12), (260, 33, 13)])
-def test_launch_variant_boundaries(dev, B, n, seed):
+def test_launch_variant_boundaries(dev, schedule, B, n, seed):
     """Sizes that sit on the boundaries of the frontier kernel's launch variants: cells per thread in registers (<= 1024
     cells: n <= 44), running state in shared memory, 64/128/256/512-thread CTAs, resident vs strided work items, and the
     chart moving from shared memory to the global workspace (n >= 72).  Ragged lengths, everything against the oracle."""
@@ -240,9 +272,38 @@ def test_launch_variant_boundaries(dev, B, n, seed):
     check_all(*synth(B, n, 60 + seed, L), dev)
 
 
-def test_cfg3_sweep_small(dev):
-    for n in (8, 16, 32):
-        check_all(*synth(512, n, 3), dev)
+@pytest.mark.parametrize("n", [8, 16, 32, 64])
+def test_cfg3_sweep_full_batch(dev, schedule, n):
+    """BASELINE.json configs[2] at its full batch (B = 512); n = 128 at B = 512 is covered through invariants in
+    test_cfg3_n128_full_batch_properties (the oracle needs minutes there)."""
+    check_all(*synth(512, n, 3), dev)
+
+
+def test_cfg3_n128_full_batch_properties(dev):
+    """n = 128 at B = 512: size-independent properties (every word has one head; marginals of each word sum to 1; decision
+    counts sum to 3 len + 1; heads form a projective single-root tree) + the first 4 sentences against the oracle."""
+    from vlgae_b200 import ops
+
+    md, ma, L = synth(512, 128, 3)
+    out = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev), want_arcs=True)
+    torch.cuda.synchronize()
+    m = out.gattach.sum(-1)
+    assert float((m[:, :, 1:].sum(1) - 1).abs().max()) < 2e-4 and float(m[:, :, 0].abs().max()) == 0
+    assert float((out.gdec.sum((1, 2, 3, 4)) - (3 * 128 + 1)).abs().max()) < 0.05
+    heads = out.heads.cpu().numpy()
+    assert (heads[:, 0] == 0).all() and ((heads[:, 1:] == 0).sum(1) == 1).all()   # exactly one child of ROOT
+    assert float(out.arcs.sum()) == 512 * 128
+    for b in range(0, 512, 97):   # projectivity: no two arcs cross
+        arcs = [(min(h, c), max(h, c)) for c, h in enumerate(heads[b]) if c >= 1]
+        for (a0, a1) in arcs:
+            for (b0, b1) in arcs:
+                assert not (a0 < b0 < a1 < b1)
+    Z, gdec, gatt = oracle.dmv_log(md[:4], ma[:4], L[:4], trim=True, f64=True)
+    best, oheads, _, _ = oracle.dmv_viterbi(md[:4], ma[:4], L[:4], trim=True)
+    np.testing.assert_allclose(out.Z[:4].cpu().numpy(), Z, rtol=Z_RTOL)
+    assert_exact(out.gattach[:4].cpu().numpy(), gatt)
+    np.testing.assert_array_equal(out.best[:4].cpu().numpy(), best)
+    np.testing.assert_array_equal(heads[:4], oheads)
 
 
 @pytest.mark.parametrize("gmax,threads,tpl", [(1, 96, 8), (1, 192, 1), (2, 192, 4), (8, 192, 2), (32, 192, 1),
@@ -284,10 +345,10 @@ def test_host_buffer_entry_point(dev):
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     check(lib().vlgae_dmv_parse_host(p(md), p(ma), p(L), B, N, -1e12, p(Z), p(gdec), p(gatt), p(best), p(heads),
                                      None), "parse_host")
-    oZ, ogdec, ogatt = oracle.dmv_log(md, ma, L)
+    oZ, ogdec, ogatt = oracle.dmv_log(md, ma, L, f64=True)
     obest, oheads, _, _ = oracle.dmv_viterbi(md, ma, L)
     np.testing.assert_allclose(Z, oZ, rtol=Z_RTOL)
-    np.testing.assert_allclose(gatt, ogatt, atol=MARG_ATOL)
+    assert_exact(gatt, ogatt)
     np.testing.assert_array_equal(best, obest)
     np.testing.assert_array_equal(heads, oheads)
 
@@ -309,7 +370,11 @@ def test_host_entry_point_pinned_zero_copy(dev, B, n, ragged):
     h = {k: torch.from_numpy(v).pin_memory() for k, v in (("md", md), ("ma", ma), ("L", L))}
     out = {"Z": torch.zeros(B).pin_memory(), "best": torch.zeros(B).pin_memory(), "gdec": torch.zeros(md.shape).pin_memory(),
            "gatt": torch.zeros(ma.shape).pin_memory(), "heads": torch.zeros(B, N, dtype=torch.int64).pin_memory()}
-    ref = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev))
+    check(lib().vlgae_dmv_set_schedule(1), "set_schedule")  # the zero-copy path runs the frontier schedule
+    try:
+        ref = ops.dmv_parse(_t(md, dev), _t(ma, dev), _t(L, dev))
+    finally:
+        check(lib().vlgae_dmv_set_schedule(0), "set_schedule")
     torch.cuda.synchronize()
     for _ in range(3):
         for v in out.values():
@@ -322,10 +387,10 @@ def test_host_entry_point_pinned_zero_copy(dev, B, n, ragged):
         np.testing.assert_array_equal(out["heads"].numpy(), ref.heads.cpu().numpy())
         np.testing.assert_array_equal(out["gatt"].numpy(), ref.gattach.cpu().numpy())
         np.testing.assert_array_equal(out["gdec"].numpy(), ref.gdec.cpu().numpy())
-    oZ, _, ogatt = oracle.dmv_log(md, ma, L)
+    oZ, _, ogatt = oracle.dmv_log(md, ma, L, f64=True)
     _, oheads, _, _ = oracle.dmv_viterbi(md, ma, L)
     np.testing.assert_allclose(out["Z"].numpy(), oZ, rtol=Z_RTOL)
-    assert_marginals(out["gatt"].numpy(), ogatt, oZ)
+    assert_exact(out["gatt"].numpy(), ogatt)
     np.testing.assert_array_equal(out["heads"].numpy(), oheads)
 
 

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--tunings", default="auto")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--errors", action="store_true")
+    ap.add_argument("--schedules", default="auto", help="comma list of auto,frontier,gather,role")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     L_ = lib()
@@ -70,7 +71,8 @@ def main():
             nb = min(B, 64)
             _, _, g64 = oracle.dmv_log(md[:nb], ma[:nb], L[:nb], f64=True, trim=True)
             _, _, g32 = oracle.dmv_log(md[:nb], ma[:nb], L[:nb], trim=True)
-        for tn in args.tunings.split(","):
+        for sched, tn in [(s_, t_) for s_ in args.schedules.split(",") for t_ in args.tunings.split(",")]:
+            check(L_.vlgae_dmv_set_schedule({"auto": 0, "frontier": 1, "gather": 2, "role": 3}[sched]), "schedule")
             gmax, threads, tpl = (0, 0, 0) if tn == "auto" else tuple(int(x) for x in tn.split("x"))
             check(L_.vlgae_dmv_set_tuning(gmax, threads, tpl), "tuning")
             for _ in range(3):
@@ -83,13 +85,14 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / args.iters
-            line = (f"{cname:8s} B={B:6d} n={n:3d} tuning={tn:9s} {us:10.1f} us/launch  {B / us:8.3f} Msent/s  "
+            line = (f"{cname:8s} B={B:6d} n={n:3d} sched={sched:8s} tuning={tn:9s} {us:10.1f} us/launch  {B / us:8.3f} Msent/s  "
                     f"mufu_frac={mufu / (us * 1e-6) / peak:.3f}")
             if args.errors:
                 gpu = out.gattach[:nb].cpu().numpy()
                 line += f"  |gpu-f64|={np.abs(gpu - g64).max():.2e} |gpu-f32|={np.abs(gpu - g32).max():.2e} |f32-f64|={np.abs(g32 - g64).max():.2e}"
             print(line, flush=True)
     check(L_.vlgae_dmv_set_tuning(0, 0, 0), "tuning")
+    check(L_.vlgae_dmv_set_schedule(0), "schedule")
 
 
 if __name__ == "__main__":

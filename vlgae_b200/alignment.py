@@ -37,7 +37,8 @@ def _workspace(dev, nbytes):
 
 
 def _launch(vf, vm, tf, tm, split, neg, pad_rows):
-    """One kernel call on prepared tensors (fp32 contiguous features, uint8 masks) -> [B, A, Q, V] (padded-row view)."""
+    """One kernel call on prepared tensors (fp32 contiguous features, uint8 masks) -> the [B, A, Q, ldv] buffer with
+    ldv = V rounded up to 8 floats when pad_rows (elements >= V of a row are not written); the caller slices ``[..., :V]``."""
     dev = vf.device
     A, V, D = vf.shape
     B, Q, _ = tf.shape
@@ -51,7 +52,7 @@ def _launch(vf, vm, tf, tm, split, neg, pad_rows):
         check(lib().vlgae_align_logits(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D,
                                        float(neg), int(split), out.data_ptr(), ldv, ws.data_ptr(), ws.numel(),
                                        torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits")
-    return out[..., :V] if ldv != V else out
+    return out
 
 
 class _AlignLogits(torch.autograd.Function):
@@ -69,13 +70,15 @@ class _AlignLogits(torch.autograd.Function):
         ctx.save_for_backward(vf, tf, vm, tm)
         ctx.in_dtypes = (vis_feat.dtype, txt_feat.dtype)
         ctx.split = int(split)
+        # the padded buffer itself is the output: a ``[..., :V]`` view taken in here would be marked as a view created
+        # inside a custom Function, and the reference's in-place write into attmap (joint.py:466-469, 548-551) would raise
         return _launch(vf, vm, tf, tm, split, neg, pad_rows)
 
     @staticmethod
     def backward(ctx, g):
         vf, tf, vm, tm = ctx.saved_tensors
-        B, A, Q, V = g.shape
-        D = vf.shape[2]
+        B, A, Q = g.shape[:3]
+        V, D = vf.shape[1], vf.shape[2]
         dev = g.device
         g = g.to(torch.float32)
         if g.stride(-1) != 1 or g.stride(2) < V or g.stride(1) != Q * g.stride(2) or g.stride(0) != A * Q * g.stride(2):
@@ -121,6 +124,8 @@ def gather_logit_simple(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=
     else:
         out = _launch(vis_feat.detach().to(torch.float32).contiguous(), vm,
                       txt_feat.detach().to(torch.float32).contiguous(), tm, split, neg, pad_rows)
+    if out.shape[-1] != V:
+        out = out[..., :V]  # an ordinary view of the Function's output: in-place writes are allowed
     if named:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

@@ -63,6 +63,11 @@ int vlgae_dmv_set_tuning(int gmax, int threads, int tpl) {
     vlgae::dmv_set_tuning(gmax, threads, tpl);
     return VLGAE_OK;
 }
+int vlgae_dmv_set_schedule(int which) {
+    if (which < 0 || which > 3) return fail(VLGAE_E_INVALID, "%s", "schedule must be 0 (auto), 1 (frontier), 2 (gather) or 3 (role)");
+    vlgae::dmv_set_schedule(which);
+    return VLGAE_OK;
+}
 const char *vlgae_last_error(void) { return g_err; }
 
 size_t vlgae_dmv_workspace_bytes(int B, int N) {

@@ -954,14 +954,36 @@ static cudaError_t launch_nt(DmvArgs a, int passes, int cap, cudaStream_t st) {
 
 static int env_int(const char *name, int dflt);
 static int g_tune_gmax = 0, g_tune_threads = 0, g_tune_tpl = 0;
+static int g_schedule = 0;  // 0 = automatic, 1 = frontier, 2 = gather, 3 = role-split
+void dmv_set_schedule(int which) { g_schedule = which; }
 
 static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, int threads, bool lat, cudaStream_t st) {
     // Default schedule: the frontier kernel (dmv_frontier.cu) whenever the chart fits in shared memory.  An explicit
     // role-kernel tuning (vlgae_dmv_set_tuning / VLGAE_DMV_THREADS / VLGAE_DMV_GMAX) or VLGAE_DMV_KERNEL=role selects
     // the role-split kernel below, which also covers the long sentences whose chart lives in global memory.
-    static const int env_role = [] { const char *v = getenv("VLGAE_DMV_KERNEL"); return v && v[0] == 'r' ? 1 : 0; }();
+    static const int env_sched = [] {
+        const char *v = getenv("VLGAE_DMV_KERNEL");
+        return !v ? 0 : (v[0] == 'f' ? 1 : (v[0] == 'g' ? 2 : (v[0] == 'r' ? 3 : 0)));
+    }();
+    const int sched = g_schedule ? g_schedule : env_sched;
+    const bool env_role = sched == 3;
     static const int env_ft = env_int("VLGAE_FRONTIER_THREADS", 0);
+    static const int env_gt = env_int("VLGAE_GATHER_THREADS", 0);
     const bool fits = dmv_frontier_fits(cap, passes, g_smem_optin);
+    // Throughput regime (more work items than can be resident at once): the gather schedule (dmv_gather.cu).  The
+    // frontier schedule keeps the latency regime, the zero-copy hand-off and the charts beyond shared memory.
+    {
+        const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count;
+        const bool can = !a.share && g_tune_gmax == 0 && g_tune_threads == 0 && a.threads == 0 &&
+                         dmv_gather_fits(cap, passes, g_smem_optin);
+        if (can && (sched == 2 || (sched == 0 && !resident))) {
+            int gt = cap <= 20 ? 32 : (cap <= 48 ? 64 : (cap <= 60 ? 128 : 256));
+            if (env_gt > 0) gt = env_gt;
+            DmvArgs f = a;
+            f.workspace = nullptr; f.ws_stride = 0;
+            return launch_dmv_gather(f, passes, cap, gt, g_sm_count, st);
+        }
+    }
     // (a chart that fits the role kernel's shared-memory layout but not the frontier's comes without a workspace)
     if (!env_role && g_tune_gmax == 0 && g_tune_threads == 0 && a.threads == 0 && cap <= 256 && (fits || a.workspace)) {
         DmvArgs f = a;

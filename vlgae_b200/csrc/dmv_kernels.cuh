@@ -57,6 +57,10 @@ bool dmv_frontier_fits(int cap, int passes, int smem_optin);
 size_t dmv_frontier_chart_bytes(int N, int passes);  // per-CTA workspace slice when the chart is in global memory
 cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, int max_grid,
                                 cudaStream_t st);
+// gather schedule (dmv_gather.cu): throughput regime, chart in shared memory, row-major squares
+bool dmv_gather_fits(int cap, int passes, int smem_optin);
+cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st);
+void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather, 3 = role-split
 size_t dmv_ws_slice_bytes(int N, int passes);  // what vlgae_dmv_workspace_bytes reserves per CTA (either schedule)
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);
