@@ -49,18 +49,11 @@ int vlgae_version(void);
 const char *vlgae_last_error(void);
 
 /*
- * Launch tuning of the DMV kernels (process-wide; 0 = automatic): gmax = most lanes that share one span
- * (1, 2, 4, 8, 16, 32), threads = CTA size (96, 192, 384 = 3 roles x lanes), tpl = split points one lane takes
- * before a span is shared between lanes (power of two <= 32).  Results do not depend on it beyond fp32
- * summation order.  Used by bench sweeps.
- */
-int vlgae_dmv_set_tuning(int gmax, int threads, int tpl);
-
-/*
- * Schedule of the DMV kernels (process-wide): 0 = automatic (latency regime -> frontier schedule, one thread per
- * target cell; throughput regime -> gather schedule, lanes stream split points), 1 = frontier, 2 = gather,
- * 3 = role-split.  A schedule that cannot run a launch (chart beyond shared memory, host-memory hand-off) falls back
- * to the automatic choice.  Results agree within the documented tolerances (max semiring: bit-exact).
+ * Schedule of the DMV kernels (process-wide): 0 = automatic, 1 = frontier (one thread per target cell, running
+ * log-sum-exp / arg-max state; the default in every regime), 2 = gather (lanes stream the split points of a span,
+ * two-pass log-sum-exp; csrc/dmv_gather.cu).  A schedule that cannot run a launch (chart beyond shared memory,
+ * host-memory hand-off) falls back to the automatic choice.  Results agree within the documented tolerances
+ * (max semiring: bit-exact).  Used by the tests and the sweep tool.
  */
 int vlgae_dmv_set_schedule(int which);
 

@@ -73,8 +73,6 @@ def main():
             _, _, g32 = oracle.dmv_log(md[:nb], ma[:nb], L[:nb], trim=True)
         for sched, tn in [(s_, t_) for s_ in args.schedules.split(",") for t_ in args.tunings.split(",")]:
             check(L_.vlgae_dmv_set_schedule({"auto": 0, "frontier": 1, "gather": 2, "role": 3}[sched]), "schedule")
-            gmax, threads, tpl = (0, 0, 0) if tn == "auto" else tuple(int(x) for x in tn.split("x"))
-            check(L_.vlgae_dmv_set_tuning(gmax, threads, tpl), "tuning")
             for _ in range(3):
                 ops.dmv_parse(tmd, tma, tL, out=out, prepared=True)
             torch.cuda.synchronize()
@@ -91,7 +89,6 @@ def main():
                 gpu = out.gattach[:nb].cpu().numpy()
                 line += f"  |gpu-f64|={np.abs(gpu - g64).max():.2e} |gpu-f32|={np.abs(gpu - g32).max():.2e} |f32-f64|={np.abs(g32 - g64).max():.2e}"
             print(line, flush=True)
-    check(L_.vlgae_dmv_set_tuning(0, 0, 0), "tuning")
     check(L_.vlgae_dmv_set_schedule(0), "schedule")
 
 

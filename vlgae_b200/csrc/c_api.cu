@@ -55,16 +55,8 @@ int vlgae_dmv_set_profile_buffer(void *device_buf) {
     vlgae::dmv_set_profile_buffer((long long *)device_buf);
     return VLGAE_OK;
 }
-int vlgae_dmv_set_tuning(int gmax, int threads, int tpl) {
-    if ((gmax != 0 && gmax != 1 && gmax != 2 && gmax != 4 && gmax != 8 && gmax != 16 && gmax != 32) ||
-        (threads != 0 && threads != 96 && threads != 192 && threads != 384 && threads != 768))
-        return fail(VLGAE_E_INVALID, "%s", "gmax must be 0/1/2/4/8/16/32 and threads 0/96/192/384/768");
-    if (tpl < 0 || tpl > 32 || (tpl & (tpl - 1))) return fail(VLGAE_E_INVALID, "%s", "tpl must be 0 or a power of two <= 32");
-    vlgae::dmv_set_tuning(gmax, threads, tpl);
-    return VLGAE_OK;
-}
 int vlgae_dmv_set_schedule(int which) {
-    if (which < 0 || which > 3) return fail(VLGAE_E_INVALID, "%s", "schedule must be 0 (auto), 1 (frontier), 2 (gather) or 3 (role)");
+    if (which < 0 || which > 2) return fail(VLGAE_E_INVALID, "%s", "schedule must be 0 (auto), 1 (frontier) or 2 (gather)");
     vlgae::dmv_set_schedule(which);
     return VLGAE_OK;
 }

@@ -1,9 +1,9 @@
 // dmv_frontier.cu -- DMV chart DP, "frontier" schedule: one CTA per sentence, one thread per (target cell, new terms).
 //
-// Same operator as dmv_kernels.cu (reference /root/reference/src/model/torch_struct/dmv.py:19-66 and the autograd
-// marginals / argmax of helpers.py:118-154), different schedule.  The role-split kernel there evaluates a width-w item
-// as "gather w terms, reduce across lanes": two shuffle trees, two barriers and ~350 instructions per warp on the
-// critical path of every width, 2 (len) widths deep -- latency-bound at ~1.7k clk per width.
+// The DMV chart operator (reference /root/reference/src/model/torch_struct/dmv.py:19-66 and the autograd
+// marginals / argmax of helpers.py:118-154).  The textbook evaluation of a width-w item is "gather w terms, reduce across
+// lanes": shuffle trees, barriers and hundreds of instructions per warp on the critical path of every width, 2 (len)
+// widths deep (round 1's role-split kernel, removed; dmv_gather.cu is the lean version of that idea).
 //
 // Here every target cell keeps a running (max, sum) -- or (best, first arg-max) -- and a term is folded in during the
 // phase in which its LATER operand becomes final.  With operand widths (a, b) a term of steps 1/2 (a + b = w - 1) is
@@ -19,7 +19,7 @@
 // parents each push one product into their two operands; within a phase every accumulator word has a single writer
 // (row owner / column owner / distinct words per item kind), so no atomics.
 //
-// Shared memory per cell (diagonal-major index as in dmv_kernels.cu).  Every item kind is its OWN float2 array
+// Shared memory per cell (diagonal-major index).  Every item kind is its OWN float2 array
 // (.x = HASCHILD, .y = NOCHILD): neighbouring lanes own neighbouring cells of one width, so a warp's access to one array
 // is 256 contiguous bytes -- two wavefronts, no bank conflicts -- and a task loads only the item kinds it needs.  (With
 // one float4 per cell, 16-byte-strided scalar accesses were 4-way conflicted and half of every float4 load was unused:
@@ -107,9 +107,15 @@ __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
 // stage dec, width-0 complete items (STOP decisions, dmv.py:39-40) and the arc scores attach + dec[GO]
 // (formed first in fp32, exactly as dmv.py:36-37 does).  dec index = dir*4 + val*2 + decision.
 // MODE 0: plain; 1: also publish the staged values in p.share (log CTA); 2: take them from p.share (max CTA)
+// order-preserving float <-> int key (atomicMax on shared-memory ints gives the maximum of the floats)
+__device__ __forceinline__ int fkey(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float funkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// mukey (log pass only, else null): per child position, the key of its best incoming arc score (first guess of the
+// per-word offsets, see log_pass)
 template <int NT, int MODE>
 __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, float *sdec, uint16_t *cw, float2 *CL, float2 *CR,
-                                             float2 *IL, float2 *IR) {
+                                             float2 *IL, float2 *IR, int *mukey = nullptr) {
     const int tid = blk_tid<NT>(), N = p.N;
     const float *dec = p.dec + (size_t)b * N * 8;
     const float *attach = p.attach + (size_t)b * N * N * 2;
@@ -151,6 +157,8 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
         sdec[t] = v;
         if (MODE == 1) sh_dec[t] = v;
     }
+    if (MODE != 2 && mukey)
+        for (int k = tid; k < Nb; k += NT) mukey[k] = fkey(NEG_BIG);
 #pragma unroll 1
     for (int d = tid; d < Nb; d += NT) {  // cell -> (width, left end)
         const int base = dbase(d, Nb);
@@ -181,11 +189,13 @@ __device__ __forceinline__ void stage_inputs(const DmvArgs &p, int b, int Nb, fl
             const int c = cidx(ch, h - ch, Nb);
             IL[c] = v;
             if (MODE == 1) sh_il[c] = v;
+            if (mukey) atomicMax(mukey + ch, fkey(fmaxf(v.x, v.y)));
         } else {
             const float2 v = make_float2(__fadd_rn(a.x, sdec[h * 8 + 4]), __fadd_rn(a.y, sdec[h * 8 + 6]));
             const int c = cidx(h, ch - h, Nb);
             IR[c] = v;
             if (MODE == 1) sh_ir[c] = v;
+            if (mukey) atomicMax(mukey + ch, fkey(fmaxf(v.x, v.y)));
         }
     }
     if (MODE == 1) {
@@ -421,35 +431,35 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     float zres = 0.f;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
-    if (p.share && attempt == 0) stage_inputs<NT, 1>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
-    else stage_inputs<NT, 0>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR);
+    int *mukey = attempt == 0 ? reinterpret_cast<int *>(mu) : nullptr;
+    if (p.share && attempt == 0) stage_inputs<NT, 1>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR, mukey);
+    else stage_inputs<NT, 0>(p, b, Nb, sdec, cw, c.CL, c.CR, c.IL, c.IR, mukey);
     blk_sync<NT>();
     // Per-word offsets: every arc score into word k is lowered by mu[k]; every tree then scores sum_k mu[k] less, so the
     // posteriors are unchanged and log Z is restored at the end, while the chart values stay O(10) instead of
     // O(-4 len) -- one fp32 ulp there is 1e-6 instead of 1.5e-5, and the marginals come out ~10x closer to the exact
-    // ones than the reference's own fp32 sweep.  First guess: best incoming arc + mean STOP costs of the word; if the top
-    // of the chart still ends up far from 0, the sweep is repeated once with the guess corrected by its residual.
-#pragma unroll 1
-    for (int k = tid; k < Nb; k += NT) {
-        float u = 0.f;
-        if (attempt == 0) {
-            float m = NEG_BIG;
-            for (int h = 0; h < k; ++h) { const float2 v = c.IR[cidx(h, k - h, Nb)]; m = fmaxf(m, fmaxf(v.x, v.y)); }
-            for (int h = k + 1; h < Nb; ++h) { const float2 v = c.IL[cidx(k, h - k, Nb)]; m = fmaxf(m, fmaxf(v.x, v.y)); }
-            if (k >= 1 && m > -1e6f)
-                u = m + 0.5f * (sdec[k * 8 + 1] + sdec[k * 8 + 3]) + 0.5f * (sdec[k * 8 + 5] + sdec[k * 8 + 7]);
-            if (!(fabsf(u) < 1e6f)) u = 0.f;
-        } else if (k >= 1) {
-            u = mu[k] + zres / (float)len;
+    // ones than the reference's own fp32 sweep.  First guess: best incoming arc (collected while staging) + mean STOP
+    // costs of the word; if the top of the chart still ends up far from 0, the sweep is repeated once with the guess
+    // corrected by its residual.
+    if (tid < 32) {
+        float part = 0.f;
+        for (int k = tid; k < Nb; k += 32) {
+            float u = 0.f;
+            if (attempt == 0) {
+                const float m = funkey(mukey[k]);
+                if (k >= 1 && m > -1e6f)
+                    u = m + 0.5f * (sdec[k * 8 + 1] + sdec[k * 8 + 3]) + 0.5f * (sdec[k * 8 + 5] + sdec[k * 8 + 7]);
+                if (!(fabsf(u) < 1e6f)) u = 0.f;
+            } else if (k >= 1) {
+                u = mu[k] + zres / (float)len;
+            }
+            mu[k] = u;
+            part += u;
         }
-        mu[k] = u;
+        for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (tid == 0) mu[Nb] = part;
     }
     blk_sync<NT>();
-    if (tid == 0) {
-        float t = 0.f;
-        for (int k = 1; k < Nb; ++k) t += mu[k];
-        mu[Nb] = t;
-    }
 #pragma unroll 1
     for (int cc = Nb + tid; cc < nc; cc += NT) {  // cell (width d, left end lo): IL is the arc into lo, IR the arc into lo + d
         const int d = cw[cc] >> 8, lo = cw[cc] & 255;
@@ -556,7 +566,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         }
     }
     zres = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65, minus the offsets
-    if (fabsf(zres) <= 32.f || len == 0) break;
+    if (fabsf(zres) <= 48.f || len == 0) break;
     blk_sync<NT>();
     }
     if (prof) p.prof[1] = clock64() - t0c;
@@ -859,7 +869,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel: persistent CTAs stride over (sentence, semiring) work items (same placement rule as dmv_kernels.cu)
+// kernel: persistent CTAs stride over (sentence, semiring) work items 
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CPT, bool GC = false>
 __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 6 : (NT == 64 ? 12 : 1)))) dmv_frontier_kernel(DmvArgs p) {

@@ -277,7 +277,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *smem, 
         blk_sync<NT>();
     }
     zres = C[len + 1].y;  // CR(0, len).NO (dmv.py:65) minus the offsets
-    if (fabsf(zres) <= 32.f || len == 0) break;
+    if (fabsf(zres) <= 48.f || len == 0) break;
     blk_sync<NT>();
     }
     if (tid == 0) p.Z[b] = zres + mu[Nb];

@@ -1,4 +1,4 @@
-// dmv_kernels.cuh -- internal interface between the C ABI (c_api.cu) and the DMV kernels.
+// dmv_kernels.cuh -- internal interface between the C ABI (c_api.cu), the launch logic (dmv_launch.cu) and the DMV kernels.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -31,10 +31,7 @@ struct DmvArgs {
     int nsm;           // SM count (work-item placement)
     int nb_lo, nb_hi;  // this launch handles sentences with nb_lo <= len + 1 <= nb_hi (length buckets)
     int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
-    int gmax;          // max lanes per span (1, 2, 4, 8); 0 = choose from the batch size
-    int threads;       // CTA size (96, 192, 384); 0 = choose from N
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
-    int tpl;           // split points per lane before a span is shared between lanes (1..32, power of 2); 0 = auto
     // frontier kernel, both passes in one launch, inputs in pinned HOST memory: the log CTA of a sentence republishes
     // what it staged (dec, arc scores) in device memory and the max CTA of the same sentence takes it from there, so
     // every input byte crosses PCIe once.  share_flag[b] == share_epoch once sentence b is published.
@@ -45,10 +42,8 @@ struct DmvArgs {
 };
 
 // passes bitmask: 1 = log semiring, 2 = max semiring
-size_t dmv_chart_bytes(int N, int passes);
 bool dmv_fits_smem(int N, int passes);
 int dmv_grid_for_workspace(int B);
-void dmv_set_tuning(int gmax, int threads, int tpl);
 void dmv_set_profile_buffer(long long *buf);
 long long *dmv_profile_buffer();  // nullptr unless a debug buffer was registered
 cudaError_t launch_dmv(const DmvArgs &a, int passes, cudaStream_t st);
@@ -60,7 +55,7 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
 // gather schedule (dmv_gather.cu): throughput regime, chart in shared memory, row-major squares
 bool dmv_gather_fits(int cap, int passes, int smem_optin);
 cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st);
-void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather, 3 = role-split
+void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather
 size_t dmv_ws_slice_bytes(int N, int passes);  // what vlgae_dmv_workspace_bytes reserves per CTA (either schedule)
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);

@@ -1,0 +1,226 @@
+// dmv_launch.cu -- host-side launch logic of the DMV kernels + the small element-wise kernels of the path.
+//
+// The chart kernels themselves live in dmv_frontier.cu (latency regime, zero-copy hand-off, charts beyond shared
+// memory) and dmv_gather.cu (gather schedule).  This file chooses the schedule, CTA size and length buckets per launch
+// and holds DMV1o.merge (reference /root/reference/src/model/torch_struct/distributions.py:253-265), the row scaling
+// used by the autograd nodes and the two roofline microbenchmarks.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "dmv_kernels.cuh"
+
+namespace vlgae {
+
+namespace {
+
+__global__ void merge_kernel(const float *dec, const float *attach, const float *root, int B, int n, float one,
+                             float zero, float *dec_w, float *attach_w) {
+    // distributions.py:253-265
+    const int N = n + 1;
+    const size_t na = (size_t)B * N * N * 2, nd = (size_t)B * N * 8;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < na + nd; t += (size_t)gridDim.x * blockDim.x) {
+        if (t < na) {
+            const int v = t & 1;
+            size_t r = t >> 1;
+            const int c = r % N; r /= N;
+            const int h = r % N;
+            const size_t b = r / N;
+            float x = zero;
+            if (h == 0) { if (c >= 1 && v == 1) x = root[b * n + (c - 1)]; }
+            else if (c >= 1) x = attach[((b * n + (h - 1)) * n + (c - 1)) * 2 + v];
+            attach_w[t] = x;
+        } else {
+            const size_t u = t - na;
+            const int k = u & 7;  // dir*4 + val*2 + decision
+            const size_t r = u >> 3;
+            const int i = r % N;
+            const size_t b = r / N;
+            float x;
+            if (i == 0) x = (k >> 2) == 1 ? one : zero;
+            else x = dec[(b * n + (i - 1)) * 8 + k];
+            dec_w[u] = x;
+        }
+    }
+}
+
+__global__ void scale_rows_kernel(const float *in, const float *g, int B, size_t inner, float *out) {
+    const size_t total = (size_t)B * inner;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+        out[t] = in[t] * g[t / inner];
+}
+
+__global__ void mufu_bench_kernel(int iters, float *sink) {
+    float a = threadIdx.x * 1e-3f, b = a + 0.1f, c = a + 0.2f, d = a + 0.3f;
+    float e = a + 0.4f, f = a + 0.5f, g = a + 0.6f, h = a + 0.7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(b));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(c)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(d));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(e)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(f));
+            asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(g)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(h));
+        }
+    }
+    if (a + b + c + d + e + f + g + h == 123.456f) sink[0] = a;
+}
+
+__global__ void fp32_bench_kernel(int iters, float *sink) {
+    float a = threadIdx.x * 1e-3f, b = a + 0.1f, c = a + 0.2f, d = a + 0.3f;
+    float e = a + 0.4f, f = a + 0.5f, g = a + 0.6f, h = a + 0.7f;
+    const float k = 1.0000001f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a) : "f"(k)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(b) : "f"(k));
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(c) : "f"(k)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(d) : "f"(k));
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(e) : "f"(k)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f) : "f"(k));
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(g) : "f"(k)); asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(h) : "f"(k));
+        }
+    }
+    if (a + b + c + d + e + f + g + h == 123.456f) sink[0] = a;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host-side launch logic
+// ---------------------------------------------------------------------------------------------
+static int g_sm_count = 0, g_smem_optin = 0, g_info_dev = -1;
+static cudaError_t device_info() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev == g_info_dev) return cudaSuccess;
+    e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) g_info_dev = dev;
+    return e;
+}
+
+size_t dmv_ws_slice_bytes(int N, int passes) { return dmv_frontier_chart_bytes(N, passes); }
+
+bool dmv_fits_smem(int N, int passes) {
+    if (device_info() != cudaSuccess) return false;
+    return dmv_frontier_fits(N, passes, g_smem_optin);
+}
+
+int dmv_grid_for_workspace(int B) {
+    if (device_info() != cudaSuccess) return 0;
+    const int cap = g_sm_count * 4;
+    return B * 2 < cap ? B * 2 : cap;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+static int g_schedule = 0;  // 0 = automatic, 1 = frontier, 2 = gather
+void dmv_set_schedule(int which) { g_schedule = which; }
+static long long *g_prof = nullptr;
+void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
+long long *dmv_profile_buffer() { return g_prof; }
+
+// one launch over the sentences with nb_lo <= len + 1 <= nb_hi, shared memory sized for `cap` positions
+static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, cudaStream_t st) {
+    static const int env_sched = [] {
+        const char *v = getenv("VLGAE_DMV_KERNEL");
+        return !v ? 0 : (v[0] == 'f' ? 1 : (v[0] == 'g' ? 2 : 0));
+    }();
+    const int sched = g_schedule ? g_schedule : env_sched;
+    static const int env_ft = env_int("VLGAE_FRONTIER_THREADS", 0);
+    static const int env_gt = env_int("VLGAE_GATHER_THREADS", 0);
+    const bool fits = dmv_frontier_fits(cap, passes, g_smem_optin);
+    const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count;
+    // The gather schedule (dmv_gather.cu) runs on request only: the frontier schedule is the faster one in every regime
+    // measured so far; it also keeps the zero-copy hand-off and the charts beyond shared memory.
+    if (sched == 2 && !a.share && dmv_gather_fits(cap, passes, g_smem_optin)) {
+        int gt = cap <= 20 ? 32 : (cap <= 48 ? 64 : (cap <= 60 ? 128 : 256));
+        if (env_gt > 0) gt = env_gt;
+        DmvArgs f = a;
+        f.workspace = nullptr; f.ws_stride = 0;
+        return launch_dmv_gather(f, passes, cap, gt, g_sm_count, st);
+    }
+    if (cap > 256 || !(fits || a.workspace)) return cudaErrorInvalidValue;
+    DmvArgs f = a;
+    // Latency regime (every work item resident at once): many threads, running state in registers.  Throughput
+    // regime: small CTAs with the state in shared memory (idle warps skip a phase entirely) -- measured on B200:
+    // COCO-like bulk 806 us vs 1126, 512 x 16 words 31 us vs 58; 40-word charts prefer 256 threads / registers.
+    // Charts beyond shared memory (N > ~72): same kernel, chart arrays in the CTA's workspace slice (L2-resident).
+    int ft;
+    bool reg_state;
+    if (!fits) { ft = env_int("VLGAE_FRONTIER_BIG_THREADS", 1024); reg_state = false; }
+    else if (resident) { ft = cap <= 24 ? 256 : 512; reg_state = true; }
+    // warp per sentence for short charts; with 5 cells per lane (15-17 positions) a sentence takes longer than in a
+    // 128-thread CTA, so that size only switches inside bulk (length-bucketed) launches (682 vs 714 us)
+    else if (cap <= 14 || (cap <= 17 && a.nb_hi < a.N))  // nb_hi < N: a length bucket of a bulk launch
+        { ft = env_int("VLGAE_FRONTIER_WARP", 1) ? 32 : (cap <= 12 ? 64 : 128); reg_state = false; }
+    else if (cap <= 33) { ft = 128; reg_state = false; }
+    else if (cap <= 45) { ft = 256; reg_state = true; }   // <= 1024 cells: 4 per thread in registers
+    else { ft = 512; reg_state = false; }                 // one CTA per SM: more threads (n = 64: 907 vs 1039 us)
+    if (env_ft > 0) ft = env_ft;
+    if (fits) { f.workspace = nullptr; f.ws_stride = 0; }
+    else f.ws_stride = dmv_ws_slice_bytes(a.N, 3);
+    return launch_dmv_frontier(f, passes, cap, ft, reg_state, g_sm_count, dmv_grid_for_workspace(a.B), st);
+}
+
+cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
+    DmvArgs a = a_in;
+    a.prof = g_prof;
+    cudaError_t e = device_info();
+    if (e != cudaSuccess) return e;
+    a.nsm = g_sm_count;
+    a.nb_lo = 0; a.nb_hi = a.N;
+    // Throughput regime (more work items than one resident wave at the padded length): one launch per length bucket,
+    // shared memory sized for the bucket, so short sentences run at 10-20 CTAs per SM instead of the 3 a 40-word
+    // chart allows.  Sentences outside a launch's bucket are skipped by its CTAs (no host knowledge of the lengths,
+    // no sorting assumption).  Longest bucket first.
+    static const int env_bucket = env_int("VLGAE_DMV_BUCKETS", 1);
+    const long long items = (long long)a.B * a.npass;
+    const bool bulk = env_bucket && items > 8192 && !a.share;
+    if (!bulk) return launch_cap(a, passes, a.N, st);
+    static const int caps[] = {8, 12, 16, 20, 24, 28, 33, 41, 49, 65, 97, 129, 256};
+    int nb = 0, bounds[16];
+    for (int c : caps) if (c < a.N) bounds[nb++] = c;
+    bounds[nb++] = a.N;
+    for (int k = nb - 1; k >= 0; --k) {
+        DmvArgs bkt = a;
+        bkt.nb_hi = bounds[k];
+        bkt.nb_lo = k > 0 ? bounds[k - 1] + 1 : 0;
+        e = launch_cap(bkt, passes, bounds[k], st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
+                         float *dec_w, float *attach_w, cudaStream_t st) {
+    const size_t total = (size_t)B * (n + 1) * ((size_t)(n + 1) * 2 + 8);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    merge_kernel<<<grid, 256, 0, st>>>(dec, attach, root, B, n, one, zero, dec_w, attach_w);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, cudaStream_t st) {
+    const size_t total = (size_t)B * inner;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    scale_rows_kernel<<<grid, 256, 0, st>>>(in, g, B, inner, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_microbench(int which, int iters, float *sink, int *grid_out, int *block_out, cudaStream_t st) {
+    cudaError_t e = device_info();
+    if (e != cudaSuccess) return e;
+    const int grid = g_sm_count * 8, block = 256;
+    if (which == 0) mufu_bench_kernel<<<grid, block, 0, st>>>(iters, sink);
+    else fp32_bench_kernel<<<grid, block, 0, st>>>(iters, sink);
+    *grid_out = grid; *block_out = block;
+    return cudaGetLastError();
+}
+
+}  // namespace vlgae
