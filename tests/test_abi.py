@@ -78,3 +78,47 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src:
                     bad.append(f)
     assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_integration_alias_recipe():
+    """aliasing vlgae_b200.torch_struct under the reference's module paths makes the
+    reference's own import statements (ldndmv.py:21-22, joint.py:20, src/__init__.py:113-117) resolve to the mirror."""
+    import importlib
+    import sys
+    import types
+
+    saved = {k: v for k, v in sys.modules.items() if k == "src" or k.startswith("src.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        # stand-ins for the reference's package skeleton (src/__init__.py needs hydra / lightning, absent here)
+        for pkg in ("src", "src.model"):
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+        for name in ("", ".dmv", ".distributions", ".semirings", ".semirings.semirings"):
+            sys.modules["src.model.torch_struct" + name] = importlib.import_module("vlgae_b200.torch_struct" + name)
+        ns = {}
+        exec("from src.model.torch_struct import DMV1o, DependencyCRF\n"
+             "from src.model.torch_struct.dmv import LEFT, RIGHT, NOCHILD, HASCHILD, GO, STOP\n"
+             "import src.model.torch_struct as stt\n", ns)
+        assert (ns["LEFT"], ns["RIGHT"], ns["HASCHILD"], ns["NOCHILD"], ns["GO"], ns["STOP"]) == (0, 1, 0, 1, 0, 1)
+        import vlgae_b200.torch_struct as vts
+
+        assert ns["DMV1o"] is vts.DMV1o and ns["DependencyCRF"] is vts.DependencyCRF
+        old = ns["stt"].semirings.semirings.NEGINF
+        ns["stt"].semirings.semirings.NEGINF = -1e20   # what src.setup_inf(1e20) does
+        assert vts.semirings.semirings.NEGINF == -1e20
+        ns["stt"].semirings.semirings.NEGINF = old
+        # unsupported methods raise instead of returning something else
+        import pytest
+        import torch
+
+        d = vts.DMV1o([torch.zeros(1, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2)], torch.tensor([1]))
+        for call in (lambda: d.kmax(2), lambda: d.topk(2), d.entropy, d.sample):
+            with pytest.raises(NotImplementedError):
+                call()
+    finally:
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

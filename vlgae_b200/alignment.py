@@ -29,10 +29,12 @@ def _plain(t):
 
 
 def _workspace(dev, nbytes):
-    ws = _ws.get(dev)
+    # one scratch buffer per (device, stream): calls on different streams must not share the packed operand tiles
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _ws[dev] = ws
+        _ws[key] = ws
     return ws
 
 

@@ -147,8 +147,13 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             static thread_local unsigned char *share = nullptr;
             static thread_local size_t share_bytes = 0;
             static thread_local unsigned epoch = 0;
+            static thread_local int share_dev = -1;
             const int stride = N * 8 + 4 * (N * (N + 1) / 2);
             const size_t need = (size_t)B * stride * 4 + (size_t)B * 4 + 64;
+            int cur_dev = 0;
+            cudaGetDevice(&cur_dev);
+            if (share && share_dev != cur_dev) { share = nullptr; share_bytes = 0; }  // another device: its own buffer (the old one stays with its device)
+            share_dev = cur_dev;
             if (share_bytes < need) {
                 if (share) { cudaStreamSynchronize(st); cudaFree(share); share = nullptr; share_bytes = 0; }
                 cudaError_t ea = cudaMalloc((void **)&share, need);
@@ -190,7 +195,14 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     // pay an allocation per batch
     static thread_local unsigned char *arena = nullptr;
     static thread_local size_t arena_bytes = 0;
+    static thread_local int arena_dev = -1;
     cudaError_t e = cudaSuccess;
+    {
+        int cur_dev = 0;
+        cudaGetDevice(&cur_dev);
+        if (arena && arena_dev != cur_dev) { arena = nullptr; arena_bytes = 0; }
+        arena_dev = cur_dev;
+    }
     if (arena_bytes < bytes) {
         if (arena) { cudaStreamSynchronize(st); cudaFree(arena); arena = nullptr; arena_bytes = 0; }
         e = cudaMalloc((void **)&arena, bytes);

@@ -878,7 +878,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
     const int nsm = p.nsm;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int item = t;
-        if (total <= (int)gridDim.x && t >= nsm) item = total - 1 - (t - nsm);
+        // (not with the host-memory hand-off: there a max CTA spins on its sentence's log CTA, which must have the
+        // lower block index so that it is scheduled first whatever else shares the GPU)
+        if (total <= (int)gridDim.x && t >= nsm && !p.share) item = total - 1 - (t - nsm);
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }

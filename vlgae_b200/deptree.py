@@ -29,10 +29,11 @@ def run(arc, lengths, semiring, want_marg):
     out = torch.empty(B, dtype=torch.float32, device=dev)
     marg = torch.empty((B, N, N), dtype=torch.float32, device=dev) if want_marg else None
     need = lib().vlgae_deptree_workspace_bytes(B, N)
-    ws = _ws.get(dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)  # per stream: concurrent calls must not share scratch
+    ws = _ws.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
-        _ws[dev] = ws
+        _ws[key] = ws
     fill = float(_sr.NEGINF)  # looked up at call time, like the reference's zero_() (quirk Q1)
     with torch.cuda.device(dev):
         check(lib().vlgae_deptree(arc.data_ptr(), lengths.data_ptr(), B, N, fill, MASK_ZERO,

@@ -39,10 +39,12 @@ def _workspace(dev: torch.device, B: int, N: int) -> Tuple[Optional[torch.Tensor
     need = lib().vlgae_dmv_workspace_bytes(B, N)
     if need == 0:
         return None, 0
-    ws = _workspaces.get(dev)
+    # one scratch buffer per (device, stream): launches on different streams must not share chart storage
+    key = (dev, _stream(dev))
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        _workspaces[dev] = ws
+        _workspaces[key] = ws
     return ws, ws.numel()
 
 

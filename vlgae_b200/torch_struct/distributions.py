@@ -105,7 +105,10 @@ class StructDistribution:
         self._unsupported("sample")
 
     def kmax(self, k):
-        return self.argmax
+        self._unsupported("kmax")
+
+    def topk(self, k):
+        self._unsupported("topk")
 
 
 class DMV1o(StructDistribution):
@@ -159,6 +162,12 @@ class DependencyCRF(StructDistribution):
     def _run(self, semiring, want_marg):
         from .. import deptree
 
+        if torch.is_grad_enabled() and self.log_potentials.requires_grad:
+            # the reference's partition / max are autograd-connected; here they are decode-only (the one caller,
+            # ldndmv.py:294-299, runs under no_grad on detached marginals) -- refuse rather than detach silently
+            raise NotImplementedError(
+                "DependencyCRF: potentials that require grad are not supported (MBR decoding only); "
+                "detach them or call under torch.no_grad()")
         return deptree.run(self.log_potentials, self.lengths, semiring, want_marg)
 
     @lazy_property
