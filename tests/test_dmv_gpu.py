@@ -116,7 +116,10 @@ def test_golden_reference_vectors(golden, dev, schedule, name):
     np.testing.assert_allclose(Z.cpu().numpy(), g["partition"][:, 0], rtol=Z_RTOL)
     assert_three_way(gatt.cpu().numpy(), g["grad_attach"], gatt64)
     assert_three_way(gdec.cpu().numpy(), g["grad_dec"], gdec64)
-    if hmd.shape[1] <= 41:  # len <= 40: the north star's plain tolerance against the reference itself
+    # the north star's plain tolerance against the reference itself wherever the reference leaves room for it: a sweep
+    # that is exact to 3e-7 (the linear-domain one) sits exactly |ref - fp64| away from the reference, which is
+    # 1.0011e-5 on the cfg2 batch
+    if np.abs(g["grad_attach"] - gatt64).max() <= 9.5e-6:
         np.testing.assert_allclose(gatt.cpu().numpy(), g["grad_attach"], rtol=0, atol=MARG_ATOL)
     np.testing.assert_array_equal(best.cpu().numpy(), g["max"][:, 0])
     np.testing.assert_array_equal(heads.cpu().numpy(), g["heads"])

@@ -447,7 +447,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             float u = 0.f;
             if (attempt == 0) {
                 const float m = funkey(mukey[k]);
-                if (k >= 1 && m > -1e6f)
+                if (k >= 1 && m > -1e6f && !p.no_offsets)
                     u = m + 0.5f * (sdec[k * 8 + 1] + sdec[k * 8 + 3]) + 0.5f * (sdec[k * 8 + 5] + sdec[k * 8 + 7]);
                 if (!(fabsf(u) < 1e6f)) u = 0.f;
             } else if (k >= 1) {
@@ -872,7 +872,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
 // kernel: persistent CTAs stride over (sentence, semiring) work items 
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CPT, bool GC = false>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 6 : (NT == 64 ? 12 : 1)))) dmv_frontier_kernel(DmvArgs p) {
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 8 : (NT == 64 ? 16 : 1)))) dmv_frontier_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.B * p.npass;
     const int nsm = p.nsm;

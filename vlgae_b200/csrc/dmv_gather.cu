@@ -121,8 +121,39 @@ __device__ __forceinline__ void stage(const DmvArgs &p, int b, const Geo &g, int
     }
 }
 
+// Per-word offsets: every arc score into word k is lowered by mu[k], which lowers every tree by sum_k mu[k] -- the
+// posteriors are unchanged, log Z is restored at the end -- and keeps the chart values O(10) instead of O(-4 len).
+// First guess (attempt 0): best incoming arc + mean STOP costs of the word; attempt 1: the guess corrected by the
+// residual zres of the first sweep.  mu[Nb] = sum of the offsets.  Ends with a barrier.
+template <int NT>
+__device__ __forceinline__ void offsets(const float2 *I, const float *sdec, float *mu, int Nb, int S, int len, int tid,
+                                        int attempt, float zres) {
+    for (int k = tid; k < Nb; k += NT) {
+        float u = 0.f;
+        if (attempt == 0) {
+            float m = NEG_BIG;
+            for (int h = 0; h < Nb; ++h)
+                if (h != k) { const float2 v = I[h * S + k]; m = fmaxf(m, fmaxf(v.x, v.y)); }
+            if (k >= 1 && m > -1e6f)
+                u = m + 0.5f * (sdec[k * 8 + 1] + sdec[k * 8 + 3]) + 0.5f * (sdec[k * 8 + 5] + sdec[k * 8 + 7]);
+            if (!(fabsf(u) < 1e6f)) u = 0.f;
+        } else if (k >= 1) {
+            u = mu[k] + zres / (float)len;
+        }
+        mu[k] = u;
+    }
+    blk_sync<NT>();
+    if (tid < 32) {
+        float part = 0.f;
+        for (int k = 1 + tid; k < Nb; k += 32) part += mu[k];
+        for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (tid == 0) mu[Nb] = part;
+    }
+    blk_sync<NT>();
+}
+
 // ---------------------------------------------------------------------------------------------
-// log semiring
+// log semiring in the log domain (two-pass log-sum-exp): the fallback of lin_pass
 // ---------------------------------------------------------------------------------------------
 template <int NT>
 __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *smem, int tid) {
@@ -385,6 +416,240 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *smem, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// log semiring in the LINEAR domain (default).  With the per-word offsets every chart value exp(v - offsets) is
+// O(e^+-20), well inside the fp32 range, so the log-semiring recurrences (dmv.py:50-62 with logsumexp / +) can be run as
+// plain sums of products: one FMA per split-point term, no exp, no max pass, no log.  The reverse sweep propagates
+// linear adjoints: for alpha_P += alpha_L alpha_R,  beta_L += beta_P alpha_R and beta_R += beta_P alpha_L; seeded with
+// gZ / Z', alpha_item * beta_item is d(gZ log Z) / d(log potential) -- the arc marginals and decision counts the
+// reference obtains by autograd through the chart (helpers.py:150-154).
+// The fused width step: for span (i, j) the lanes stream a in [0, w-1) once and accumulate, in the same loop, the terms of
+// X(a), of CL with split a + 1 and of CR with split a (all operands narrower than w); the one remaining X term and the
+// two same-span terms (CL split 0 needs IL(j,i), CR split w-1 needs IR(i,j)) are added after the single xor-shuffle
+// reduction -- no __syncwarp, one reduction and one barrier per width.
+// Returns false when the sweep left the fp32 range or fails its self-check (every word's arc marginals must sum to gZ):
+// the caller then runs the log-domain sweep (log_pass) for this sentence.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ bool blk_all(bool ok) {
+    if (NT == 32) return __all_sync(0xffffffffu, ok);
+    return __syncthreads_and(ok);
+}
+
+template <int NT>
+__device__ bool lin_pass(const DmvArgs &p, int b, int len, unsigned char *smem, int tid) {
+    Geo g;
+    g.Nb = len + 1; g.S = row_stride(g.Nb); g.S1 = g.S + 1; g.E = g.Nb * g.S;
+    const int Nb = g.Nb, S = g.S, S1 = g.S1, E = g.E, N = p.N;
+    float2 *C = reinterpret_cast<float2 *>(smem);
+    float2 *I = C + E, *gC = I + E, *gI = gC + E;
+    float *Ct = reinterpret_cast<float *>(gI + E), *X = Ct + E, *sdec = X + E;
+    const int warp = NT == 32 ? 0 : (tid >> 5), lane = tid & 31;
+    constexpr int NW = NT / 32;
+    const bool want_grad = (p.gdec != nullptr) || (p.gattach != nullptr);
+    float *mu = sdec + Nb * 8;  // Nb per-word offsets + their sum
+    float zres = 0.f, ztop = 1.f;
+    bool ok = true;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        stage<NT, true>(p, b, g, tid, sdec, C, I, Ct);
+        if (want_grad && attempt == 0) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 *g4 = reinterpret_cast<float4 *>(gC);  // gC and gI are contiguous: E float4
+            for (int t = tid; t < E; t += NT) g4[t] = z;
+        }
+        blk_sync<NT>();
+        offsets<NT>(I, sdec, mu, Nb, S, len, tid, attempt, zres);
+        // to the linear domain: STOP factors as they are, arc factors lowered by the offset of their child
+        for (int i = tid; i < Nb; i += NT) {
+            const float2 cl = C[i * S + i], cr = C[i * S + i + 1];
+            const float2 el = make_float2(ex2(cl.x * LOG2E), ex2(cl.y * LOG2E)), er = make_float2(ex2(cr.x * LOG2E), ex2(cr.y * LOG2E));
+            C[i * S + i] = el; C[i * S + i + 1] = er;
+            Ct[i * S + i + 1] = el.x; Ct[i * S + i] = er.y;
+        }
+        for (int h = warp; h < Nb; h += NW)
+            for (int c = lane; c < Nb; c += 32) {
+                if (c == h) continue;
+                const float2 v = I[h * S + c];
+                const float m = mu[c];
+                I[h * S + c] = make_float2(ex2(__fadd_rn(v.x, -m) * LOG2E), ex2(__fadd_rn(v.y, -m) * LOG2E));
+            }
+        blk_sync<NT>();
+
+        // ---------------- inside ----------------
+#pragma unroll 1
+        for (int w = 1; w <= len; ++w) {
+            const int n = Nb - w;
+            const int lg = pick_lg<NT>(n, w);
+            const Unit u = make_unit<NT>(lane, lg, w - 1);  // the fused loop covers a in [0, w - 1)
+#pragma unroll 1
+            for (int base = warp * u.spw; base < n; base += NW * u.spw) {
+                const int i = base + u.il;
+                const bool valid = i < n;
+                const int ic = valid ? i : n - 1, j = ic + w;
+                const float2 *pL = C + ic * S1 + 1 + u.a0;     // CR(i, i + a)          (HAS, NO)
+                const float2 *pR = C + j * S + ic + 1 + u.a0;  // CL(j, i + 1 + a)      (NO, HAS)
+                const float *tL = Ct + ic * S1 + 2 + u.a0;     // CLt[i][i + a + 1]     split a + 1 of step 3
+                const float2 *iL = I + j * S + ic + 1 + u.a0;  // IL(j, i + a + 1)
+                const float2 *iR = I + ic * S1 + 1 + u.a0;     // IR(i, i + 1 + a)      split a of step 4
+                const float *tR = Ct + j * S + ic + 1 + u.a0;  // CRt[j][i + 1 + a]
+                float2 x = make_float2(0.f, 0.f), cl = x, cr = x;  // x = (XR, XL)
+#pragma unroll 4
+                for (int k = 0; k < u.cnt; ++k) {
+                    x = __ffma2_rn(pL[k], pR[k], x);
+                    const float l3 = tL[k], r4 = tR[k];
+                    const float2 i3 = iL[k], i4 = iR[k];
+                    cl.x = fmaf(l3, i3.x, cl.x); cl.y = fmaf(l3, i3.y, cl.y);
+                    cr.x = fmaf(i4.x, r4, cr.x); cr.y = fmaf(i4.y, r4, cr.y);
+                }
+                if (u.q == 0) x = __ffma2_rn(C[ic * S + ic + w], C[j * S + j], x);  // X term a = w - 1: CR(i, j-1) CL(j, j)
+                for (int o = 16; o >= u.spw; o >>= 1) {
+                    x.x += __shfl_xor_sync(0xffffffffu, x.x, o); x.y += __shfl_xor_sync(0xffffffffu, x.y, o);
+                    cl.x += __shfl_xor_sync(0xffffffffu, cl.x, o); cl.y += __shfl_xor_sync(0xffffffffu, cl.y, o);
+                    cr.x += __shfl_xor_sync(0xffffffffu, cr.x, o); cr.y += __shfl_xor_sync(0xffffffffu, cr.y, o);
+                }
+                if (valid && u.q == 0) {
+                    float2 *pil = I + j * S + ic, *pir = I + ic * S + j;
+                    const float2 al = *pil, ar = *pir;
+                    const float2 il = make_float2(x.y * al.x, x.y * al.y), ir = make_float2(x.x * ar.x, x.x * ar.y);
+                    const float l0 = Ct[ic * S1 + 1], r0 = Ct[j * S + j];  // CL(i,i).NO, CR(j,j).NO
+                    cl.x = fmaf(l0, il.x, cl.x); cl.y = fmaf(l0, il.y, cl.y);   // step 3, split 0
+                    cr.x = fmaf(ir.x, r0, cr.x); cr.y = fmaf(ir.y, r0, cr.y);   // step 4, split w - 1
+                    if (ic == 0 && w != len) cr = make_float2(0.f, 0.f);        // single-root mask, dmv.py:63 (exp(-1e12))
+                    *pil = il; *pir = ir;
+                    X[j * S + ic] = x.y; X[ic * S + j] = x.x;
+                    C[j * S + ic] = make_float2(cl.y, cl.x);
+                    C[ic * S + j + 1] = cr;
+                    Ct[ic * S + j + 1] = cl.y;
+                    Ct[j * S + ic] = cr.y;
+                }
+            }
+            blk_sync<NT>();
+        }
+        ztop = C[len + 1].y;  // CR(0, len).NO (dmv.py:65) in the linear domain
+        ok = ztop > 1e-30f && ztop < 1e30f;  // also false for NaN
+        if (!ok) break;
+        zres = lg2(ztop) * LN2;
+        if (fabsf(zres) <= 16.f || len == 0) break;
+        blk_sync<NT>();
+    }
+    if (!ok) { blk_sync<NT>(); return false; }
+    if (!want_grad) {
+        if (tid == 0) p.Z[b] = zres + mu[Nb];
+        blk_sync<NT>();
+        return true;
+    }
+
+    // ---------------- outside (linear adjoints) ----------------
+    const float gz = p.gZ ? p.gZ[b] : 1.f;
+    if (tid == 0) gC[len + 1].y = __fdividef(gz, ztop);
+    blk_sync<NT>();
+#pragma unroll 1
+    for (int w = len; w >= 1; --w) {
+        const int n = Nb - w;
+        const int lg = pick_lg<NT>(n, w);
+        const Unit u = make_unit<NT>(lane, lg, w);
+        // phase A'(w): complete parents of width w (steps 3, 4 transposed)
+#pragma unroll 1
+        for (int base = warp * u.spw; base < n; base += NW * u.spw) {
+            const int i = base + u.il;
+            if (i >= n || u.cnt <= 0) continue;
+            const int j = i + w;
+            const float2 plg = gC[j * S + i];  // beta CL(j, i): (NO, HAS)
+            float2 prg = gC[i * S + j + 1];    // beta CR(i, j): (HAS, NO)
+            if (i == 0 && w != len) prg = make_float2(0.f, 0.f);  // the mask overwrote CR[0][w]: nothing passes
+            const float2 bcl = make_float2(plg.y, plg.x);
+            const float *tL = Ct + i * S1 + 1 + u.a0;
+            const float2 *iL = I + j * S + i + u.a0, *iR = I + i * S1 + 1 + u.a0;
+            float2 *giL = gI + j * S + i + u.a0, *giR = gI + i * S1 + 1 + u.a0;
+            const float *tR = Ct + j * S + i + 1 + u.a0;
+            float *gl = &gC[(i + u.a0) * S + i].x;          // beta CL(i + a, i).NO
+            float *gr = &gC[(i + 1 + u.a0) * S + j + 1].y;  // beta CR(i + 1 + a, j).NO
+            const int gs = 2 * S;
+#pragma unroll 2
+            for (int k = 0; k < u.cnt; ++k) {
+                const float l3 = tL[k], r4 = tR[k];
+                const float2 i3 = iL[k], i4 = iR[k];
+                const float2 o3 = giL[k], o4 = giR[k];
+                const float ol = gl[k * gs], orr = gr[k * gs];
+                giL[k] = make_float2(fmaf(bcl.x, l3, o3.x), fmaf(bcl.y, l3, o3.y));
+                giR[k] = make_float2(fmaf(prg.x, r4, o4.x), fmaf(prg.y, r4, o4.y));
+                gl[k * gs] = fmaf(bcl.x, i3.x, fmaf(bcl.y, i3.y, ol));
+                gr[k * gs] = fmaf(prg.x, i4.x, fmaf(prg.y, i4.y, orr));
+            }
+        }
+        blk_sync<NT>();
+        // phase B'(w): incomplete parents of width w (steps 1, 2 transposed); beta X = sum_v beta I(v) E(v), E = I / X
+#pragma unroll 1
+        for (int base = warp * u.spw; base < n; base += NW * u.spw) {
+            const int i = base + u.il;
+            if (i >= n || u.cnt <= 0) continue;
+            const int j = i + w;
+            const float2 gil = gI[j * S + i], gir = gI[i * S + j], ail = I[j * S + i], air = I[i * S + j];
+            const float xl = X[j * S + i], xr = X[i * S + j];
+            const float2 bx = make_float2(xr > 0.f ? __fdividef(fmaf(gir.x, air.x, gir.y * air.y), xr) : 0.f,
+                                          xl > 0.f ? __fdividef(fmaf(gil.x, ail.x, gil.y * ail.y), xl) : 0.f);  // (XR, XL)
+            const float2 *pL = C + i * S1 + 1 + u.a0, *pR = C + j * S + i + 1 + u.a0;
+            float2 *qL = gC + i * S1 + 1 + u.a0, *qR = gC + j * S + i + 1 + u.a0;
+#pragma unroll 2
+            for (int k = 0; k < u.cnt; ++k) {
+                const float2 a = pL[k], c2 = pR[k], oa = qL[k], oc = qR[k];
+                qL[k] = __ffma2_rn(bx, c2, oa);  // CR(i, r): .HAS from step 2, .NO from step 1
+                qR[k] = __ffma2_rn(bx, a, oc);   // CL(j, r + 1) stored (NO, HAS): .NO from step 2, .HAS from step 1
+            }
+        }
+        blk_sync<NT>();
+    }
+
+    // ---------------- outputs: alpha * beta, self-check, copy out ----------------
+    for (int h = warp; h < Nb; h += NW)
+        for (int c = lane; c < Nb; c += 32) {
+            if (c == h) continue;
+            const float2 a = I[h * S + c], bt = gI[h * S + c];
+            gI[h * S + c] = make_float2(a.x == 0.f ? 0.f : a.x * bt.x, a.y == 0.f ? 0.f : a.y * bt.y);
+        }
+    blk_sync<NT>();
+    bool good = true;
+    for (int c = 1 + tid; c < Nb; c += NT) {  // every word has exactly one head: its arc marginals sum to gZ
+        float t = 0.f;
+        for (int h = 0; h < Nb; ++h)
+            if (h != c) { const float2 v = gI[h * S + c]; t += v.x + v.y; }
+        if (!(fabsf(t - gz) <= 1e-3f * fabsf(gz) + 1e-30f)) good = false;
+    }
+    if (!blk_all<NT>(good)) return false;
+    if (tid == 0) p.Z[b] = zres + mu[Nb];
+    if (p.gattach) {
+        float2 *ga = reinterpret_cast<float2 *>(p.gattach + (size_t)b * N * N * 2);
+        for (int h = warp; h < N; h += NW)
+            for (int c = lane; c < N; c += 32) {
+                float2 v = make_float2(0.f, 0.f);
+                if (h < Nb && c < Nb && h != c) v = gI[h * S + c];
+                ga[(size_t)h * N + c] = v;
+            }
+    }
+    if (p.gdec) {
+        float *gd = p.gdec + (size_t)b * N * 8;
+        for (int t = tid; t < N * 2; t += NT) {
+            const int i = t >> 1, dir = t & 1;
+            float2 go = make_float2(0.f, 0.f), stop = make_float2(0.f, 0.f);
+            if (i < Nb) {
+                if (dir == 0) {
+                    for (int c = 0; c < i; ++c) { const float2 v = gI[i * S + c]; go.x += v.x; go.y += v.y; }
+                    const float2 a = C[i * S + i], bt = gC[i * S + i];  // (NO, HAS)
+                    stop = make_float2(a.y * bt.y, a.x * bt.x);
+                } else {
+                    for (int c = i + 1; c < Nb; ++c) { const float2 v = gI[i * S + c]; go.x += v.x; go.y += v.y; }
+                    const float2 a = C[i * S + i + 1], bt = gC[i * S + i + 1];
+                    stop = make_float2(a.x * bt.x, a.y * bt.y);
+                }
+            }
+            *reinterpret_cast<float4 *>(gd + i * 8 + dir * 4) = make_float4(go.x, stop.x, go.y, stop.y);  // [dir][val][decision]
+        }
+    }
+    blk_sync<NT>();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // max semiring: Viterbi chart with first-max back-pointers + breadth-first back-trace
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void amax(float &v, int &a, float t, int idx) {
@@ -422,52 +687,63 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *smem, 
     if (p.heads) for (int t = tid; t < N; t += NT) p.heads[(size_t)b * N + t] = 0;
     blk_sync<NT>();
 
+    // Fused width step (as in lin_pass): the lanes of span (i, j) stream a in [0, w-1) once and fold, in the same loop,
+    // the terms of X(a), of CL with split a + 1 and of CR with split a; the remaining X term (a = w-1) and the two
+    // same-span terms are folded after the single shuffle merge.  First-maximum rule (torch.max returns the smallest
+    // maximal index, semirings.py:200-202): strict > inside a lane's increasing chunk, (value, smaller index) across
+    // lanes, CL's split 0 wins ties (>=), CR's split w-1 and X's a = w-1 lose them (>).
 #pragma unroll 1
     for (int w = 1; w <= len; ++w) {
         const int n = Nb - w;
         const int lg = pick_lg<NT>(n, w);
-        const Unit u = make_unit<NT>(lane, lg, w);
+        const Unit u = make_unit<NT>(lane, lg, w - 1);
 #pragma unroll 1
         for (int base = warp * u.spw; base < n; base += NW * u.spw) {
             const int i = base + u.il;
             const bool valid = i < n;
             const int ic = valid ? i : n - 1, j = ic + w;
             const float2 *pL = C + ic * S1 + 1 + u.a0, *pR = C + j * S + ic + 1 + u.a0;
-            float vxr = NEG_BIG, vxl = NEG_BIG;
-            int axr = 255, axl = 255;
-#pragma unroll 4
-            for (int k = 0; k < u.cnt; ++k) {
-                const float2 t = __fadd2_rn(pL[k], pR[k]);  // (XR term, XL term)
-                amax(vxr, axr, t.x, u.a0 + k);
-                amax(vxl, axl, t.y, u.a0 + k);
-            }
-            for (int o = 16; o >= u.spw; o >>= 1) { amerge(vxr, axr, o); amerge(vxl, axl, o); }
-            if (valid && u.q == 0) {
-                float2 *il = I + j * S + ic, *ir = I + ic * S + j;
-                const float2 al = *il, ar = *ir;
-                *il = make_float2(__fadd_rn(vxl, al.x), __fadd_rn(vxl, al.y));
-                *ir = make_float2(__fadd_rn(vxr, ar.x), __fadd_rn(vxr, ar.y));
-                BX[j * S + ic] = (uint8_t)axl;
-                BX[ic * S + j] = (uint8_t)axr;
-            }
-            __syncwarp();
-            const float *tL = Ct + ic * S1 + 1 + u.a0;
-            const float2 *iL = I + j * S + ic + u.a0, *iR = I + ic * S1 + 1 + u.a0;
+            const float *tL = Ct + ic * S1 + 2 + u.a0;
+            const float2 *iL = I + j * S + ic + 1 + u.a0, *iR = I + ic * S1 + 1 + u.a0;
             const float *tR = Ct + j * S + ic + 1 + u.a0;
-            float vl0 = NEG_BIG, vl1 = NEG_BIG, vr0 = NEG_BIG, vr1 = NEG_BIG;
-            int al0 = 255, al1 = 255, ar0 = 255, ar1 = 255;
+            float vxr = NEG_BIG, vxl = NEG_BIG, vl0 = NEG_BIG, vl1 = NEG_BIG, vr0 = NEG_BIG, vr1 = NEG_BIG;
+            int axr = 255, axl = 255, al0 = 255, al1 = 255, ar0 = 255, ar1 = 255;
 #pragma unroll 4
             for (int k = 0; k < u.cnt; ++k) {
+                const int a = u.a0 + k;
+                const float2 t = __fadd2_rn(pL[k], pR[k]);  // (XR term, XL term), split a
+                amax(vxr, axr, t.x, a);
+                amax(vxl, axl, t.y, a);
                 const float l3 = tL[k], r4 = tR[k];
                 const float2 i3 = iL[k], i4 = iR[k];
-                amax(vl0, al0, __fadd_rn(l3, i3.x), u.a0 + k);
-                amax(vl1, al1, __fadd_rn(l3, i3.y), u.a0 + k);
-                amax(vr0, ar0, __fadd_rn(i4.x, r4), u.a0 + k);
-                amax(vr1, ar1, __fadd_rn(i4.y, r4), u.a0 + k);
+                amax(vl0, al0, __fadd_rn(l3, i3.x), a + 1);  // step 3, split a + 1
+                amax(vl1, al1, __fadd_rn(l3, i3.y), a + 1);
+                amax(vr0, ar0, __fadd_rn(i4.x, r4), a);      // step 4, split a
+                amax(vr1, ar1, __fadd_rn(i4.y, r4), a);
             }
-            for (int o = 16; o >= u.spw; o >>= 1) { amerge(vl0, al0, o); amerge(vl1, al1, o); amerge(vr0, ar0, o); amerge(vr1, ar1, o); }
+            for (int o = 16; o >= u.spw; o >>= 1) {
+                amerge(vxr, axr, o); amerge(vxl, axl, o);
+                amerge(vl0, al0, o); amerge(vl1, al1, o); amerge(vr0, ar0, o); amerge(vr1, ar1, o);
+            }
             if (valid && u.q == 0) {
+                const float2 t = __fadd2_rn(C[ic * S + ic + w], C[j * S + j]);  // X term a = w - 1: the largest split
+                amax(vxr, axr, t.x, w - 1);
+                amax(vxl, axl, t.y, w - 1);
+                float2 *pil = I + j * S + ic, *pir = I + ic * S + j;
+                const float2 al = *pil, ar = *pir;
+                const float2 il = make_float2(__fadd_rn(vxl, al.x), __fadd_rn(vxl, al.y));
+                const float2 ir = make_float2(__fadd_rn(vxr, ar.x), __fadd_rn(vxr, ar.y));
+                const float l0 = Ct[ic * S1 + 1], r0 = Ct[j * S + j];  // CL(i,i).NO, CR(j,j).NO
+                float t0 = __fadd_rn(l0, il.x), t1 = __fadd_rn(l0, il.y);   // step 3, split 0: first index
+                if (t0 >= vl0) { vl0 = t0; al0 = 0; }
+                if (t1 >= vl1) { vl1 = t1; al1 = 0; }
+                t0 = __fadd_rn(ir.x, r0); t1 = __fadd_rn(ir.y, r0);         // step 4, split w - 1: last index
+                amax(vr0, ar0, t0, w - 1);
+                amax(vr1, ar1, t1, w - 1);
                 if (ic == 0 && w != len) { vr0 = p.mask_zero; vr1 = p.mask_zero; }
+                *pil = il; *pir = ir;
+                BX[j * S + ic] = (uint8_t)axl;
+                BX[ic * S + j] = (uint8_t)axr;
                 C[j * S + ic] = make_float2(vl1, vl0);
                 C[ic * S + j + 1] = make_float2(vr0, vr1);
                 Ct[ic * S + j + 1] = vl1;
@@ -562,15 +838,19 @@ __global__ void __launch_bounds__(NT * WPC, MINB) dmv_gather_kernel(DmvArgs p, i
     const int sub = NT == 32 ? (int)(threadIdx.x >> 5) : 0;
     const int tid = NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     unsigned char *slice = smem_raw + (size_t)sub * slice_bytes;
-    const int total = p.B * p.npass;
-    for (int item = blockIdx.x * WPC + sub; item < total; item += gridDim.x * WPC) {
+    // work items = (sentence, semiring), log items first (they cost about twice a max item)
+    const int total = p.B * p.npass, step = gridDim.x * WPC;
+    for (int item = blockIdx.x * WPC + sub; item < total; item += step) {
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }
         const int len = clamp_len(p, b);
         if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
-        if (which == 0) log_pass<NT>(p, b, len, slice, tid);
-        else max_pass<NT>(p, b, len, slice, tid);
+        if (which == 0) {
+            if (p.log_domain || !lin_pass<NT>(p, b, len, slice, tid)) log_pass<NT>(p, b, len, slice, tid);
+        } else {
+            max_pass<NT>(p, b, len, slice, tid);
+        }
     }
 }
 
@@ -607,9 +887,9 @@ cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int s
         kern<<<grid, nt * wpc, smem, st>>>(a, (int)slice);
         return cudaGetLastError();
     };
-    if (threads <= 32) return go(dmv_gather_kernel<32, 4, 1>, 32, 4);
-    if (threads <= 64) return go(dmv_gather_kernel<64, 1, 1>, 64, 1);
-    if (threads <= 128) return go(dmv_gather_kernel<128, 1, 1>, 128, 1);
+    if (threads <= 32) return go(dmv_gather_kernel<32, 4, 3>, 32, 4);
+    if (threads <= 64) return go(dmv_gather_kernel<64, 1, 6>, 64, 1);
+    if (threads <= 128) return go(dmv_gather_kernel<128, 1, 3>, 128, 1);
     return go(dmv_gather_kernel<256, 1, 1>, 256, 1);
 }
 

@@ -32,6 +32,8 @@ struct DmvArgs {
     int nb_lo, nb_hi;  // this launch handles sentences with nb_lo <= len + 1 <= nb_hi (length buckets)
     int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
+    int no_offsets;    // debug: log-semiring sweeps on the raw scores (no per-word offsets)
+    int log_domain;    // gather schedule: 1 = force the log-domain sweep (default: linear domain with log-domain fallback)
     // frontier kernel, both passes in one launch, inputs in pinned HOST memory: the log CTA of a sentence republishes
     // what it staged (dec, arc scores) in device memory and the max CTA of the same sentence takes it from there, so
     // every input byte crosses PCIe once.  share_flag[b] == share_epoch once sentence b is published.

@@ -136,7 +136,7 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, cudaStream_
     // The gather schedule (dmv_gather.cu) runs on request only: the frontier schedule is the faster one in every regime
     // measured so far; it also keeps the zero-copy hand-off and the charts beyond shared memory.
     if (sched == 2 && !a.share && dmv_gather_fits(cap, passes, g_smem_optin)) {
-        int gt = cap <= 20 ? 32 : (cap <= 48 ? 64 : (cap <= 60 ? 128 : 256));
+        int gt = cap <= 20 ? 32 : (cap <= 28 ? 64 : (cap <= 60 ? 128 : 256));
         if (env_gt > 0) gt = env_gt;
         DmvArgs f = a;
         f.workspace = nullptr; f.ws_stride = 0;
@@ -172,6 +172,9 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     a.nsm = g_sm_count;
     a.nb_lo = 0; a.nb_hi = a.N;
+    static const int env_no_off = env_int("VLGAE_DMV_NO_OFFSETS", 0), env_logdom = env_int("VLGAE_GATHER_LOG_DOMAIN", 0);
+    a.no_offsets = env_no_off;
+    a.log_domain = env_logdom;
     // Throughput regime (more work items than one resident wave at the padded length): one launch per length bucket,
     // shared memory sized for the bucket, so short sentences run at 10-20 CTAs per SM instead of the 3 a 40-word
     // chart allows.  Sentences outside a launch's bucket are skipped by its CTAs (no host knowledge of the lengths,
