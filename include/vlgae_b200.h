@@ -192,6 +192,37 @@ int vlgae_align_max_over_factors(const float *vis_feat, const unsigned char *vis
                                  const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill,
                                  int split, float *maxv, int *argv, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Fused grounding consumers: everything the reference's loss and decode read from attmap, without
+ * the [B][A][Q][V] tensor.
+ *
+ * vlgae_align_maxima: BOTH maxima in one pass of the tcgen05 kernel.
+ *   maxv[b][a][q] / argv  = attmap.max("V")   (joint.py:473 loss txt2vis, :520 decode)        as vlgae_align_max_over_factors
+ *   maxq[b][a][v] / argq  = attmap.max("Q")   (joint.py:480 loss vis2txt)                     needs Q <= 128; either may be NULL
+ *   masks as in vlgae_align_logits (a masked entry is neg_fill); arg = smallest attaining index (torch.max).
+ *   workspace: vlgae_align_reduce_workspace_bytes.
+ * vlgae_align_diagonal: the diagonal slab attmap[b, b] -> out [B][Q][V] (A = B; joint.py:466-469, 522-524), exact fp32.
+ * vlgae_grounding_ce (A = B): out2[0] = -sum_{b,q} log_softmax_A(maxv)[b,b,q] * txt_marginal[b,q]   (joint.py:476-477)
+ *                             out2[1] = -sum_{a,v} log_softmax_B(maxq)[a,a,v] * vis_mask[a,v]       (joint.py:481-483)
+ *   (maxq NULL: only out2[0]).  The caller patches the POS prior into the diagonals of maxv / maxq first (joint.py:446-470).
+ * vlgae_topk_rows: idx[row][0..k) = indices of the k <= 8 largest entries of x[row][0..V), descending, smaller index first
+ *   on ties (match_logit.argsort(-1, descending=True)[..., :5], joint.py:594).
+ * vlgae_align_max_over_factors_backward: backward of maxv through the contraction (torch routes the gradient of
+ *   attmap.max to the arg-max entry): grad_txt[b,q,:] = sum_a g[b,a,q] vis[a,argv,:], grad_vis[a,argv,:] += g[b,a,q] txt[b,q,:],
+ *   nothing where the arg-max entry is masked.  Either output may be NULL.  D <= 128.
+ */
+int vlgae_align_maxima(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                       const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
+                       float *maxv, int *argv, float *maxq, int *argq, void *workspace, size_t workspace_bytes, void *stream);
+int vlgae_align_diagonal(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                         const unsigned char *txt_mask, int B, int V, int Q, int D, float neg_fill, float *out, void *stream);
+int vlgae_grounding_ce(const float *maxv, const float *maxq, const float *txt_marginal, const unsigned char *vis_mask, int B,
+                       int Q, int V, float *out2, void *stream);
+int vlgae_topk_rows(const float *x, long long rows, int V, int k, int *idx, void *stream);
+int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *argv, const float *vis_feat,
+                                          const unsigned char *vis_mask, const float *txt_feat, const unsigned char *txt_mask,
+                                          int A, int V, int B, int Q, int D, float *grad_vis, float *grad_txt, void *stream);
+
 /* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
 int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);
 

@@ -198,6 +198,33 @@ def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, n
     return (maxatt * tm[:, None, :]).sum(-1) / tm.sum(1, keepdims=True)
 
 
+def loss_grounding_factor_ce(attmap, txt_marginal, vis_mask, prior=None, vis2txt=True):
+    """The two cross-entropy sums of ``loss_grounding_factor_ce`` (joint.py:439-491) in float64 numpy:
+    ``txt2vis = -sum(diag(log_softmax_A(attmap.max(V))) * txt_marginal)`` (:473-477) and
+    ``vis2txt = -sum(diag(log_softmax_B(attmap.max(Q))) * vis_mask)`` (:480-483), after the POS prior
+    ``attmap[b, b, 1:T+1, outside the group] -= mask * 100`` (:446-470).  prior: list of (mask [B,T,1] bool, lo, hi)."""
+    att = np.array(attmap, dtype=np.float64)
+    B = att.shape[0]
+    ar = np.arange(B)
+    for mask, lo, hi in (prior or []):
+        T = mask.shape[1]
+        m = mask.astype(np.float64) * 100
+        att[ar, ar, 1:T + 1, :lo] -= m
+        att[ar, ar, 1:T + 1, hi:] -= m
+
+    def lsm(x, axis):
+        mx = x.max(axis=axis, keepdims=True)
+        return x - mx - np.log(np.exp(x - mx).sum(axis=axis, keepdims=True))
+
+    logit = lsm(att.max(-1), 1)                      # [B, A, Q], softmax over A
+    txt2vis = -(logit[ar, ar] * np.asarray(txt_marginal, dtype=np.float64)).sum()
+    v2t = None
+    if vis2txt:
+        logit = lsm(att.max(2), 0)                   # [B, A, V], softmax over B
+        v2t = -(logit[ar, ar] * np.asarray(vis_mask, dtype=np.float64)).sum()
+    return txt2vis, v2t
+
+
 def word_factor_attention(vis_feat, txt_feat, vis_mid):
     """``softmax_v(<txt[b,q,:], vis[b,v,:]>) @ vis_mid[b]`` (joint.py:668-673; the caller drops ROOT with ``[:, 1:]``
     before and adds the residual + LayerNorm after)."""

@@ -149,6 +149,79 @@ def run_align(name, A, V, B, Q, D, seed):
     print(name, tuple(att.shape))
 
 
+def run_align_loss(name, B, nb, T, D, seed):
+    """loss_grounding_factor_ce (joint.py:439-491) and the head of decode_grounding_on_factor (:518-551, :594), re-typed
+    line for line on attmap from gather_logit_simple above; A = B, V = nb + nb^2 + nb + 1 (obj, rel, attr, img),
+    Q = 2 (T + 1) (words incl. ROOT, then arcs)."""
+    g = torch.Generator().manual_seed(seed)
+    vis_split = [nb, nb * nb, nb, 1]
+    names_f = ["obj", "rel", "attr", "img"]
+    V, Q = sum(vis_split), 2 * (T + 1)
+    vis_feat = torch.randn(B, V, D, generator=g) * 0.5
+    txt_feat = torch.randn(B, Q, D, generator=g) * 0.5
+    vis_mask = torch.rand(B, V, generator=g) > 0.15
+    vis_mask[:, 0] = True
+    lens = torch.randint(2, T + 1, (B,), generator=g)
+    m = torch.arange(T + 1)[None, :] <= lens[:, None]
+    m[:, 0] = False
+    txt_mask = torch.cat([m, m], dim=1)
+    txt_marginal = torch.rand(B, Q, generator=g) * txt_mask
+    pos_mask = {n: torch.rand(B, T, 1, generator=g) > 0.6 for n in ("obj", "rel", "attr")}
+    vis = (vis_feat.refine_names("A", "V", "D"), vis_mask.refine_names("A", "V"), None)
+    txt = (txt_feat.refine_names("B", "Q", "D"), txt_mask.refine_names("B", "Q"), txt_marginal)
+    out = {}
+    for use_prior in (False, True):
+        attmap = gather_logit_simple(vis, txt)
+        # ---- joint.py:446-470
+        if use_prior:
+            names = attmap.names
+            attmap = attmap.rename(None)
+            arange = torch.arange(len(attmap))
+            offset = 0
+            for i, (fname, width) in enumerate(zip(names_f, vis_split)):
+                if fname in pos_mask:
+                    mask = pos_mask[fname]
+                else:
+                    offset += width
+                    continue
+                attmap[arange, arange, 1: mask.shape[1] + 1, :offset] -= mask * 100
+                attmap[arange, arange, 1: mask.shape[1] + 1, offset + width:] -= (mask * 100)
+                offset += width
+            attmap = attmap.refine_names(*names)
+        # ---- joint.py:473-483
+        logit = attmap.max("V").values
+        logit = logit.log_softmax("A")
+        txt2vis = -(logit.rename(None).diagonal().T * txt_marginal).sum()
+        logit = attmap.max("Q").values
+        logit = logit.log_softmax("B")
+        vis2txt = -(logit.rename(None).diagonal().T * vis_mask).sum()
+        k = "prior" if use_prior else "plain"
+        out["txt2vis_" + k], out["vis2txt_" + k] = txt2vis.numpy(), vis2txt.numpy()
+    # ---- decode head, joint.py:518-551 (+ :594)
+    match_logit = gather_logit_simple(vis, txt)
+    factor2img = match_logit.max("V").values.max("A").indices
+    match_logit = match_logit.diagonal().refine_names("Q", "V", "B").align_to("B", "Q", "V").rename(None)
+    out["diag"] = match_logit.clone().numpy()
+    arange = torch.arange(len(match_logit))
+    offset = 0
+    for i, (fname, width) in enumerate(zip(names_f, vis_split)):
+        if fname in pos_mask:
+            mask = pos_mask[fname]
+        else:
+            offset += width
+            continue
+        match_logit[arange, 1: mask.shape[1] + 1, :offset] -= 1e10 * mask
+        match_logit[arange, 1: mask.shape[1] + 1, offset + width:] -= (1e10 * mask)
+        offset += width
+    top5 = match_logit.argsort(-1, descending=True)[..., :5]
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), vis_feat=vis_feat.numpy(), vis_mask=vis_mask.numpy(), txt_feat=txt_feat.numpy(),
+        txt_mask=txt_mask.numpy(), txt_marginal=txt_marginal.numpy(), vis_split=np.array(vis_split),
+        pos_obj=pos_mask["obj"].numpy(), pos_rel=pos_mask["rel"].numpy(), pos_attr=pos_mask["attr"].numpy(),
+        factor2img=factor2img.rename(None).numpy(), decode_logit=match_logit.numpy(), top5=top5.numpy(), **out)
+    print(name, "B", B, "V", V, "Q", Q, {k: float(v) for k, v in out.items() if k != "diag"})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -198,6 +271,7 @@ def main():
     # alignment
     run_align("align_small", A=3, V=11, B=4, Q=10, D=16, seed=21)
     run_align("align_mid", A=5, V=150, B=6, Q=18, D=128, seed=22)
+    run_align_loss("align_loss", B=6, nb=7, T=9, D=64, seed=23)
 
 
 if __name__ == "__main__":

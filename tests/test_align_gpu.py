@@ -235,3 +235,102 @@ def test_inplace_write_into_attmap_then_backward(dev, pad):
     got, want = att.detach().cpu().numpy(), ref.detach().cpu().numpy()
     masked = ~keep.expand(B, A, Q, V).cpu().numpy()
     assert np.abs(got - want)[~masked].max() < 1e-2 and (got[masked] <= -1e19).all()
+
+
+# ---- fused grounding consumers ------------------------------------------------------------------
+def _loss_inputs(g, dev):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    off = np.concatenate([[0], np.cumsum(g["vis_split"])])
+    prior = [(t(g["pos_obj"]), int(off[0]), int(off[1])), (t(g["pos_rel"]), int(off[1]), int(off[2])),
+             (t(g["pos_attr"]), int(off[2]), int(off[3]))]
+    return t(g["vis_feat"]), t(g["vis_mask"]), t(g["txt_feat"]), t(g["txt_mask"]), t(g["txt_marginal"]), prior
+
+
+@pytest.mark.parametrize("A,V,B,Q,D", [(3, 150, 4, 20, 64), (5, 1369, 6, 82, 128), (2, 129, 2, 128, 32), (4, 40, 3, 5, 8)])
+def test_fused_maxima_bit_identical(dev, A, V, B, Q, D):
+    """Both maxima of one pass (vlgae_align_maxima) equal torch.max of the materialised logits bit for bit, arg-max =
+    smallest attaining index, incl. fully masked rows / columns."""
+    from vlgae_b200.alignment import fused_maxima, gather_logit_simple
+
+    g_ = torch.Generator(device=dev).manual_seed(V + Q)
+    vis = torch.randn(A, V, D, generator=g_, device=dev)
+    txt = torch.randn(B, Q, D, generator=g_, device=dev)
+    vm = torch.rand(A, V, generator=g_, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g_, device=dev) > 0.2
+    vm[0, :] = False       # an image with every factor masked
+    tm[B - 1, :] = False   # a caption with every query masked
+    att = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=False)
+    maxv, argv, maxq, argq = fused_maxima(vis, vm, txt, tm)
+    torch.cuda.synchronize()
+    rv, rq = att.max(-1), att.max(2)
+    assert torch.equal(maxv, rv.values) and torch.equal(maxq, rq.values)
+    # first maximal index (torch.max on CUDA may return any index on exact ties; compare through the values it points to)
+    assert torch.equal(att.gather(-1, argv.long().unsqueeze(-1)).squeeze(-1), rv.values)
+    assert torch.equal(att.gather(2, argq.long().unsqueeze(2)).squeeze(2), rq.values)
+    first_v = (att == rv.values.unsqueeze(-1)).float().argmax(-1)
+    first_q = (att == rq.values.unsqueeze(2)).float().argmax(2)
+    assert torch.equal(argv.long(), first_v) and torch.equal(argq.long(), first_q)
+
+
+def test_diagonal_slab_and_topk(golden, dev):
+    from vlgae_b200.alignment import diagonal_slab, topk_rows
+
+    g = golden("align_loss")
+    vis, vm, txt, tm, _, _ = _loss_inputs(g, dev)
+    diag = diagonal_slab(vis, vm, txt, tm)
+    got, want = diag.cpu().numpy(), g["diag"]
+    masked = want <= -1e19
+    assert ((got <= -1e19) == masked).all()
+    np.testing.assert_allclose(got[~masked], want[~masked], rtol=1e-5, atol=1e-5)
+    # top 5 of the decode logits (joint.py:594) on the reference's own tensor: same sets, same order where values differ
+    dl = torch.from_numpy(g["decode_logit"]).to(dev)
+    top = topk_rows(dl, 5).cpu().numpy()
+    vals = np.take_along_axis(g["decode_logit"], top, -1)
+    want_vals = np.take_along_axis(g["decode_logit"], g["top5"], -1)
+    np.testing.assert_array_equal(vals, want_vals)
+    assert (np.diff(vals, axis=-1) <= 0).all()
+    x = torch.tensor([[1.0, 3.0, 3.0, 2.0, 3.0, 0.0]], device=dev)
+    assert topk_rows(x, 5).tolist() == [[1, 2, 4, 3, 0]]   # ties: smaller index first
+
+
+@pytest.mark.parametrize("use_prior", [False, True])
+def test_fused_grounding_loss_matches_reference(golden, dev, use_prior):
+    """loss_grounding_factor_ce through the fused consumers (no [B, A, Q, V] tensor) against the reference's own lines."""
+    from vlgae_b200.alignment import FusedMatch, grounding_loss_fused
+
+    g = golden("align_loss")
+    vis, vm, txt, tm, marg, prior = _loss_inputs(g, dev)
+    match = FusedMatch(vis, vm, txt, tm)
+    total, loss, (t2v, v2t) = grounding_loss_fused(match, marg, vm, 37, prior=prior if use_prior else None, vis2txt=1.0)
+    k = "prior" if use_prior else "plain"
+    np.testing.assert_allclose(float(t2v), float(g["txt2vis_" + k]), rtol=2e-4)
+    np.testing.assert_allclose(float(v2t), float(g["vis2txt_" + k]), rtol=2e-4)
+    np.testing.assert_allclose(float(total), 2 * 37, rtol=1e-5)   # each term is self-normalised to num_token (:477-483)
+    # decode accesses of the UNMODIFIED reference method (joint.py:520-524)
+    factor2img = match.max("V").values.max("A").indices
+    np.testing.assert_array_equal(factor2img.rename(None).cpu().numpy(), g["factor2img"])
+    d = match.diagonal().refine_names("Q", "V", "B").align_to("B", "Q", "V").rename(None)
+    assert d.shape == g["diag"].shape
+
+
+def test_max_over_factors_backward_kernel(dev):
+    """gather_logit_reduced's backward (kernel, vlgae_align_max_over_factors_backward) against autograd through the
+    reference formula in fp64."""
+    from vlgae_b200.alignment import gather_logit_reduced
+
+    g_ = torch.Generator(device=dev).manual_seed(3)
+    A, V, B, Q, D = 4, 70, 5, 12, 48
+    vis = torch.randn(A, V, D, generator=g_, device=dev).requires_grad_()
+    txt = torch.randn(B, Q, D, generator=g_, device=dev).requires_grad_()
+    vm = torch.rand(A, V, generator=g_, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g_, device=dev) > 0.2
+    marg = torch.rand(B, Q, generator=g_, device=dev) * tm
+    w = torch.randn(B, A, generator=g_, device=dev)
+    (gather_logit_reduced(vis, vm, txt, tm, marg) * w).sum().backward()
+    vis2, txt2 = vis.detach().double().requires_grad_(), txt.detach().double().requires_grad_()
+    att = torch.einsum("avd,bqd->baqv", vis2, txt2)
+    att = att.masked_fill(~vm[None, :, None, :], -1e20).masked_fill(~tm[:, None, :, None], -1e20)
+    ref = (att.max(-1).values * marg.double().unsqueeze(1)).sum(-1) / marg.double().sum(1, keepdim=True)
+    (ref * w.double()).sum().backward()
+    assert float((vis.grad.double() - vis2.grad).abs().max()) < 1e-4
+    assert float((txt.grad.double() - txt2.grad).abs().max()) < 1e-4

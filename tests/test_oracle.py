@@ -152,3 +152,16 @@ def test_alignment_matches_reference(golden, name):
     assert ((att == -1e20) == (g["attmap"] == -1e20)).all()
     red = oracle.gather_logit_reduced(g["vis_feat"], g["vis_mask"], g["txt_feat"], g["txt_mask"], g["txt_marginal"])
     np.testing.assert_allclose(red, g["reduced"], rtol=1e-4, atol=1e-4)
+
+
+def test_grounding_loss_restatement(golden):
+    """oracle.loss_grounding_factor_ce against the reference's loss lines (joint.py:439-491, re-typed in gen_golden.py),
+    without and with the POS prior."""
+    g = golden("align_loss")
+    att = oracle.gather_logit_simple(g["vis_feat"], g["vis_mask"], g["txt_feat"], g["txt_mask"])
+    off = np.concatenate([[0], np.cumsum(g["vis_split"])])
+    prior = [(g["pos_obj"], off[0], off[1]), (g["pos_rel"], off[1], off[2]), (g["pos_attr"], off[2], off[3])]
+    t2v, v2t = oracle.loss_grounding_factor_ce(att, g["txt_marginal"], g["vis_mask"])
+    np.testing.assert_allclose([t2v, v2t], [g["txt2vis_plain"], g["vis2txt_plain"]], rtol=1e-5)
+    t2v, v2t = oracle.loss_grounding_factor_ce(att, g["txt_marginal"], g["vis_mask"], prior)
+    np.testing.assert_allclose([t2v, v2t], [g["txt2vis_prior"], g["vis2txt_prior"]], rtol=1e-5)

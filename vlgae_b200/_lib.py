@@ -41,6 +41,14 @@ PROTOTYPES = {
     "vlgae_align_reduce_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vlgae_align_max_over_factors": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                              c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlgae_align_maxima": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlgae_align_diagonal": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                     c_void_p]),
+    "vlgae_grounding_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vlgae_topk_rows": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "vlgae_align_max_over_factors_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vlgae_scale_rows": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "vlgae_microbench_mufu": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "vlgae_microbench_fp32": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),

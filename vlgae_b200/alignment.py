@@ -183,19 +183,22 @@ class _MaxOverFactors(torch.autograd.Function):
         vis, txt, vm, tm, argv = ctx.saved_tensors
         B, A, Q = g.shape
         V, D = vis.shape[1], vis.shape[2]
-        arg = argv.long()
-        a_idx = torch.arange(A, device=g.device).view(1, A, 1).expand(B, A, Q)
-        keep = vm.bool()[a_idx, arg] & tm.bool().view(B, 1, Q)
-        g = (g * keep).to(torch.float32)
-        gv = gt = None
-        if ctx.needs_input_grad[1]:
-            sel = vis.to(torch.float32)[a_idx, arg]                       # [B, A, Q, D]
-            gt = torch.einsum("baq,baqd->bqd", g, sel).to(txt.dtype)
-        if ctx.needs_input_grad[0]:
-            src = (g.unsqueeze(-1) * txt.to(torch.float32).unsqueeze(1)).reshape(-1, D)   # [B*A*Q, D]
-            flat = (a_idx * V + arg).reshape(-1)
-            gv = torch.zeros(A * V, D, dtype=torch.float32, device=g.device).index_add_(0, flat, src)
-            gv = gv.view(A, V, D).to(vis.dtype)
+        dev = g.device
+        vf, tf = vis.to(torch.float32).contiguous(), txt.to(torch.float32).contiguous()
+        vmu = vm.to(torch.bool).contiguous().view(torch.uint8)
+        tmu = tm.to(torch.bool).contiguous().view(torch.uint8)
+        g = g.to(torch.float32).contiguous()
+        gv = torch.empty((A, V, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        gt = torch.empty((B, Q, D), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dev):
+            check(lib().vlgae_align_max_over_factors_backward(
+                g.data_ptr(), argv.data_ptr(), vf.data_ptr(), vmu.data_ptr(), tf.data_ptr(), tmu.data_ptr(), A, V, B, Q, D,
+                gv.data_ptr() if gv is not None else None, gt.data_ptr() if gt is not None else None,
+                torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_max_over_factors_backward")
+        if gv is not None:
+            gv = gv.to(vis.dtype)
+        if gt is not None:
+            gt = gt.to(txt.dtype)
         return gv, gt, None, None, None, None
 
 
@@ -207,6 +210,148 @@ def gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal, *
     maxatt, _ = _MaxOverFactors.apply(vis_feat, txt_feat, vis_mask, txt_mask, split, -INF)
     tm = _plain(txt_marginal)
     return torch.sum(maxatt * tm.unsqueeze(1), dim=-1) / tm.sum(1, keepdim=True)
+
+
+# ---- fused grounding consumers: loss and decode without the [B, A, Q, V] tensor ------------------
+def _prep4(vis_feat, vis_mask, txt_feat, txt_mask):
+    vf, vm, tf, tm = map(_plain, (vis_feat, vis_mask, txt_feat, txt_mask))
+    dev = vf.device
+    if dev.type != "cuda":
+        raise VlgaeError("vlgae_b200.alignment needs CUDA tensors (there is no CPU fallback)")
+    A, V, D = vf.shape
+    B, Q, D2 = tf.shape
+    if D != D2 or tuple(vm.shape) != (A, V) or tuple(tm.shape) != (B, Q):
+        raise VlgaeError("gather_logit: vis [A,V,D], vis_mask [A,V], txt [B,Q,D], txt_mask [B,Q] expected")
+    vf = vf.detach().to(torch.float32).contiguous()
+    tf = tf.detach().to(torch.float32).contiguous()
+    vm = vm.to(torch.bool).contiguous().view(torch.uint8)
+    tm = tm.to(torch.bool).contiguous().view(torch.uint8)
+    return dev, A, V, B, Q, D, vf, vm, tf, tm
+
+
+def fused_maxima(vis_feat, vis_mask, txt_feat, txt_mask, *, split=3, neg=-INF):
+    """(maxv [B,A,Q], argv, maxq [B,A,V], argq): ``attmap.max("V")`` and ``attmap.max("Q")`` (joint.py:473, 480, 520) in ONE
+    pass of the tcgen05 kernel (vlgae_align_maxima); values bit-identical to the maxima of the materialised logits."""
+    dev, A, V, B, Q, D, vf, vm, tf, tm = _prep4(vis_feat, vis_mask, txt_feat, txt_mask)
+    maxv = torch.empty((B, A, Q), dtype=torch.float32, device=dev)
+    argv = torch.empty((B, A, Q), dtype=torch.int32, device=dev)
+    maxq = torch.empty((B, A, V), dtype=torch.float32, device=dev)
+    argq = torch.empty((B, A, V), dtype=torch.int32, device=dev)
+    ws = _workspace(dev, max(lib().vlgae_align_reduce_workspace_bytes(A, V, B, Q, D), 1))
+    with torch.cuda.device(dev):
+        check(lib().vlgae_align_maxima(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), A, V, B, Q, D, float(neg),
+                                       int(split), maxv.data_ptr(), argv.data_ptr(), maxq.data_ptr(), argq.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream),
+              "vlgae_align_maxima")
+    return maxv, argv, maxq, argq
+
+
+def diagonal_slab(vis_feat, vis_mask, txt_feat, txt_mask, *, neg=-INF):
+    """attmap[b, b] for every caption -> [B, Q, V] (exact fp32; joint.py:466-469, 522-524).  Needs A == B."""
+    dev, A, V, B, Q, D, vf, vm, tf, tm = _prep4(vis_feat, vis_mask, txt_feat, txt_mask)
+    if A != B:
+        raise VlgaeError("diagonal_slab: one image per caption expected (A == B)")
+    out = torch.empty((B, Q, V), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().vlgae_align_diagonal(vf.data_ptr(), vm.data_ptr(), tf.data_ptr(), tm.data_ptr(), B, V, Q, D, float(neg),
+                                         out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_diagonal")
+    return out
+
+
+def grounding_ce(maxv, maxq, txt_marginal, vis_mask):
+    """(txt2vis, vis2txt) of loss_grounding_factor_ce (joint.py:473-483) from the two maxima; vis2txt is None without maxq."""
+    dev = maxv.device
+    B, A, Q = maxv.shape
+    if A != B:
+        raise VlgaeError("grounding_ce: A == B expected")
+    maxv = maxv.to(torch.float32).contiguous()
+    marg = _plain(txt_marginal).to(device=dev, dtype=torch.float32).contiguous()
+    V = 0
+    vm = None
+    if maxq is not None:
+        maxq = maxq.to(torch.float32).contiguous()
+        V = maxq.shape[2]
+        vm = _plain(vis_mask).to(torch.bool).contiguous().view(torch.uint8)
+    out2 = torch.empty(2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().vlgae_grounding_ce(maxv.data_ptr(), maxq.data_ptr() if maxq is not None else None, marg.data_ptr(),
+                                       vm.data_ptr() if vm is not None else None, B, Q, V, out2.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream), "vlgae_grounding_ce")
+    return out2[0], (out2[1] if maxq is not None else None)
+
+
+def topk_rows(x, k=5):
+    """Indices of the k largest entries along the last dim, descending (``x.argsort(-1, descending=True)[..., :k]``,
+    joint.py:594); ties: smaller index first."""
+    if x.device.type != "cuda":
+        raise VlgaeError("vlgae_b200.alignment needs CUDA tensors (there is no CPU fallback)")
+    x = x.to(torch.float32).contiguous()
+    V = x.shape[-1]
+    rows = x.numel() // max(V, 1)
+    idx = torch.empty(x.shape[:-1] + (k,), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().vlgae_topk_rows(x.data_ptr(), rows, V, k, idx.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream),
+              "vlgae_topk_rows")
+    return idx.long()
+
+
+class _Max:
+    def __init__(self, values, indices):
+        self.values, self.indices = values, indices
+
+
+class FusedMatch:
+    """What ``inputs["match_logit"]`` holds under ``gather_logit_mode: b200_fused``: the two maxima and the diagonal slab
+    instead of the [B, A, Q, V] tensor.  It answers the three accesses the reference's ``decode_grounding_on_factor``
+    makes (joint.py:520-524) -- ``.max("V")``, ``.max("Q")`` and ``.diagonal()`` -- so that method runs on it UNMODIFIED;
+    ``loss_grounding_factor_ce_fused_impl`` is the matching loss.  Forward only (validation / test / bulk decode): training
+    keeps the materialised, differentiable ``gather_logit_mode: b200``."""
+
+    names = ("B", "A", "Q", "V")
+
+    def __init__(self, vis_feat, vis_mask, txt_feat, txt_mask):
+        self.maxv, self.argv, self.maxq, self.argq = fused_maxima(vis_feat, vis_mask, txt_feat, txt_mask)
+        self.diag = diagonal_slab(vis_feat, vis_mask, txt_feat, txt_mask)
+        B, A, Q = self.maxv.shape
+        self.shape = (B, A, Q, self.maxq.shape[2])
+
+    def max(self, dim):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if dim in ("V", -1, 3):
+                return _Max(self.maxv.refine_names("B", "A", "Q"), self.argv.long().refine_names("B", "A", "Q"))
+            if dim in ("Q", 2):
+                return _Max(self.maxq.refine_names("B", "A", "V"), self.argq.long().refine_names("B", "A", "V"))
+        raise VlgaeError(f"FusedMatch.max: only the V and Q axes are reduced by the fused kernel, got {dim!r}")
+
+    def diagonal(self):
+        return self.diag.permute(1, 2, 0)  # [Q, V, B], as torch's diagonal() of a [B, A, Q, V] tensor
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def grounding_loss_fused(match, txt_marginal, vis_mask, num_token, *, prior=None, vis2txt=1.0):
+    """The two cross-entropy terms of ``loss_grounding_factor_ce`` (joint.py:439-491) from a FusedMatch.
+    prior: optional list of ``(mask [B, T, 1] bool, lo, hi)``: the POS prior lowers, on the diagonal a = b only, the scores of
+    the words flagged by ``mask`` outside the factor group ``[lo, hi)`` by 100 (joint.py:446-470)."""
+    maxv, maxq = match.maxv, match.maxq
+    if prior:
+        diag = match.diag.clone()
+        for mask, lo, hi in prior:
+            T = mask.shape[1]
+            m = mask.to(diag.dtype) * 100
+            diag[:, 1:T + 1, :lo] -= m
+            diag[:, 1:T + 1, hi:] -= m
+        ar = torch.arange(diag.shape[0], device=diag.device)
+        maxv, maxq = maxv.clone(), maxq.clone()
+        maxv[ar, ar] = diag.max(-1).values   # [B, Q]
+        maxq[ar, ar] = diag.max(1).values    # [B, V]
+    t2v, v2t = grounding_ce(maxv, maxq if vis2txt > 0 else None, txt_marginal, vis_mask)
+    loss = {"txt2vis": t2v / (t2v.detach() + 1e-6) * num_token}
+    if vis2txt > 0:
+        loss["mt_vis2txt"] = vis2txt * v2t / (v2t.detach() + 1e-6) * num_token
+    return sum(loss.values()), loss, (t2v, v2t)
 
 
 def word_factor_attention(vis_feat, txt_feat, vis_mid):
@@ -231,3 +376,30 @@ def gather_logit_reduced_impl(self, inputs, vis, txt, vp):
     vis_feat, vis_mask, _ = vis
     txt_feat, txt_mask, txt_marginal = txt
     return gather_logit_reduced(vis_feat, vis_mask, txt_feat, txt_mask, txt_marginal)
+
+
+def gather_logit_fused_impl(self, inputs, vis, txt, vp):
+    """``gather_logit_mode: b200_fused`` -- the consumers' view of attmap without the tensor (forward only)."""
+    vis_feat, vis_mask, _ = vis
+    txt_feat, txt_mask, _txt_marginal = txt
+    return FusedMatch(vis_feat, vis_mask, txt_feat, txt_mask)
+
+
+def loss_grounding_factor_ce_fused_impl(self, inputs, vp):
+    """``loss_grounding_mode: factor|ce`` on a FusedMatch (mirrors joint.py:439-491, POS prior included)."""
+    match = inputs["match_logit"]
+    _txt_feat, _txt_mask, txt_marginal = inputs["txt_packed"]
+    _vis_feat, vis_mask, vis_split = inputs["vis_packed"]
+    prior = None
+    if self.cfg.loss_grounding_args.use_pos_prior:
+        prior, offset = [], 0
+        pos = {"obj": getattr(self, "pos_for_obj", None), "rel": getattr(self, "pos_for_rel", None),
+               "attr": getattr(self, "pos_for_attr", None)}
+        for name, width in zip(self.vis_factor_names, vis_split):
+            if name in pos:
+                mask = vp.tag.unsqueeze(-1).eq(pos[name]).any(-1, keepdim=True)
+                prior.append((mask, offset, offset + width))
+            offset += width
+    total, loss, _ = grounding_loss_fused(match, txt_marginal, vis_mask, vp.num_token, prior=prior,
+                                          vis2txt=self.cfg.loss_grounding_args.vis2txt)
+    return total, loss

@@ -500,12 +500,46 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                 for (int j = 0; j < 16; ++j) r[k][j] = __float_as_uint(neg);
                         }
                         if constexpr (REDUCE) {
+                            // (optional) max over the QUERIES, the easy direction of this layout: a thread holds one
+                            // factor's scores for its 16-query chunks, so the maximum over q is thread-local; the two
+                            // warps of a quadrant (alternate chunks) merge through one shared-memory slot.  First
+                            // maximum = smallest q (torch.max); masked queries / factors never win (all masked: neg, 0).
+                            float mq = neg;
+                            int aq = 0;
+                            unsigned long long *s_pq = reinterpret_cast<unsigned long long *>(
+                                reinterpret_cast<uint8_t *>(s_run) + p.run_bytes - 2048) + team * TILE_M + quad * 32 + lane;
+                            if (p.maxq) {
+#pragma unroll
+                                for (int k = 0; k < MAXCH; ++k) {
+                                    const int c0 = half * 16 + k * 4 * kEpiWarps;
+                                    const uint32_t w32 = k == 0 ? mb_cur.x : (k == 1 ? mb_cur.y : (k == 2 ? mb_cur.z : mb_cur.w));
+                                    const uint32_t bits = w32 >> (half * 16);
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (c0 + j < q_lim && ((bits >> j) & 1u)) {
+                                            const float x = __uint_as_float(r[k][j]);
+                                            if (x > mq) { mq = x; aq = c0 + j; }
+                                        }
+                                }
+                                if (half == 1) *s_pq = ((unsigned long long)__float_as_uint(mq) << 32) | (unsigned)aq;
+                            }
                             // transpose through the staged tile, then one warp per query row: each lane takes 4
                             // consecutive factors (one LDS.128), REDUX gives the row maximum, the lowest lane that holds
                             // it gives the first arg-max (torch.max's tie rule); v-tiles merge by atomicMax on
                             // (ordered value bits << 32 | ~v), so equal values keep the smaller factor index
                             float *tile_out = s_out + (size_t)team * out_tile_floats;
                             named_bar(1 + team, 32 * kTeamWarps);  // the previous tile's rows have been reduced
+                            if (p.maxq && half == 0) {
+                                const unsigned long long o = *s_pq;
+                                const float m1 = __uint_as_float((uint32_t)(o >> 32));
+                                const int a1 = (int)(uint32_t)o;
+                                if (m1 > mq || (m1 == mq && m1 > neg && a1 < aq)) { mq = m1; aq = a1; }
+                                if (v_ok) {
+                                    const size_t oo = ((size_t)b * p.A + a) * p.V + (size_t)(vt0 + t) * TILE_M + quad * 32 + lane;
+                                    p.maxq[oo] = mq;
+                                    if (p.argq) p.argq[oo] = aq;
+                                }
+                            }
 #pragma unroll
                             for (int k = 0; k < MAXCH; ++k) {
                                 const int c0 = half * 16 + k * 4 * kEpiWarps;
@@ -668,7 +702,8 @@ cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_
 // mode 0 / 1: materialise the logits in `out`; mode 2: reduce over the factors (maxv / argv)
 static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask,
                                      int A, int V, int B, int Q, int D, float neg, int split, float *out, int ldv,
-                                     float *maxv, int *argv, void *workspace, cudaStream_t st) {
+                                     float *maxv, int *argv, void *workspace, cudaStream_t st, float *maxq = nullptr,
+                                     int *argq = nullptr) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
     const AlignPlan pl = align_plan(A, V, B, Q, D);
@@ -687,7 +722,8 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }  // measurement aids, see the kernel
     a.prof = dmv_profile_buffer();
     const bool reduce = maxv != nullptr;
-    a.maxv = maxv; a.argv = argv;
+    a.maxv = maxv; a.argv = argv; a.maxq = maxq; a.argq = argq;
+    if (maxq && pl.QT != 1) return cudaErrorInvalidValue;  // the max over the queries lives inside one query tile
     // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
     { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || ((bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0)); }
     // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
@@ -703,7 +739,7 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
         bch = (B + bmax - 1) / bmax;
         while ((long long)A * bch < 6LL * g_align_sm && bch < B) ++bch;
         b_per = (B + bch - 1) / bch;
-        run_bytes = ((size_t)2 * b_per * Q * 8 + 15) & ~(size_t)15;
+        run_bytes = (((size_t)2 * b_per * Q * 8 + 15) & ~(size_t)15) + 2048;  // + exchange slots of the max over the queries
     }
     const size_t out_tile_bytes = (size_t)out_rows * 512, fixed = sizeof(AlignSmem) + 64 + 512 + run_bytes;
     int out_bufs = a.bulk ? 2 : 0;
@@ -747,6 +783,13 @@ cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const
                                 int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
                                 cudaStream_t st) {
     return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, nullptr, 0, maxv, argv, workspace, st);
+}
+
+cudaError_t launch_align_maxima(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                                int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, float *maxq,
+                                int *argq, void *workspace, cudaStream_t st) {
+    return launch_align_mode(vis, vis_mask, txt, txt_mask, A, V, B, Q, D, neg, split, nullptr, 0, maxv, argv, workspace, st, maxq,
+                             argq);
 }
 
 }  // namespace vlgae

@@ -20,7 +20,9 @@ struct AlignArgs {
     float neg;
     float *maxv;  // MODE 2: [B][A][Q] max over the factors
     int *argv;    // MODE 2: [B][A][Q] first arg-max, or null
-    uint32_t run_bytes;  // MODE 2: shared memory of the running maxima
+    float *maxq;  // MODE 2, optional: [B][A][V] max over the queries (needs Q <= 128: one query tile)
+    int *argq;    // MODE 2, optional: [B][A][V] first arg-max over the queries
+    uint32_t run_bytes;  // MODE 2: shared memory of the running maxima (+ 2 KB of exchange slots when maxq is set)
     long long *prof;  // debug: per CTA 8 counters of the MMA warp (clocks waiting for captions / accumulators / issuing)
 };
 
@@ -48,5 +50,18 @@ cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, con
 cudaError_t launch_align_reduce(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
                                 int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, void *workspace,
                                 cudaStream_t st);
+// both maxima in one pass: + maxq [B][A][V] / argq (max over the queries; Q <= 128)
+cudaError_t launch_align_maxima(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
+                                int V, int B, int Q, int D, float neg, int split, float *maxv, int *argv, float *maxq,
+                                int *argq, void *workspace, cudaStream_t st);
+// small fp32 kernels of the fused grounding consumers (align_consumers.cu)
+cudaError_t launch_align_diagonal(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int B,
+                                  int V, int Q, int D, float neg, float *out, cudaStream_t st);
+cudaError_t launch_grounding_ce(const float *maxv, const float *maxq, const float *txt_marginal, const uint8_t *vis_mask,
+                                int B, int Q, int V, float *out2, cudaStream_t st);
+cudaError_t launch_topk_rows(const float *x, long long rows, int V, int k, int *idx, cudaStream_t st);
+cudaError_t launch_max_over_factors_backward(const float *g, const int *argv, const float *vis, const uint8_t *vis_mask,
+                                             const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
+                                             float *grad_vis, float *grad_txt, cudaStream_t st);
 
 }  // namespace vlgae

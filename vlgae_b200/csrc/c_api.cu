@@ -358,6 +358,60 @@ int vlgae_align_max_over_factors(const float *vis_feat, const unsigned char *vis
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align reduce launch");
 }
 
+int vlgae_align_maxima(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                       const unsigned char *txt_mask, int A, int V, int B, int Q, int D, float neg_fill, int split,
+                       float *maxv, int *argv, float *maxq, int *argq, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!vis_feat || !vis_mask || !txt_feat || !txt_mask || !maxv) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (A < 0 || V < 0 || B < 0 || Q < 0) return fail(VLGAE_E_INVALID, "%s", "negative extent");
+    if (D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "D must be in [1, 128]");
+    if (split != 1 && split != 3) return fail(VLGAE_E_INVALID, "%s", "split must be 1 or 3");
+    if (maxq && Q > 128) return fail(VLGAE_E_INVALID, "%s", "the fused max over the queries needs Q <= 128");
+    if (A == 0 || B == 0 || Q == 0) return VLGAE_OK;
+    if (V == 0) return fail(VLGAE_E_INVALID, "%s", "max over an empty factor axis");
+    const size_t need = vlgae_align_reduce_workspace_bytes(A, V, B, Q, D);
+    if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "alignment workspace too small");
+    cudaError_t e = vlgae::launch_align_maxima(vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D, neg_fill, split, maxv, argv,
+                                               maxq, argq, workspace, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align maxima launch");
+}
+
+int vlgae_align_diagonal(const float *vis_feat, const unsigned char *vis_mask, const float *txt_feat,
+                         const unsigned char *txt_mask, int B, int V, int Q, int D, float neg_fill, float *out, void *stream) {
+    if (!vis_feat || !vis_mask || !txt_feat || !txt_mask || !out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B < 0 || V < 0 || Q < 0 || D < 1 || D > 256) return fail(VLGAE_E_INVALID, "%s", "bad extent");
+    if (B == 0 || V == 0 || Q == 0) return VLGAE_OK;
+    if (((size_t)((D + 3) & ~3) * (64 + (size_t)Q)) * 4 > 200 * 1024) return fail(VLGAE_E_INVALID, "%s", "Q * D too large for the diagonal kernel");
+    cudaError_t e = vlgae::launch_align_diagonal(vis_feat, vis_mask, txt_feat, txt_mask, B, V, Q, D, neg_fill, out, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "align diagonal launch");
+}
+
+int vlgae_grounding_ce(const float *maxv, const float *maxq, const float *txt_marginal, const unsigned char *vis_mask, int B,
+                       int Q, int V, float *out2, void *stream) {
+    if (!maxv || !txt_marginal || !out2 || (maxq && !vis_mask)) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B <= 0 || Q <= 0 || (maxq && V <= 0)) return fail(VLGAE_E_INVALID, "%s", "bad extent");
+    cudaError_t e = vlgae::launch_grounding_ce(maxv, maxq, txt_marginal, vis_mask, B, Q, V, out2, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "grounding ce launch");
+}
+
+int vlgae_topk_rows(const float *x, long long rows, int V, int k, int *idx, void *stream) {
+    if (!x || !idx) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (rows < 0 || V < 1 || k < 1 || k > 8) return fail(VLGAE_E_INVALID, "%s", "rows >= 0, V >= 1, 1 <= k <= 8 expected");
+    if (rows == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_topk_rows(x, rows, V, k, idx, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "topk launch");
+}
+
+int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *argv, const float *vis_feat,
+                                          const unsigned char *vis_mask, const float *txt_feat, const unsigned char *txt_mask,
+                                          int A, int V, int B, int Q, int D, float *grad_vis, float *grad_txt, void *stream) {
+    if (!grad_maxv || !argv || !vis_feat || !vis_mask || !txt_feat || !txt_mask) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (A < 0 || V < 0 || B < 0 || Q < 0 || D < 1 || D > VLGAE_ALIGN_MAX_D) return fail(VLGAE_E_INVALID, "%s", "bad extent");
+    if (A == 0 || V == 0 || B == 0 || Q == 0 || (!grad_vis && !grad_txt)) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_max_over_factors_backward(grad_maxv, argv, vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D,
+                                                            grad_vis, grad_txt, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "max backward launch");
+}
+
 static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
     if (!ms_host || !ops_host || iters < 1) return fail(VLGAE_E_INVALID, "%s", "bad microbench arguments");
     cudaStream_t st = (cudaStream_t)stream;
