@@ -50,10 +50,12 @@ const char *vlgae_last_error(void);
 
 /*
  * Schedule of the DMV kernels (process-wide): 0 = automatic, 1 = frontier (one thread per target cell, running
- * log-sum-exp / arg-max state; the default in every regime), 2 = gather (lanes stream the split points of a span,
- * two-pass log-sum-exp; csrc/dmv_gather.cu).  A schedule that cannot run a launch (chart beyond shared memory,
- * host-memory hand-off) falls back to the automatic choice.  Results agree within the documented tolerances
- * (max semiring: bit-exact).  Used by the tests and the sweep tool.
+ * log-sum-exp / arg-max state; the latency regime, short sentences, charts beyond 41 positions, host-memory hand-off),
+ * 2 = gather (lanes stream the split points of a span; log semiring in the linear domain on per-word offset scores with
+ * a self-check, value-only Viterbi with a re-evaluating back-trace; csrc/dmv_gather.cu).  Automatic = gather for
+ * batches beyond one resident wave padded to 28 .. 41 positions, frontier otherwise.  A schedule that cannot run a
+ * launch (chart beyond its layout, no workspace for the redo flags) falls back to the automatic choice.  Results agree
+ * within the documented tolerances (max semiring: bit-exact).  Used by the tests and the sweep tool.
  */
 int vlgae_dmv_set_schedule(int which);
 
@@ -66,9 +68,11 @@ int vlgae_dmv_set_profile_buffer(void *device_buf);
 
 /*
  * Bytes of device scratch the DMV entry points need for a batch of B sentences
- * padded to N positions.  Charts live in shared memory when they fit (N <= ~80);
- * otherwise each resident CTA keeps its chart in this workspace (L2-resident).
- * May return 0.
+ * padded to N positions: B redo flags of the gather schedule (a sentence whose
+ * linear-domain sweep fails its self-check is flagged and redone in the log domain
+ * by a follow-up launch), plus, when the chart does not fit in shared memory
+ * (N > ~72), one chart slice per resident CTA (L2-resident).  Without a workspace
+ * the entry points keep to the frontier schedule.
  */
 size_t vlgae_dmv_workspace_bytes(int B, int N);
 

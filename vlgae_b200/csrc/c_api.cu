@@ -32,13 +32,19 @@ int check_dmv(const float *dec, const float *attach, const int64_t *lengths, int
     return VLGAE_OK;
 }
 
+// workspace = per-sentence redo flags of the gather schedule (always) | chart slices (only when N is beyond shared memory)
+size_t redo_bytes(int B) { return ((size_t)B * 4 + 255) & ~(size_t)255; }
+
 int run_dmv(vlgae::DmvArgs &a, int passes, void *workspace, size_t workspace_bytes, void *stream) {
     if (a.B == 0) return VLGAE_OK;
+    const size_t rb = redo_bytes(a.B);
     if (!vlgae::dmv_fits_smem(a.N, passes)) {
         const size_t need = vlgae_dmv_workspace_bytes(a.B, a.N);
         if (!workspace || workspace_bytes < need) return fail(VLGAE_E_WORKSPACE, "%s", "workspace too small for this N");
-        a.workspace = workspace;
+        a.workspace = (unsigned char *)workspace + rb;
     }
+    // without the flags (no workspace passed) the launch logic keeps to the frontier schedule
+    a.redo = (workspace && workspace_bytes >= rb && !a.share) ? (int *)workspace : nullptr;
     a.npass = passes == 3 ? 2 : 1;
     a.first_pass = passes == 2 ? 1 : 0;
     cudaError_t e = vlgae::launch_dmv(a, passes, (cudaStream_t)stream);
@@ -64,8 +70,8 @@ const char *vlgae_last_error(void) { return g_err; }
 
 size_t vlgae_dmv_workspace_bytes(int B, int N) {
     if (B <= 0 || N < 1 || N > VLGAE_DMV_MAX_N) return 0;
-    if (vlgae::dmv_fits_smem(N, 3)) return 0;
-    return (size_t)vlgae::dmv_grid_for_workspace(B) * vlgae::dmv_ws_slice_bytes(N, 3);
+    if (vlgae::dmv_fits_smem(N, 3)) return redo_bytes(B);
+    return redo_bytes(B) + (size_t)vlgae::dmv_grid_for_workspace(B) * vlgae::dmv_ws_slice_bytes(N, 3);
 }
 
 int vlgae_dmv_inside_outside(const float *dec, const float *attach, const int64_t *lengths, int B, int N,
@@ -124,7 +130,7 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     // sentences hide behind the chart sweeps of the long ones, and the eight per-call copies (each a few us of fixed
     // cost) disappear: cfg2 182 us -> see DESIGN.md.  Pageable buffers take the staged path below.
     static const bool env_zero_copy = [] { const char *v = getenv("VLGAE_ZERO_COPY"); return !(v && v[0] == '0'); }();
-    if (env_zero_copy && ws == 0) {
+    if (env_zero_copy && vlgae::dmv_fits_smem(N, 3)) {
         const void *hp[8] = {dec_host, attach_host, lengths_host, Z_host, gdec_host, gattach_host, best_host, heads_host};
         void *dp[8];
         bool pinned = true;

@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 12
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }
+        if (p.only && p.only[b] == 0) continue;  // follow-up launch of the gather schedule: flagged sentences only
         const int len = clamp_len(p, b);  // read once: the lengths may live in host memory (one PCIe round trip)
         if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         unsigned char *chart = GC ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
@@ -905,6 +906,7 @@ __global__ void __launch_bounds__(32 * WPC, CPT <= 3 ? 6 : 4) dmv_frontier_warp_
         int b, which;
         if (p.npass == 2) { which = item >= p.B; b = which ? item - p.B : item; }
         else { which = p.first_pass; b = item; }
+        if (p.only && p.only[b] == 0) continue;
         const int len = clamp_len(p, b);
         if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         if (which == 0) log_pass<32, CPT, false>(p, b, len, slice, nullptr);

@@ -33,7 +33,11 @@ struct DmvArgs {
     int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
     int no_offsets;    // debug: log-semiring sweeps on the raw scores (no per-word offsets)
-    int log_domain;    // gather schedule: 1 = force the log-domain sweep (default: linear domain with log-domain fallback)
+    int log_domain;    // unused (kept for the debug environment switch)
+    // gather schedule (linear-domain log semiring): redo[b] = 1 when sentence b failed the sweep's self-check; the
+    // follow-up frontier launch handles exactly the sentences with only[b] != 0 (null = all)
+    int *redo;         // [B] or null
+    const int *only;   // [B] or null
     // frontier kernel, both passes in one launch, inputs in pinned HOST memory: the log CTA of a sentence republishes
     // what it staged (dec, arc scores) in device memory and the max CTA of the same sentence takes it from there, so
     // every input byte crosses PCIe once.  share_flag[b] == share_epoch once sentence b is published.
@@ -54,7 +58,9 @@ bool dmv_frontier_fits(int cap, int passes, int smem_optin);
 size_t dmv_frontier_chart_bytes(int N, int passes);  // per-CTA workspace slice when the chart is in global memory
 cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, bool reg_state, int sm_count, int max_grid,
                                 cudaStream_t st);
-// gather schedule (dmv_gather.cu): throughput regime, chart in shared memory, row-major squares
+// gather schedule (dmv_gather.cu): throughput regime, chart in shared memory, row-major squares of up to
+// DMV_GATHER_MAX_POSITIONS positions
+constexpr int DMV_GATHER_MAX_POSITIONS = 41;
 bool dmv_gather_fits(int cap, int passes, int smem_optin);
 cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st);
 void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather

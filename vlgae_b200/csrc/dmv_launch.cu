@@ -122,26 +122,11 @@ static long long *g_prof = nullptr;
 void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
 long long *dmv_profile_buffer() { return g_prof; }
 
-// one launch over the sentences with nb_lo <= len + 1 <= nb_hi, shared memory sized for `cap` positions
-static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, cudaStream_t st) {
-    static const int env_sched = [] {
-        const char *v = getenv("VLGAE_DMV_KERNEL");
-        return !v ? 0 : (v[0] == 'f' ? 1 : (v[0] == 'g' ? 2 : 0));
-    }();
-    const int sched = g_schedule ? g_schedule : env_sched;
+// frontier launch configuration for a length bucket sized for `cap` positions
+static cudaError_t launch_frontier_cap(const DmvArgs &a, int passes, int cap, cudaStream_t st) {
     static const int env_ft = env_int("VLGAE_FRONTIER_THREADS", 0);
-    static const int env_gt = env_int("VLGAE_GATHER_THREADS", 0);
     const bool fits = dmv_frontier_fits(cap, passes, g_smem_optin);
-    const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count;
-    // The gather schedule (dmv_gather.cu) runs on request only: the frontier schedule is the faster one in every regime
-    // measured so far; it also keeps the zero-copy hand-off and the charts beyond shared memory.
-    if (sched == 2 && !a.share && dmv_gather_fits(cap, passes, g_smem_optin)) {
-        int gt = cap <= 20 ? 32 : (cap <= 28 ? 64 : (cap <= 60 ? 128 : 256));
-        if (env_gt > 0) gt = env_gt;
-        DmvArgs f = a;
-        f.workspace = nullptr; f.ws_stride = 0;
-        return launch_dmv_gather(f, passes, cap, gt, g_sm_count, st);
-    }
+    const bool resident = (long long)a.B * a.npass <= 2LL * g_sm_count && !a.only;
     if (cap > 256 || !(fits || a.workspace)) return cudaErrorInvalidValue;
     DmvArgs f = a;
     // Latency regime (every work item resident at once): many threads, running state in registers.  Throughput
@@ -165,6 +150,24 @@ static cudaError_t launch_cap(const DmvArgs &a, int passes, int cap, cudaStream_
     return launch_dmv_frontier(f, passes, cap, ft, reg_state, g_sm_count, dmv_grid_for_workspace(a.B), st);
 }
 
+// Gather schedule (dmv_gather.cu: linear-domain log semiring, value-only Viterbi) for the sentences of a length range,
+// followed by a frontier launch restricted to the sentences whose linear-domain sweep flagged itself (normally none: the
+// launch then costs a few microseconds of flag reads).
+static cudaError_t launch_gather_range(const DmvArgs &a, int passes, int cap, cudaStream_t st) {
+    static const int env_gt = env_int("VLGAE_GATHER_THREADS", 0);
+    DmvArgs f = a;
+    f.workspace = nullptr; f.ws_stride = 0; f.only = nullptr;
+    cudaError_t e = launch_dmv_gather(f, passes, cap, env_gt > 0 ? env_gt : 128, g_sm_count, st);
+    if (e != cudaSuccess || !(passes & 1)) return e;
+    DmvArgs r = a;
+    r.npass = 1; r.first_pass = 0; r.only = a.redo; r.redo = nullptr; r.workspace = nullptr; r.ws_stride = 0;
+    return launch_frontier_cap(r, 1, cap, st);
+}
+
+static bool gather_usable(const DmvArgs &a, int passes, int cap) {
+    return a.redo && !a.share && !a.only && dmv_gather_fits(cap, passes, g_smem_optin);
+}
+
 cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     DmvArgs a = a_in;
     a.prof = g_prof;
@@ -172,26 +175,58 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     a.nsm = g_sm_count;
     a.nb_lo = 0; a.nb_hi = a.N;
-    static const int env_no_off = env_int("VLGAE_DMV_NO_OFFSETS", 0), env_logdom = env_int("VLGAE_GATHER_LOG_DOMAIN", 0);
+    static const int env_no_off = env_int("VLGAE_DMV_NO_OFFSETS", 0);
     a.no_offsets = env_no_off;
-    a.log_domain = env_logdom;
+    static const int env_sched = [] {
+        const char *v = getenv("VLGAE_DMV_KERNEL");
+        return !v ? 0 : (v[0] == 'f' ? 1 : (v[0] == 'g' ? 2 : 0));
+    }();
+    const int sched = g_schedule ? g_schedule : env_sched;
     // Throughput regime (more work items than one resident wave at the padded length): one launch per length bucket,
     // shared memory sized for the bucket, so short sentences run at 10-20 CTAs per SM instead of the 3 a 40-word
     // chart allows.  Sentences outside a launch's bucket are skipped by its CTAs (no host knowledge of the lengths,
     // no sorting assumption).  Longest bucket first.
     static const int env_bucket = env_int("VLGAE_DMV_BUCKETS", 1);
+    // measured on B200 (tools/dmv_sweep.py, 512 full-length sentences): the gather schedule overtakes the frontier
+    // schedule between 24 and 28 words (n = 24: 75 vs 52 us, n = 28: 89 vs 103 us, n = 40: 157 vs 220 us)
+    static const int env_gather_lo = env_int("VLGAE_GATHER_MIN_POSITIONS", 28);
+    // in a bulk launch (length buckets, tens of waves) the gather schedule already wins from 18 positions on
+    // (COCO-shaped 16384 sentences: 585 us with the buckets >= 18 on the gather schedule, 661 us with those >= 28)
+    static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 18);
     const long long items = (long long)a.B * a.npass;
     const bool bulk = env_bucket && items > 8192 && !a.share;
-    if (!bulk) return launch_cap(a, passes, a.N, st);
+    const int gcap = a.N < DMV_GATHER_MAX_POSITIONS ? a.N : DMV_GATHER_MAX_POSITIONS;
+    if (!bulk) {
+        // one launch.  Latency regime (every work item resident at once): frontier schedule.  Beyond one wave the
+        // gather schedule takes the batches padded to env_gather_lo .. 41 positions (and any batch on request: tests,
+        // sweeps) -- lengths are not known on the host, so the padded length decides.
+        const bool resident = items <= 2LL * g_sm_count;
+        const bool want = sched == 2 || (sched == 0 && !resident && a.N >= env_gather_lo);
+        if (want && a.N <= DMV_GATHER_MAX_POSITIONS && gather_usable(a, passes, a.N))
+            return launch_gather_range(a, passes, a.N, st);
+        return launch_frontier_cap(a, passes, a.N, st);
+    }
     static const int caps[] = {8, 12, 16, 20, 24, 28, 33, 41, 49, 65, 97, 129, 256};
     int nb = 0, bounds[16];
     for (int c : caps) if (c < a.N) bounds[nb++] = c;
     bounds[nb++] = a.N;
+    const bool use_gather = sched != 1 && gather_usable(a, passes, gcap);
+    bool gather_done = false;
     for (int k = nb - 1; k >= 0; --k) {
         DmvArgs bkt = a;
         bkt.nb_hi = bounds[k];
         bkt.nb_lo = k > 0 ? bounds[k - 1] + 1 : 0;
-        e = launch_cap(bkt, passes, bounds[k], st);
+        if (use_gather && bkt.nb_hi <= gcap && bkt.nb_hi >= env_gather_bulk_lo) {
+            // every bucket between env_gather_bulk_lo and the layout's capacity goes into ONE gather launch
+            if (gather_done) continue;
+            int lo = bkt.nb_lo;
+            for (int kk = k - 1; kk >= 0 && bounds[kk] >= env_gather_bulk_lo; --kk) lo = kk > 0 ? bounds[kk - 1] + 1 : 0;
+            bkt.nb_lo = lo;
+            e = launch_gather_range(bkt, passes, bkt.nb_hi, st);
+            gather_done = true;
+        } else {
+            e = launch_frontier_cap(bkt, passes, bounds[k], st);
+        }
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
