@@ -227,6 +227,22 @@ int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *arg
                                           const unsigned char *vis_mask, const float *txt_feat, const unsigned char *txt_mask,
                                           int A, int V, int B, int Q, int D, float *grad_vis, float *grad_txt, void *stream);
 
+/*
+ * Word -> factor attention of DependencyBoxRel._forward (reference joint.py:668-673):
+ *     attmap = einsum("bvd,bqd->bqv", vis_feat, txt_feat).softmax(2);  out = einsum("bqv,bvh->bqh", attmap, vis_mid)
+ * one caption per CTA, the factors streamed in tiles with an online softmax (the [B][n][V] attention map is never written).
+ *   vis_feat [B][V][D], txt_feat [B][n][D] (the caller drops ROOT with [:, 1:] first, joint.py:669), vis_mid [B][V][H], fp32
+ *   out [B][n][H];  lse [B][n] or NULL: row log-sum-exp of the scores, what the backward needs besides out
+ *   n <= 64, H <= 256, (n + 64) * D + 32 * H floats of shared memory must fit (D = 128, H = 256 do).
+ * vlgae_word_attention_backward: gradients of out w.r.t. the three inputs given grad_out [B][n][H]; the probabilities are
+ *   recomputed from lse.  grad_vis [B][V][D], grad_txt [B][n][D], grad_mid [B][V][H]; any may be NULL.
+ */
+int vlgae_word_attention(const float *vis_feat, const float *txt_feat, const float *vis_mid, int B, int V, int n, int D, int H,
+                         float *out, float *lse, void *stream);
+int vlgae_word_attention_backward(const float *vis_feat, const float *txt_feat, const float *vis_mid, const float *out,
+                                  const float *lse, const float *grad_out, int B, int V, int n, int D, int H,
+                                  float *grad_vis, float *grad_txt, float *grad_mid, void *stream);
+
 /* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
 int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);
 

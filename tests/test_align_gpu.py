@@ -151,18 +151,41 @@ def test_max_over_factors_equals_max_of_materialised(dev, A, V, B, Q, D):
     assert np.abs(got - want)[~masked].max(initial=0.0) <= scale * 2.0 ** -15
 
 
-def test_word_factor_attention(dev):
-    """Row a10 (joint.py:668-673): library GEMMs + softmax, checked against the numpy restatement."""
+@pytest.mark.parametrize("B,V,n,D,H", [(4, 300, 12, 128, 256), (3, 1369, 40, 128, 256), (2, 33, 1, 16, 8), (2, 31, 64, 64, 100)])
+def test_word_factor_attention(dev, B, V, n, D, H):
+    """Row a10 (joint.py:668-673): the online-softmax kernel against the numpy restatement, and its backward against
+    autograd through the reference's own two einsums + softmax evaluated in fp64."""
     from vlgae_b200.alignment import word_factor_attention
 
     g = torch.Generator(device=dev).manual_seed(5)
-    vis = torch.randn(4, 300, 128, generator=g, device=dev) * 0.3
-    txt = torch.randn(4, 12, 128, generator=g, device=dev) * 0.3
-    mid = torch.randn(4, 300, 256, generator=g, device=dev)
-    torch.backends.cuda.matmul.allow_tf32 = False
-    got = word_factor_attention(vis, txt, mid).cpu().numpy()
-    want = oracle.word_factor_attention(vis.cpu().numpy(), txt.cpu().numpy(), mid.cpu().numpy())
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    vis = (torch.randn(B, V, D, generator=g, device=dev) * 0.3).requires_grad_()
+    txt = (torch.randn(B, n, D, generator=g, device=dev) * 0.3).requires_grad_()
+    mid = torch.randn(B, V, H, generator=g, device=dev).requires_grad_()
+    out = word_factor_attention(vis, txt, mid)
+    want = oracle.word_factor_attention(vis.detach().cpu().numpy(), txt.detach().cpu().numpy(), mid.detach().cpu().numpy())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    go = torch.randn(B, n, H, generator=g, device=dev)
+    gv, gt, gm = torch.autograd.grad(out, [vis, txt, mid], go)
+    v64, t64, m64 = (x.detach().double().requires_grad_() for x in (vis, txt, mid))
+    ref = torch.einsum("bqv,bvh->bqh", torch.einsum("bvd,bqd->bqv", v64, t64).softmax(2), m64)  # joint.py:670-673
+    rv, rt, rm = torch.autograd.grad(ref, [v64, t64, m64], go.double())
+    for got, exp in ((gv, rv), (gt, rt), (gm, rm)):
+        np.testing.assert_allclose(got.cpu().numpy(), exp.cpu().numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_word_factor_attention_only_some_grads(dev):
+    from vlgae_b200.alignment import word_factor_attention
+
+    g = torch.Generator(device=dev).manual_seed(6)
+    vis = torch.randn(2, 50, 32, generator=g, device=dev)
+    txt = torch.randn(2, 7, 32, generator=g, device=dev).requires_grad_()
+    mid = torch.randn(2, 50, 16, generator=g, device=dev)
+    out = word_factor_attention(vis, txt, mid)
+    (gt,) = torch.autograd.grad(out.sum(), [txt])
+    t64 = txt.detach().double().requires_grad_()
+    ref = torch.einsum("bqv,bvh->bqh", torch.einsum("bvd,bqd->bqv", vis.double(), t64).softmax(2), mid.double())
+    (rt,) = torch.autograd.grad(ref.sum(), [t64])
+    np.testing.assert_allclose(gt.cpu().numpy(), rt.cpu().numpy(), rtol=2e-4, atol=2e-5)
 
 
 @pytest.mark.parametrize("A,V,B,Q,D,pad", [(2, 150, 3, 20, 128, False), (3, 300, 4, 82, 128, True), (2, 129, 2, 130, 64, False),

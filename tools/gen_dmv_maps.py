@@ -130,41 +130,41 @@ def best_map(Nb, w, T, streams, term_clk, reduce_vals, max_warps=4):
 
 
 def main():
-    S = 42
-    CAP = S - 1
     kinds = [("inside / Viterbi (fused steps 1-4, w - 1 split points)", streams_inside, lambda w: w - 1, 41, 6),
              ("reverse sweep, complete parents (w split points)", streams_aprime, lambda w: w, 80, 0),
              ("reverse sweep, incomplete parents (w split points)", streams_bprime, lambda w: w, 40, 0)]
     lines = ["// dmv_maps.inc -- generated by tools/gen_dmv_maps.py (bank model of the shared memory); do not edit.",
-             "// entry = lg | c << 3 | chunk_major << 9 for (CTA size: 4 or 8 warps, pass, positions Nb, width w); row stride %d" % S,
-             "static __constant__ unsigned short g_dmv_map[2][3][%d][%d] = {" % (CAP + 1, CAP + 1)]
-    tot_wf = [0, 0, 0]
-    ideal = [0.0, 0.0, 0.0]
-    for max_warps in (4, 8):
-        lines.append(" {  // CTAs of %d warps" % max_warps)
-        for kidx, (name, sf, tf, ipt, rv) in enumerate(kinds):
-            lines.append("  {  // " + name)
-            streams = sf(S)
-            for Nb in range(CAP + 1):
-                row = []
-                for w in range(CAP + 1):
-                    T = tf(w)
-                    if w < 1 or w >= Nb or T <= 0:
-                        row.append(0)
-                        continue
-                    _, lg, c, qm, wf = best_map(Nb, w, T, streams, ipt, rv, max_warps)
-                    row.append(lg | (c << 3) | (qm << 9))
-                    if Nb == CAP and max_warps == 8:
-                        tot_wf[kidx] += wf
-                        ideal[kidx] += (Nb - w) * T * sum(wd * m for wd, _, m in streams) / 128.0
-                lines.append("    {" + ", ".join(str(v) for v in row) + "},")
-            lines.append("  },")
-        lines.append(" },")
-    lines.append("};")
+             "// entry = lg | c << 3 | chunk_major << 9 for (CTA size: 2, 4 or 8 warps; pass; positions Nb; width w), one table per row stride S"]
+    for S in (26, 34, 42):
+        CAP = S - 1
+        lines.append("static __device__ const unsigned short g_dmv_map_%d[3][3][%d][%d] = {" % (S, CAP + 1, CAP + 1))
+        tot_wf = [0, 0, 0]
+        ideal = [0.0, 0.0, 0.0]
+        for max_warps in (2, 4, 8):
+            lines.append(" {  // CTAs of %d warps" % max_warps)
+            for kidx, (name, sf, tf, ipt, rv) in enumerate(kinds):
+                lines.append("  {  // " + name)
+                streams = sf(S)
+                for Nb in range(CAP + 1):
+                    row = []
+                    for w in range(CAP + 1):
+                        T = tf(w)
+                        if w < 1 or w >= Nb or T <= 0:
+                            row.append(0)
+                            continue
+                        _, lg, c, qm, wf = best_map(Nb, w, T, streams, ipt, rv, max_warps)
+                        row.append(lg | (c << 3) | (qm << 9))
+                        if Nb == CAP and max_warps == 4:
+                            tot_wf[kidx] += wf
+                            ideal[kidx] += (Nb - w) * T * sum(wd * m for wd, _, m in streams) / 128.0
+                    lines.append("    {" + ", ".join(str(v) for v in row) + "},")
+                lines.append("  },")
+            lines.append(" },")
+        lines.append("};")
+        for kidx, (name, *_rest) in enumerate(kinds):
+            print(f"S = {S}: {name}: {tot_wf[kidx]} wavefronts at Nb = {CAP} (ideal {ideal[kidx]:.0f}, efficiency {ideal[kidx] / max(tot_wf[kidx], 1):.2f})", flush=True)
     with open(os.path.join(ROOT, "vlgae_b200", "csrc", "dmv_maps.inc"), "w") as f:
         f.write("\n".join(lines) + "\n")
-    for kidx, (name, *_rest) in enumerate(kinds):
-        print(f"{name}: {tot_wf[kidx]} wavefronts at Nb = {CAP} (ideal {ideal[kidx]:.0f}, efficiency {ideal[kidx] / max(tot_wf[kidx], 1):.2f})")
 
 
 if __name__ == "__main__":

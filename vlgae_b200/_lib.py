@@ -49,6 +49,10 @@ PROTOTYPES = {
     "vlgae_topk_rows": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p]),
     "vlgae_align_max_over_factors_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vlgae_word_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
+    "vlgae_word_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlgae_scale_rows": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "vlgae_microbench_mufu": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "vlgae_microbench_fp32": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),

@@ -354,15 +354,57 @@ def grounding_loss_fused(match, txt_marginal, vis_mask, num_token, *, prior=None
     return sum(loss.values()), loss, (t2v, v2t)
 
 
+class _WordAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vis, txt, mid):
+        dev = vis.device
+        B, V, D = vis.shape
+        n, H = txt.shape[1], mid.shape[2]
+        vf, tf, mf = (x.detach().to(torch.float32).contiguous() for x in (vis, txt, mid))
+        out = torch.empty((B, n, H), dtype=torch.float32, device=dev)
+        lse = torch.empty((B, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().vlgae_word_attention(vf.data_ptr(), tf.data_ptr(), mf.data_ptr(), B, V, n, D, H, out.data_ptr(),
+                                             lse.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "vlgae_word_attention")
+        ctx.save_for_backward(vf, tf, mf, out, lse)
+        ctx.dtypes = (vis.dtype, txt.dtype, mid.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        vf, tf, mf, out, lse = ctx.saved_tensors
+        dev = g.device
+        B, V, D = vf.shape
+        n, H = tf.shape[1], mf.shape[2]
+        g = g.to(torch.float32).contiguous()
+        need = ctx.needs_input_grad
+        gv = torch.empty_like(vf) if need[0] else None
+        gt = torch.empty_like(tf) if need[1] else None
+        gm = torch.empty_like(mf) if need[2] else None
+        if n > 0:
+            with torch.cuda.device(dev):
+                check(lib().vlgae_word_attention_backward(
+                    vf.data_ptr(), tf.data_ptr(), mf.data_ptr(), out.data_ptr(), lse.data_ptr(), g.data_ptr(), B, V, n, D, H,
+                    gv.data_ptr() if gv is not None else None, gt.data_ptr() if gt is not None else None,
+                    gm.data_ptr() if gm is not None else None, torch.cuda.current_stream(dev).cuda_stream),
+                    "vlgae_word_attention_backward")
+        else:
+            gv, gm = (x.zero_() if x is not None else None for x in (gv, gm))
+        return tuple(x.to(dt) if x is not None else None for x, dt in zip((gv, gt, gm), ctx.dtypes))
+
+
 def word_factor_attention(vis_feat, txt_feat, vis_mid):
     """Per-sample word -> factor attention of ``DependencyBoxRel._forward`` (joint.py:668-673):
-    ``softmax_v(<txt[b,q,:], vis[b,v,:]>) @ vis_mid[b]`` -> [B, Q, H].  Two plain batched GEMMs and a softmax (0.3 % of the
-    alignment contraction's flops at the cfg2 shape): run as library calls, differentiable through torch."""
+    ``softmax_v(<txt[b,q,:], vis[b,v,:]>) @ vis_mid[b]`` -> [B, n, H] in one kernel (``vlgae_word_attention``: online softmax
+    over tiles of factors, the [B, n, V] map is never written); differentiable w.r.t. all three inputs through
+    ``vlgae_word_attention_backward``.  n <= 64 words, H <= 256."""
     vis_feat, txt_feat, vis_mid = map(_plain, (vis_feat, txt_feat, vis_mid))
     if vis_feat.device.type != "cuda":
         raise VlgaeError("vlgae_b200.alignment needs CUDA tensors (there is no CPU fallback)")
-    att = torch.bmm(txt_feat, vis_feat.transpose(1, 2)).softmax(2)
-    return torch.bmm(att, vis_mid)
+    if vis_feat.dim() != 3 or txt_feat.dim() != 3 or vis_mid.dim() != 3 or vis_feat.shape[0] != txt_feat.shape[0] \
+            or vis_mid.shape[:2] != vis_feat.shape[:2] or vis_feat.shape[2] != txt_feat.shape[2]:
+        raise VlgaeError("word_factor_attention: vis [B,V,D], txt [B,n,D], vis_mid [B,V,H] expected")
+    return _WordAttention.apply(vis_feat, txt_feat, vis_mid)
 
 
 # ---- drop-in methods for the reference's implementation-group registry -------------------------------------------

@@ -63,5 +63,11 @@ cudaError_t launch_topk_rows(const float *x, long long rows, int V, int k, int *
 cudaError_t launch_max_over_factors_backward(const float *g, const int *argv, const float *vis, const uint8_t *vis_mask,
                                              const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
                                              float *grad_vis, float *grad_txt, cudaStream_t st);
+// word -> factor attention (word_attention.cu; joint.py:668-673)
+cudaError_t launch_word_attention(const float *vis, const float *txt, const float *mid, int B, int V, int n, int D, int H,
+                                  float *out, float *lse, cudaStream_t st);
+cudaError_t launch_word_attention_backward(const float *vis, const float *txt, const float *mid, const float *out,
+                                           const float *lse, const float *gout, int B, int V, int n, int D, int H, float *gvis,
+                                           float *gtxt, float *gmid, cudaStream_t st);
 
 }  // namespace vlgae

@@ -418,6 +418,28 @@ int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *arg
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "max backward launch");
 }
 
+int vlgae_word_attention(const float *vis_feat, const float *txt_feat, const float *vis_mid, int B, int V, int n, int D, int H,
+                         float *out, float *lse, void *stream) {
+    if (!vis_feat || !txt_feat || !vis_mid || !out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B < 0 || V < 1 || n < 0 || n > 64 || D < 1 || H < 1 || H > 256)
+        return fail(VLGAE_E_INVALID, "%s", "B >= 0, V >= 1, 0 <= n <= 64, D >= 1, 1 <= H <= 256 expected");
+    if (B == 0 || n == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_word_attention(vis_feat, txt_feat, vis_mid, B, V, n, D, H, out, lse, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "word attention launch");
+}
+
+int vlgae_word_attention_backward(const float *vis_feat, const float *txt_feat, const float *vis_mid, const float *out,
+                                  const float *lse, const float *grad_out, int B, int V, int n, int D, int H,
+                                  float *grad_vis, float *grad_txt, float *grad_mid, void *stream) {
+    if (!vis_feat || !txt_feat || !vis_mid || !out || !lse || !grad_out) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B < 0 || V < 1 || n < 1 || n > 64 || D < 1 || H < 1 || H > 256)
+        return fail(VLGAE_E_INVALID, "%s", "B >= 0, V >= 1, 1 <= n <= 64, D >= 1, 1 <= H <= 256 expected");
+    if (B == 0 || (!grad_vis && !grad_txt && !grad_mid)) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_word_attention_backward(vis_feat, txt_feat, vis_mid, out, lse, grad_out, B, V, n, D, H, grad_vis,
+                                                          grad_txt, grad_mid, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "word attention backward launch");
+}
+
 static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
     if (!ms_host || !ops_host || iters < 1) return fail(VLGAE_E_INVALID, "%s", "bad microbench arguments");
     cudaStream_t st = (cudaStream_t)stream;

@@ -150,18 +150,94 @@ static cudaError_t launch_frontier_cap(const DmvArgs &a, int passes, int cap, cu
     return launch_dmv_frontier(f, passes, cap, ft, reg_state, g_sm_count, dmv_grid_for_workspace(a.B), st);
 }
 
-// Gather schedule (dmv_gather.cu: linear-domain log semiring, value-only Viterbi) for the sentences of a length range,
-// followed by a frontier launch restricted to the sentences whose linear-domain sweep flagged itself (normally none: the
-// launch then costs a few microseconds of flag reads).
-static cudaError_t launch_gather_range(const DmvArgs &a, int passes, int cap, cudaStream_t st) {
+// Independent launches of one call (the two semirings, the length ranges / buckets: disjoint sentences or disjoint
+// outputs) go to side streams forked from the caller's stream and joined before the call returns to it, so the tail of
+// one launch (its last, partly empty wave) overlaps the head of the next instead of idling the SMs.  Event fork / join
+// only: legal under stream capture.  VLGAE_DMV_LANES=0 keeps everything on the caller's stream.
+struct Lanes {
+    static constexpr int NSIDE = 6;
+    cudaStream_t main = nullptr, side[NSIDE] = {};
+    cudaEvent_t fork = nullptr, join[NSIDE] = {};
+    bool used[NSIDE] = {};
+    bool on = false;
+    int dev = -1;
+    cudaError_t begin(cudaStream_t st, bool enable) {
+        main = st; on = false;
+        for (bool &u : used) u = false;
+        if (!enable) return cudaSuccess;
+        int d = 0;
+        cudaError_t e = cudaGetDevice(&d);
+        if (e != cudaSuccess) return e;
+        if (d != dev) {  // first use on this device (streams of a previous device are left to the driver)
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            static const int env_prio = env_int("VLGAE_DMV_LANE_PRIORITY", 1);
+            for (int k = 0; k < NSIDE; ++k) {
+                // lanes 1..3 carry the log-semiring launches, the long ones: their CTAs are placed first
+                const int prio = (k < 3 && env_prio) ? greatest : least;
+                if ((e = cudaStreamCreateWithPriority(&side[k], cudaStreamNonBlocking, prio)) != cudaSuccess) return e;
+                if ((e = cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+            }
+            if ((e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+            dev = d;
+        }
+        if ((e = cudaEventRecord(fork, st)) != cudaSuccess) return e;
+        on = true;
+        return cudaSuccess;
+    }
+    // lane 0 is the caller's stream
+    cudaStream_t get(int lane) {
+        if (!on || lane <= 0) return main;
+        const int k = (lane - 1) % NSIDE;
+        if (!used[k]) { cudaStreamWaitEvent(side[k], fork, 0); used[k] = true; }
+        return side[k];
+    }
+    cudaError_t end() {
+        if (!on) return cudaSuccess;
+        for (int k = 0; k < NSIDE; ++k) {
+            if (!used[k]) continue;
+            cudaError_t e = cudaEventRecord(join[k], side[k]);
+            if (e != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(main, join[k], 0)) != cudaSuccess) return e;
+        }
+        on = false;
+        return cudaSuccess;
+    }
+};
+static thread_local Lanes g_lanes;
+
+// Gather schedule (dmv_gather.cu: linear-domain log semiring, value-only Viterbi) for the sentences with lo <= len + 1 <= hi.
+// With `split`, one launch pair per row stride of the layout (charts of <= 25 / 33 / 41 positions: 10 / 6 / 4
+// log-semiring CTAs per SM), longest first; the log-semiring launches take the high-priority lanes 1..3, the Viterbi
+// launches lane 0 (the caller's stream) and lanes 4, 5.
+// The caller joins the lanes and then calls launch_gather_redo: ONE frontier launch restricted to the sentences whose
+// linear-domain sweep flagged itself (normally none: that launch then costs a few microseconds of flag reads).
+static cudaError_t launch_gather_ranges(const DmvArgs &a, int passes, int lo, int hi, bool split, Lanes &lanes) {
     static const int env_gt = env_int("VLGAE_GATHER_THREADS", 0);
-    DmvArgs f = a;
-    f.workspace = nullptr; f.ws_stride = 0; f.only = nullptr;
-    cudaError_t e = launch_dmv_gather(f, passes, cap, env_gt > 0 ? env_gt : 128, g_sm_count, st);
-    if (e != cudaSuccess || !(passes & 1)) return e;
+    static const int ghi[] = {41, 33, 25}, glo[] = {34, 26, 0};
+    for (int which = 1; which <= 2; ++which) {  // log-semiring launches first: the longer ones
+        if (!(passes & which)) continue;
+        for (int k = 0; k < 3; ++k) {
+            int rlo = glo[k] > lo ? glo[k] : lo, rhi = ghi[k] < hi ? ghi[k] : hi;
+            if (!split) { rlo = lo; rhi = hi; }
+            if (rlo > rhi) continue;
+            DmvArgs f = a;
+            f.workspace = nullptr; f.ws_stride = 0; f.only = nullptr;
+            f.nb_lo = rlo; f.nb_hi = rhi;
+            const int lane = which == 1 ? 1 + k : (k == 0 ? 0 : 3 + k);
+            cudaError_t e = launch_dmv_gather(f, which, rhi, env_gt, g_sm_count, lanes.get(lane));
+            if (e != cudaSuccess) return e;
+            if (!split) break;
+        }
+    }
+    return cudaSuccess;
+}
+static cudaError_t launch_gather_redo(const DmvArgs &a, int passes, int lo, int hi, cudaStream_t st) {
+    if (!(passes & 1)) return cudaSuccess;
     DmvArgs r = a;
     r.npass = 1; r.first_pass = 0; r.only = a.redo; r.redo = nullptr; r.workspace = nullptr; r.ws_stride = 0;
-    return launch_frontier_cap(r, 1, cap, st);
+    r.nb_lo = lo; r.nb_hi = hi;
+    return launch_frontier_cap(r, 1, hi, st);
 }
 
 static bool gather_usable(const DmvArgs &a, int passes, int cap) {
@@ -192,7 +268,10 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     static const int env_gather_lo = env_int("VLGAE_GATHER_MIN_POSITIONS", 28);
     // in a bulk launch (length buckets, tens of waves) the gather schedule already wins from 18 positions on
     // (COCO-shaped 16384 sentences: 585 us with the buckets >= 18 on the gather schedule, 661 us with those >= 28)
-    static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 18);
+    // (r2c, lanes + length split: 528 us from 12 positions on, 604 us from 18)
+    static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 12);
+    static const int env_lanes = env_int("VLGAE_DMV_LANES", 1);
+    static const int env_split = env_int("VLGAE_GATHER_SPLIT", 1);
     const long long items = (long long)a.B * a.npass;
     const bool bulk = env_bucket && items > 8192 && !a.share;
     const int gcap = a.N < DMV_GATHER_MAX_POSITIONS ? a.N : DMV_GATHER_MAX_POSITIONS;
@@ -202,33 +281,47 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
         // sweeps) -- lengths are not known on the host, so the padded length decides.
         const bool resident = items <= 2LL * g_sm_count;
         const bool want = sched == 2 || (sched == 0 && !resident && a.N >= env_gather_lo);
-        if (want && a.N <= DMV_GATHER_MAX_POSITIONS && gather_usable(a, passes, a.N))
-            return launch_gather_range(a, passes, a.N, st);
+        // (a batch of several waves is split by length like a bulk launch: short sentences then run at 6-10 CTAs per SM)
+        if (want && a.N <= DMV_GATHER_MAX_POSITIONS && gather_usable(a, passes, a.N)) {
+            Lanes &lanes = g_lanes;
+            if ((e = lanes.begin(st, env_lanes && passes == 3)) != cudaSuccess) return e;
+            // (one launch pair: splitting a few waves by length adds more launch tails than the residency gains)
+            e = launch_gather_ranges(a, passes, 0, a.N, env_split > 1, lanes);
+            const cudaError_t e2 = lanes.end();
+            if (e != cudaSuccess || e2 != cudaSuccess) return e != cudaSuccess ? e : e2;
+            return launch_gather_redo(a, passes, 0, a.N, st);
+        }
         return launch_frontier_cap(a, passes, a.N, st);
     }
+    Lanes &lanes = g_lanes;
+    if ((e = lanes.begin(st, env_lanes != 0)) != cudaSuccess) return e;
+    int gather_lo = a.N + 1;  // lowest chart size handled by the gather launches
+    if (sched != 1 && gather_usable(a, passes, gcap) && env_gather_bulk_lo <= gcap) {
+        gather_lo = env_gather_bulk_lo;
+        e = launch_gather_ranges(a, passes, gather_lo, gcap, env_split != 0, lanes);
+        if (e != cudaSuccess) { lanes.end(); return e; }
+    }
+    const int gather_hi = gather_lo <= a.N ? gcap : 0;  // [gather_lo, gather_hi] is done
     static const int caps[] = {8, 12, 16, 20, 24, 28, 33, 41, 49, 65, 97, 129, 256};
     int nb = 0, bounds[16];
     for (int c : caps) if (c < a.N) bounds[nb++] = c;
     bounds[nb++] = a.N;
-    const bool use_gather = sched != 1 && gather_usable(a, passes, gcap);
-    bool gather_done = false;
     for (int k = nb - 1; k >= 0; --k) {
         DmvArgs bkt = a;
         bkt.nb_hi = bounds[k];
         bkt.nb_lo = k > 0 ? bounds[k - 1] + 1 : 0;
-        if (use_gather && bkt.nb_hi <= gcap && bkt.nb_hi >= env_gather_bulk_lo) {
-            // every bucket between env_gather_bulk_lo and the layout's capacity goes into ONE gather launch
-            if (gather_done) continue;
-            int lo = bkt.nb_lo;
-            for (int kk = k - 1; kk >= 0 && bounds[kk] >= env_gather_bulk_lo; --kk) lo = kk > 0 ? bounds[kk - 1] + 1 : 0;
-            bkt.nb_lo = lo;
-            e = launch_gather_range(bkt, passes, bkt.nb_hi, st);
-            gather_done = true;
-        } else {
-            e = launch_frontier_cap(bkt, passes, bounds[k], st);
+        // clip the bucket against the range the gather launches took
+        if (gather_hi) {
+            if (bkt.nb_lo >= gather_lo && bkt.nb_hi <= gather_hi) continue;
+            if (bkt.nb_lo < gather_lo && bkt.nb_hi >= gather_lo) bkt.nb_hi = gather_lo - 1;
+            else if (bkt.nb_lo <= gather_hi && bkt.nb_hi > gather_hi) bkt.nb_lo = gather_hi + 1;
         }
-        if (e != cudaSuccess) return e;
+        // the frontier buckets share one lane (each is a short launch; the lane runs beside the gather launches)
+        e = launch_frontier_cap(bkt, passes, bkt.nb_hi, lanes.get(gather_hi ? 6 : 0));
+        if (e != cudaSuccess) { lanes.end(); return e; }
     }
+    if ((e = lanes.end()) != cudaSuccess) return e;
+    if (gather_hi) return launch_gather_redo(a, passes, gather_lo, gather_hi, st);
     return cudaSuccess;
 }
 

@@ -19,9 +19,10 @@ constexpr int WA_TV = 32;   // factors per tile
 constexpr int WA_NQ = 64;   // max queries
 
 // shared: txt [n][D] | vis tile [TV][D] | mid tile [TV][H] | P [n][TV] | m [n] | l [n] | alpha [n]
+// (tile rows are padded by one float: lanes that walk the factors of a tile then hit distinct banks)
 template <bool BWD>
 __host__ __device__ inline size_t wa_smem(int n, int D, int H) {
-    size_t f = (size_t)n * D + (size_t)WA_TV * D + (size_t)WA_TV * H + (size_t)n * WA_TV + 3 * (size_t)n;
+    size_t f = (size_t)n * D + (size_t)WA_TV * (D + 1) + (size_t)WA_TV * (H + 1) + (size_t)n * WA_TV + 3 * (size_t)n;
     if (BWD) f += (size_t)n * H + (size_t)n * WA_TV + (size_t)n * D;  // dO [n][H] | dS [n][TV] | dtxt [n][D]
     return f * sizeof(float);
 }
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(WA_T) word_attn_fwd_kernel(const float *__rest
                                                              const float *__restrict__ mid, int V, int n, int D, int H,
                                                              float *__restrict__ out, float *__restrict__ lse) {
     extern __shared__ __align__(16) float sm[];
-    float *s_txt = sm, *s_vis = s_txt + n * D, *s_mid = s_vis + WA_TV * D, *s_p = s_mid + WA_TV * H;
+    const int DP = D + 1, HP = H + 1;
+    float *s_txt = sm, *s_vis = s_txt + n * D, *s_mid = s_vis + WA_TV * DP, *s_p = s_mid + WA_TV * HP;
     float *s_m = s_p + n * WA_TV, *s_l = s_m + n, *s_a = s_l + n;
     const int b = blockIdx.x, tid = threadIdx.x;
     const float *vb = vis + (size_t)b * V * D, *mb = mid + (size_t)b * V * H;
@@ -42,8 +44,8 @@ __global__ void __launch_bounds__(WA_T) word_attn_fwd_kernel(const float *__rest
     __syncthreads();
     for (int v0 = 0; v0 < V; v0 += WA_TV) {
         const int tv = min(WA_TV, V - v0);
-        for (int t = tid; t < tv * D; t += WA_T) s_vis[t] = vb[(size_t)v0 * D + t];
-        for (int t = tid; t < tv * H; t += WA_T) s_mid[t] = mb[(size_t)v0 * H + t];
+        for (int t = tid; t < tv * D; t += WA_T) s_vis[(t / D) * DP + t % D] = vb[(size_t)v0 * D + t];
+        for (int t = tid; t < tv * H; t += WA_T) s_mid[(t / H) * HP + t % H] = mb[(size_t)v0 * H + t];
         __syncthreads();
         // scores S[q][v] = <txt[q], vis[v]>
         for (int e = tid; e < n * WA_TV; e += WA_T) {
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(WA_T) word_attn_fwd_kernel(const float *__rest
             float s = -INFINITY;
             if (v < tv) {
                 s = 0.f;
-                const float *a = s_txt + q * D, *c = s_vis + v * D;
+                const float *a = s_txt + q * D, *c = s_vis + v * DP;
                 for (int d = 0; d < D; ++d) s = fmaf(a[d], c[d], s);
             }
             s_p[e] = s;
@@ -75,18 +77,23 @@ __global__ void __launch_bounds__(WA_T) word_attn_fwd_kernel(const float *__rest
         }
         __syncthreads();
         if (tid < H) {
-#pragma unroll 4
-            for (int q = 0; q < n; ++q) {
-                float o = acc[q] * s_a[q];
-                const float *pr = s_p + q * WA_TV;
-                for (int v = 0; v < tv; ++v) o = fmaf(pr[v], s_mid[v * H + tid], o);
-                acc[q] = o;
+#pragma unroll  // fully unrolled: acc[] stays in registers
+            for (int q = 0; q < WA_NQ; ++q) {
+                if (q < n) {
+                    float o = acc[q] * s_a[q];
+                    const float *pr = s_p + q * WA_TV;
+                    for (int v = 0; v < tv; ++v) o = fmaf(pr[v], s_mid[v * HP + tid], o);
+                    acc[q] = o;
+                }
             }
         }
         __syncthreads();
     }
-    if (tid < H)
-        for (int q = 0; q < n; ++q) out[((size_t)b * n + q) * H + tid] = acc[q] / s_l[q];
+    if (tid < H) {
+#pragma unroll
+        for (int q = 0; q < WA_NQ; ++q)
+            if (q < n) out[((size_t)b * n + q) * H + tid] = acc[q] / s_l[q];
+    }
     if (lse && tid < n) lse[(size_t)b * n + tid] = s_m[tid] + __logf(s_l[tid]);
 }
 
@@ -97,7 +104,8 @@ __global__ void __launch_bounds__(WA_T) word_attn_bwd_kernel(const float *__rest
                                                              int V, int n, int D, int H, float *__restrict__ gvis,
                                                              float *__restrict__ gtxt, float *__restrict__ gmid) {
     extern __shared__ __align__(16) float sm[];
-    float *s_txt = sm, *s_vis = s_txt + n * D, *s_mid = s_vis + WA_TV * D, *s_p = s_mid + WA_TV * H;
+    const int DP = D + 1, HP = H + 1;
+    float *s_txt = sm, *s_vis = s_txt + n * D, *s_mid = s_vis + WA_TV * DP, *s_p = s_mid + WA_TV * HP;
     float *s_lse = s_p + n * WA_TV, *s_dr = s_lse + n, *s_unused = s_dr + n;
     float *s_do = s_unused + n, *s_ds = s_do + n * H, *s_dt = s_ds + n * WA_TV;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -114,17 +122,17 @@ __global__ void __launch_bounds__(WA_T) word_attn_bwd_kernel(const float *__rest
     __syncthreads();
     for (int v0 = 0; v0 < V; v0 += WA_TV) {
         const int tv = min(WA_TV, V - v0);
-        for (int t = tid; t < tv * D; t += WA_T) s_vis[t] = vb[(size_t)v0 * D + t];
-        for (int t = tid; t < tv * H; t += WA_T) s_mid[t] = mb[(size_t)v0 * H + t];
+        for (int t = tid; t < tv * D; t += WA_T) s_vis[(t / D) * DP + t % D] = vb[(size_t)v0 * D + t];
+        for (int t = tid; t < tv * H; t += WA_T) s_mid[(t / H) * HP + t % H] = mb[(size_t)v0 * H + t];
         __syncthreads();
         for (int e = tid; e < n * WA_TV; e += WA_T) {
             const int q = e / WA_TV, v = e - q * WA_TV;
             float pv = 0.f, ds = 0.f;
             if (v < tv) {
                 float s = 0.f, dp = 0.f;
-                const float *a = s_txt + q * D, *c = s_vis + v * D;
+                const float *a = s_txt + q * D, *c = s_vis + v * DP;
                 for (int d = 0; d < D; ++d) s = fmaf(a[d], c[d], s);
-                const float *g = s_do + q * H, *m = s_mid + v * H;
+                const float *g = s_do + q * H, *m = s_mid + v * HP;
                 for (int h = 0; h < H; ++h) dp = fmaf(g[h], m[h], dp);
                 pv = __expf(s - s_lse[q]);
                 ds = pv * (dp - s_dr[q]);
@@ -149,7 +157,7 @@ __global__ void __launch_bounds__(WA_T) word_attn_bwd_kernel(const float *__rest
         for (int e = tid; e < n * D; e += WA_T) {  // dtxt[q][d] += sum_v dS[q][v] vis[v][d]
             const int q = e / D, d = e - q * D;
             float a = s_dt[e];
-            for (int v = 0; v < tv; ++v) a = fmaf(s_ds[q * WA_TV + v], s_vis[v * D + d], a);
+            for (int v = 0; v < tv; ++v) a = fmaf(s_ds[q * WA_TV + v], s_vis[v * DP + d], a);
             s_dt[e] = a;
         }
         __syncthreads();
