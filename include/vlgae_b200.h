@@ -228,6 +228,36 @@ int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *arg
                                           int A, int V, int B, int Q, int D, float *grad_vis, float *grad_txt, void *stream);
 
 /*
+ * Construction of the DMV score tensors: the step right before the chart,
+ * DiscriminativeNDMV._forward (reference src/model/ldndmv.py:184-209) on the projected operands of the rank-r scorer
+ * DMVFactorizedBilinear (src/model/nn/dmv_spec.py:68-76), fused with DMV1o.merge (torch_struct/distributions.py:253-265):
+ *     rule[b,h,t,d,v]  = <x1[b,h,d,v,:], x2[t,d,v,:]>, log_softmax over the vocabulary t                 (:185)
+ *     attach[b,h,c,v]  = rule[b,h,token[b,c],dir(h,c),v]  (dir: LEFT if c < h, RIGHT if c > h; 0 on the diagonal;
+ *                        neg_fill for every child of a head with head_mask[b,h] != 0)                    (:188-198)
+ *     dec[b,h,d,v,k]   = log_softmax_k(dec_score[b,h,k,d,v])                                             (:202)
+ *     root[b,c]        = log_softmax(root_score)[token[b,c]]                                             (:206-207)
+ *     merged_dec [B][n+1][2][2][2], merged_attach [B][n+1][n+1][2] = merge(dec, attach, root, one, zero) (:209)
+ * The [B][n][T][2][2] rule tensor is never written: one streaming log-sum-exp pass over the vocabulary, then the n
+ * gathered columns are recomputed while the merged tensors are written in the layout vlgae_dmv_* load.
+ *   x1 [B][n][2][2][r] = attach_scorer.project1(h_parent), x2 [T][2][2][r] = attach_scorer.project2(h_child), fp32
+ *   token [B][n] int64 in [0, T);  head_mask [B][n] bytes or NULL (cfg.function_mask);  r in {4, 8, 16, 32}
+ *   dec_score [B][n][2][2][2] = dec_scorer(h_parent, h_dec) (decision-major, before the permute);  root_score [T]
+ *   lse [B][n][2][2], root_lse [1]: written here, read by the backward;  workspace: vlgae_dmv_scores_workspace_bytes
+ * vlgae_dmv_scores_backward: gradients w.r.t. x1, x2, dec_score, root_score given the gradients w.r.t. the merged tensors
+ *   (e.g. the chart's marginals); the softmax over the vocabulary is recomputed in two streaming passes, not stored.
+ */
+size_t vlgae_dmv_scores_workspace_bytes(int B, int n);
+int vlgae_dmv_scores(const float *x1, const float *x2, const int64_t *token, const unsigned char *head_mask,
+                     const float *dec_score, const float *root_score, int B, int n, int T, int r, float one, float zero,
+                     float neg_fill, float *merged_dec, float *merged_attach, float *lse, float *root_lse, void *workspace,
+                     size_t workspace_bytes, void *stream);
+int vlgae_dmv_scores_backward(const float *x1, const float *x2, const int64_t *token, const unsigned char *head_mask,
+                              const float *dec_score, const float *root_score, const float *lse, const float *root_lse,
+                              const float *grad_merged_dec, const float *grad_merged_attach, int B, int n, int T, int r,
+                              float *grad_x1, float *grad_x2, float *grad_dec_score, float *grad_root_score, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
+/*
  * Word -> factor attention of DependencyBoxRel._forward (reference joint.py:668-673):
  *     attmap = einsum("bvd,bqd->bqv", vis_feat, txt_feat).softmax(2);  out = einsum("bqv,bvh->bqh", attmap, vis_mid)
  * one caption per CTA, the factors streamed in tiles with an online softmax (the [B][n][V] attention map is never written).

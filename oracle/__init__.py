@@ -234,3 +234,30 @@ def word_factor_attention(vis_feat, txt_feat, vis_mid):
     p = np.exp(s)
     p /= p.sum(-1, keepdims=True)
     return np.einsum("bqv,bvh->bqh", p, vis_mid)
+
+
+def dmv_scores(x1, x2, token, dec_score, root_score, head_mask=None, one=0.0, zero=NEGINF, neg=-INF):
+    """Score-tensor construction of ``DiscriminativeNDMV._forward`` (/root/reference/src/model/ldndmv.py:184-209) on the
+    projected operands of ``DMVFactorizedBilinear`` (/root/reference/src/model/nn/dmv_spec.py:68-76), followed by
+    ``merge``.  x1 [B,n,2,2,r], x2 [T,2,2,r], token [B,n], dec_score [B,n,2(decision),2,2], root_score [T].
+    Returns (attach [B,n,n,2], dec [B,n,2,2,2], root [B,n], merged_dec, merged_attach), fp32 like the reference."""
+    x1, x2, dec_score, root_score = _f32(x1), _f32(x2), _f32(dec_score), _f32(root_score)
+    token = np.asarray(token, dtype=np.int64)
+    B, n = token.shape
+
+    def lsm(x, axis):
+        mx = x.max(axis=axis, keepdims=True)
+        return x - mx - np.log(np.exp(x - mx).sum(axis=axis, keepdims=True, dtype=np.float32))
+
+    rule = lsm(np.einsum("bhdve,cdve->bhcdv", x1, x2).astype(np.float32), 2)          # :185
+    idx = np.broadcast_to(token.reshape(B, 1, n, 1, 1), (B, n, n, 2, 2))
+    prob = np.take_along_axis(rule, idx, axis=2)                                         # :188-189
+    left = np.tril(np.ones((n, n), dtype=np.float32), -1)[None, :, :, None]
+    right = np.triu(np.ones((n, n), dtype=np.float32), 1)[None, :, :, None]
+    attach = prob[..., LEFT, :] * left + prob[..., RIGHT, :] * right                     # :190-193
+    if head_mask is not None:
+        attach = np.where(np.asarray(head_mask, dtype=bool)[:, :, None, None], np.float32(neg), attach)  # :194-198
+    dec = lsm(np.transpose(dec_score, (0, 1, 3, 4, 2)), -1)                              # :202
+    root = lsm(root_score, -1)[token]                                                    # :206-207
+    md, ma = merge(dec, attach, root, one, zero)                                         # :209
+    return attach.astype(np.float32), dec.astype(np.float32), root.astype(np.float32), md, ma

@@ -33,7 +33,8 @@ int check_dmv(const float *dec, const float *attach, const int64_t *lengths, int
 }
 
 // workspace = per-sentence redo flags of the gather schedule (always) | chart slices (only when N is beyond shared memory)
-size_t redo_bytes(int B) { return ((size_t)B * 4 + 255) & ~(size_t)255; }
+// (+ the work counters of the gather launches behind the flags)
+size_t redo_bytes(int B) { return ((size_t)(B + vlgae::DMV_GATHER_COUNTERS) * 4 + 255) & ~(size_t)255; }
 
 int run_dmv(vlgae::DmvArgs &a, int passes, void *workspace, size_t workspace_bytes, void *stream) {
     if (a.B == 0) return VLGAE_OK;
@@ -45,6 +46,7 @@ int run_dmv(vlgae::DmvArgs &a, int passes, void *workspace, size_t workspace_byt
     }
     // without the flags (no workspace passed) the launch logic keeps to the frontier schedule
     a.redo = (workspace && workspace_bytes >= rb && !a.share) ? (int *)workspace : nullptr;
+    a.counter = a.redo ? a.redo + a.B : nullptr;
     a.npass = passes == 3 ? 2 : 1;
     a.first_pass = passes == 2 ? 1 : 0;
     cudaError_t e = vlgae::launch_dmv(a, passes, (cudaStream_t)stream);
@@ -416,6 +418,52 @@ int vlgae_align_max_over_factors_backward(const float *grad_maxv, const int *arg
     cudaError_t e = vlgae::launch_max_over_factors_backward(grad_maxv, argv, vis_feat, vis_mask, txt_feat, txt_mask, A, V, B, Q, D,
                                                             grad_vis, grad_txt, (cudaStream_t)stream);
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "max backward launch");
+}
+
+size_t vlgae_dmv_scores_workspace_bytes(int B, int n) {
+    if (B <= 0 || n <= 0) return 256;
+    return vlgae::dmv_scores_workspace_bytes(B, n);
+}
+
+static int check_scores(int B, int n, int T, int r, size_t workspace_bytes, const void *workspace) {
+    if (B < 0 || n < 1 || n + 1 > VLGAE_DMV_MAX_N || T < 1) return fail(VLGAE_E_INVALID, "%s", "B >= 0, 1 <= n <= 255, T >= 1 expected");
+    if (r != 4 && r != 8 && r != 16 && r != 32) return fail(VLGAE_E_INVALID, "%s", "rank must be 4, 8, 16 or 32");
+    if (B > 0 && (!workspace || workspace_bytes < vlgae::dmv_scores_workspace_bytes(B, n)))
+        return fail(VLGAE_E_WORKSPACE, "%s", "workspace too small (vlgae_dmv_scores_workspace_bytes)");
+    return VLGAE_OK;
+}
+
+int vlgae_dmv_scores(const float *x1, const float *x2, const int64_t *token, const unsigned char *head_mask,
+                     const float *dec_score, const float *root_score, int B, int n, int T, int r, float one, float zero,
+                     float neg_fill, float *merged_dec, float *merged_attach, float *lse, float *root_lse, void *workspace,
+                     size_t workspace_bytes, void *stream) {
+    if (!x1 || !x2 || !token || !dec_score || !root_score || !merged_dec || !merged_attach || !lse || !root_lse)
+        return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    int rc = check_scores(B, n, T, r, workspace_bytes, workspace);
+    if (rc) return rc;
+    if (B == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_dmv_scores(x1, x2, (const long long *)token, head_mask, dec_score, root_score, B, n, T, r, one,
+                                             zero, neg_fill, merged_dec, merged_attach, lse, root_lse, workspace,
+                                             vlgae::dmv_sm_count(), (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "dmv scores launch");
+}
+
+int vlgae_dmv_scores_backward(const float *x1, const float *x2, const int64_t *token, const unsigned char *head_mask,
+                              const float *dec_score, const float *root_score, const float *lse, const float *root_lse,
+                              const float *grad_merged_dec, const float *grad_merged_attach, int B, int n, int T, int r,
+                              float *grad_x1, float *grad_x2, float *grad_dec_score, float *grad_root_score, void *workspace,
+                              size_t workspace_bytes, void *stream) {
+    if (!x1 || !x2 || !token || !dec_score || !root_score || !lse || !root_lse || !grad_merged_dec || !grad_merged_attach ||
+        !grad_x1 || !grad_x2 || !grad_dec_score || !grad_root_score)
+        return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    int rc = check_scores(B, n, T, r, workspace_bytes, workspace);
+    if (rc) return rc;
+    if (B == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_dmv_scores_backward(x1, x2, (const long long *)token, head_mask, dec_score, root_score, lse, root_lse,
+                                                      grad_merged_dec, grad_merged_attach, B, n, T, r, grad_x1, grad_x2,
+                                                      grad_dec_score, grad_root_score, workspace, vlgae::dmv_sm_count(),
+                                                      (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "dmv scores backward launch");
 }
 
 int vlgae_word_attention(const float *vis_feat, const float *txt_feat, const float *vis_mid, int B, int V, int n, int D, int H,

@@ -38,6 +38,9 @@ struct DmvArgs {
     // follow-up frontier launch handles exactly the sentences with only[b] != 0 (null = all)
     int *redo;         // [B] or null
     const int *only;   // [B] or null
+    // gather schedule: sentences are handed out through this counter (zeroed before the launch) instead of a fixed
+    // stride, so a CTA that becomes resident late (another launch of the call still holds the SM) simply takes fewer
+    int *counter;      // or null
     // frontier kernel, both passes in one launch, inputs in pinned HOST memory: the log CTA of a sentence republishes
     // what it staged (dec, arc scores) in device memory and the max CTA of the same sentence takes it from there, so
     // every input byte crosses PCIe once.  share_flag[b] == share_epoch once sentence b is published.
@@ -61,6 +64,7 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
 // gather schedule (dmv_gather.cu): throughput regime, chart in shared memory, row-major squares of up to
 // DMV_GATHER_MAX_POSITIONS positions
 constexpr int DMV_GATHER_MAX_POSITIONS = 41;
+constexpr int DMV_GATHER_COUNTERS = 16;  // ints reserved behind the redo flags
 bool dmv_gather_fits(int cap, int passes, int smem_optin);
 cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st);
 void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather
@@ -68,6 +72,17 @@ size_t dmv_ws_slice_bytes(int N, int passes);  // what vlgae_dmv_workspace_bytes
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);
 cudaError_t launch_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, cudaStream_t st);
+// score-tensor construction (dmv_scores.cu; ldndmv.py:184-209)
+size_t dmv_scores_workspace_bytes(int B, int n);
+cudaError_t launch_dmv_scores(const float *x1, const float *x2, const long long *token, const unsigned char *head_mask,
+                              const float *dec_score, const float *root_score, int B, int n, int T, int r, float one, float zero,
+                              float neg_fill, float *mdec, float *mattach, float *lse, float *root_lse, void *ws, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_dmv_scores_backward(const float *x1, const float *x2, const long long *token, const unsigned char *head_mask,
+                                       const float *dec_score, const float *root_score, const float *lse, const float *root_lse,
+                                       const float *g_mdec, const float *g_mattach, int B, int n, int T, int r, float *g_x1,
+                                       float *g_x2, float *g_dec_score, float *g_root_score, void *ws, int sm_count, cudaStream_t st);
+int dmv_sm_count();
 cudaError_t launch_microbench(int which, int iters, float *sink, int *grid_out, int *block_out, cudaStream_t st);
 
 }  // namespace vlgae

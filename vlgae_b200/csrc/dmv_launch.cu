@@ -99,6 +99,8 @@ static cudaError_t device_info() {
     return e;
 }
 
+int dmv_sm_count() { return device_info() == cudaSuccess ? g_sm_count : 148; }
+
 size_t dmv_ws_slice_bytes(int N, int passes) { return dmv_frontier_chart_bytes(N, passes); }
 
 bool dmv_fits_smem(int N, int passes) {
@@ -225,6 +227,7 @@ static cudaError_t launch_gather_ranges(const DmvArgs &a, int passes, int lo, in
             f.workspace = nullptr; f.ws_stride = 0; f.only = nullptr;
             f.nb_lo = rlo; f.nb_hi = rhi;
             const int lane = which == 1 ? 1 + k : (k == 0 ? 0 : 3 + k);
+            if (a.counter) f.counter = a.counter + (which - 1) * 3 + k;
             cudaError_t e = launch_dmv_gather(f, which, rhi, env_gt, g_sm_count, lanes.get(lane));
             if (e != cudaSuccess) return e;
             if (!split) break;
@@ -272,6 +275,7 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 12);
     static const int env_lanes = env_int("VLGAE_DMV_LANES", 1);
     static const int env_split = env_int("VLGAE_GATHER_SPLIT", 1);
+    static const int env_dynamic = env_int("VLGAE_GATHER_DYNAMIC", 1);
     const long long items = (long long)a.B * a.npass;
     const bool bulk = env_bucket && items > 8192 && !a.share;
     const int gcap = a.N < DMV_GATHER_MAX_POSITIONS ? a.N : DMV_GATHER_MAX_POSITIONS;
@@ -284,7 +288,9 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
         // (a batch of several waves is split by length like a bulk launch: short sentences then run at 6-10 CTAs per SM)
         if (want && a.N <= DMV_GATHER_MAX_POSITIONS && gather_usable(a, passes, a.N)) {
             Lanes &lanes = g_lanes;
-            if ((e = lanes.begin(st, env_lanes && passes == 3)) != cudaSuccess) return e;
+            if (!env_dynamic) a.counter = nullptr;
+            if (a.counter && (e = cudaMemsetAsync(a.counter, 0, DMV_GATHER_COUNTERS * sizeof(int), st)) != cudaSuccess) return e;
+            if ((e = lanes.begin(st, env_lanes && passes == 3 && a.counter)) != cudaSuccess) return e;
             // (one launch pair: splitting a few waves by length adds more launch tails than the residency gains)
             e = launch_gather_ranges(a, passes, 0, a.N, env_split > 1, lanes);
             const cudaError_t e2 = lanes.end();
@@ -294,6 +300,8 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
         return launch_frontier_cap(a, passes, a.N, st);
     }
     Lanes &lanes = g_lanes;
+    if (!env_dynamic) a.counter = nullptr;
+    if (a.counter && (e = cudaMemsetAsync(a.counter, 0, DMV_GATHER_COUNTERS * sizeof(int), st)) != cudaSuccess) return e;
     if ((e = lanes.begin(st, env_lanes != 0)) != cudaSuccess) return e;
     int gather_lo = a.N + 1;  // lowest chart size handled by the gather launches
     if (sched != 1 && gather_usable(a, passes, gcap) && env_gather_bulk_lo <= gcap) {
