@@ -411,6 +411,101 @@ def alignment_leg(dev, iters=10):
     }
 
 
+def neighbour_legs(dev, iters=10):
+    """The rows either side of the chart at the cfg2 shape: score-tensor construction (ldndmv.py:184-209)
+    and the word -> factor attention (8a row a10, joint.py:668-673), each beside the reference's own torch formula on the
+    same GPU (the formula materialises the [B,n,T,2,2] rule tensor / the [B,n,V] attention map)."""
+    import torch
+
+    import oracle
+    from vlgae_b200.alignment import word_factor_attention
+    from vlgae_b200.scores import dmv_scores
+
+    res = {}
+    g = torch.Generator(device=dev).manual_seed(31)
+    B, n, T, r = BATCH_PER_GPU, MAX_LEN, 10000, 16
+    x1 = (torch.randn(B, n, 2, 2, r, generator=g, device=dev) * 0.5).requires_grad_()
+    x2 = (torch.randn(T, 2, 2, r, generator=g, device=dev) * 0.5).requires_grad_()
+    ds = torch.randn(B, n, 2, 2, 2, generator=g, device=dev).requires_grad_()
+    rs = torch.randn(T, generator=g, device=dev).requires_grad_()
+    token = torch.randint(0, T, (B, n), generator=g, device=dev)
+    gmd = torch.randn(B, n + 1, 2, 2, 2, generator=g, device=dev)
+    gma = torch.randn(B, n + 1, n + 1, 2, generator=g, device=dev)
+
+    def ref_scores():  # ldndmv.py:185-209 with torch calls (rule tensor materialised), merge through the CUDA merge kernel
+        from vlgae_b200.torch_struct import DMV1o
+
+        rule = torch.einsum("bhdve,cdve->bhcdv", x1, x2).log_softmax(2)
+        prob = rule.gather(2, token.reshape(B, 1, n, 1, 1).expand(B, n, n, 2, 2))
+        lm = torch.tril(torch.ones(n, n, device=dev), -1)[None, :, :, None]
+        rm = torch.triu(torch.ones(n, n, device=dev), 1)[None, :, :, None]
+        att = prob[..., 0, :] * lm + prob[..., 1, :] * rm
+        dec = ds.permute(0, 1, 3, 4, 2).log_softmax(-1)
+        root = rs.log_softmax(-1)[token]
+        return DMV1o.merge(dec, att, root)
+
+    md, ma = dmv_scores(x1, x2, token, ds, rs)
+    rmd, rma = ref_scores()
+    fwd_err = float((ma - rma).abs().max())
+    mine = torch.autograd.grad([md, ma], [x1, x2], [gmd, gma])
+    theirs = torch.autograd.grad([rmd, rma], [x1, x2], [gmd, gma])
+    bwd_err = max(float((a - b).abs().max() / b.abs().max().clamp_min(1.0)) for a, b in zip(mine, theirs))
+    nb = 2
+    _, _, _, _, oma = oracle.dmv_scores(x1[:nb].detach().cpu().numpy(), x2.detach().cpu().numpy(), token[:nb].cpu().numpy(),
+                                        ds[:nb].detach().cpu().numpy(), rs.detach().cpu().numpy())
+    ora_err = float(np.abs(ma[:nb].detach().cpu().numpy() - oma).max())
+    if not (fwd_err <= 2e-5 and ora_err <= 2e-5 and bwd_err <= 1e-4):
+        raise SystemExit(f"bench.py: parity gate failed on leg scores: fwd {fwd_err} oracle {ora_err} bwd {bwd_err}")
+    del rmd, rma, mine, theirs
+
+    def both(fn):
+        a, b_ = fn()
+        torch.autograd.grad([a, b_], [x1, x2, ds, rs], [gmd, gma])
+
+    ms_f = timed_launches(lambda: dmv_scores(x1.detach(), x2.detach(), token, ds.detach(), rs.detach()), iters)
+    ms_fb = timed_launches(lambda: both(lambda: dmv_scores(x1, x2, token, ds, rs)), iters)
+    ms_rf = timed_launches(lambda: ref_scores(), 3)
+    ms_rfb = timed_launches(lambda: both(ref_scores), 3)
+    res["scores"] = {
+        "workload": f"vlgae_dmv_scores B={B} n={n} n_token={T} rank={r} (ldndmv.py:184-209 + merge), forward and forward+backward",
+        "ms_forward": ms_f, "ms_forward_backward": ms_fb,
+        "torch_formula_same_gpu_ms_forward": ms_rf, "torch_formula_same_gpu_ms_forward_backward": ms_rfb,
+        "rule_tensor_bytes_not_written": B * n * T * 4 * 4,
+        "parity": {"max_abs_vs_torch_formula": fwd_err, "max_abs_vs_oracle": ora_err, "grad_max_rel_vs_torch_autograd": bwd_err},
+        "gpu_launches_per_call": {"forward": 3, "backward": 4},
+    }
+    del x1, x2, ds, rs, gmd, gma
+    # ---- a10
+    V, D, H = 36 + 36 * 36 + 36 + 1, 128, 256
+    vis = (torch.randn(B, V, D, generator=g, device=dev) * 0.2).requires_grad_()
+    txt = (torch.randn(B, n, D, generator=g, device=dev) * 0.2).requires_grad_()
+    mid = torch.randn(B, V, H, generator=g, device=dev).requires_grad_()
+    go = torch.randn(B, n, H, generator=g, device=dev)
+
+    def ref_att():  # joint.py:670-673
+        return torch.einsum("bqv,bvh->bqh", torch.einsum("bvd,bqd->bqv", vis, txt).softmax(2), mid)
+
+    out = word_factor_attention(vis, txt, mid)
+    want = oracle.word_factor_attention(vis[:4].detach().cpu().numpy(), txt[:4].detach().cpu().numpy(), mid[:4].detach().cpu().numpy())
+    a_err = float(np.abs(out[:4].detach().cpu().numpy() - want).max())
+    ga = torch.autograd.grad(out, [vis, txt, mid], go)
+    gr = torch.autograd.grad(ref_att(), [vis, txt, mid], go)
+    ab_err = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-3)) for a, b in zip(ga, gr))
+    if not (a_err <= 1e-4 and ab_err <= 1e-3):
+        raise SystemExit(f"bench.py: parity gate failed on leg word_attention: fwd {a_err} bwd {ab_err}")
+    ms_f = timed_launches(lambda: word_factor_attention(vis.detach(), txt.detach(), mid.detach()), iters)
+    ms_fb = timed_launches(lambda: torch.autograd.grad(word_factor_attention(vis, txt, mid), [vis, txt, mid], go), iters)
+    ms_rf = timed_launches(lambda: ref_att(), iters)
+    ms_rfb = timed_launches(lambda: torch.autograd.grad(ref_att(), [vis, txt, mid], go), iters)
+    res["word_attention"] = {
+        "workload": f"vlgae_word_attention B={B} V={V} n={n} D={D} H={H} (joint.py:668-673)",
+        "ms_forward": ms_f, "ms_forward_backward": ms_fb,
+        "torch_formula_same_gpu_ms_forward": ms_rf, "torch_formula_same_gpu_ms_forward_backward": ms_rfb,
+        "parity": {"max_abs_vs_oracle": a_err, "grad_max_rel_vs_torch_autograd": ab_err},
+    }
+    return res
+
+
 # ----------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------
@@ -827,6 +922,10 @@ def run_b200_arm(args):
         a_ms, a_red, a_bwd = max_over_ranks(align["ms"], align["reduced"]["ms"], align["backward"]["ms"])
         align["max_over_ranks_ms"] = {"logits": a_ms, "reduced": a_red, "backward": a_bwd, "ranks": world}
 
+    neighbours = None
+    if not args.no_align and rank == 0:
+        neighbours = neighbour_legs(dev, 5 if getattr(args, "quick", False) else 10)
+
     if rank == 0:
         wc = work_counts(L0)
         per_launch_s = elapsed_ms * 1e-3 / args.steps
@@ -866,6 +965,8 @@ def run_b200_arm(args):
             line["legs"] = legs
         if align is not None:
             line["alignment"] = align
+        if neighbours is not None:
+            line["neighbours"] = neighbours
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -227,7 +227,9 @@ struct AlignSmem {
 template <int KB, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     constexpr bool BULK = MODE >= 1;      // a staged [query][128 factors] tile per epilogue team
-    constexpr bool REDUCE = MODE == 2;
+    constexpr bool REDUCE = MODE >= 2;
+    constexpr bool MAXQ = MODE == 3;      // REDUCE + the max over the queries (its own instantiation: the plain reduction
+                                          // stays free of the extra registers, which spilled under the 96-register cap)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int nq = p.nq, S = p.stages, NB = p.out_bufs;
     const uint32_t chunk_b = (uint32_t)nq * 128u;         // one (part, k-block) chunk of a caption tile
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                             int aq = 0;
                             unsigned long long *s_pq = reinterpret_cast<unsigned long long *>(
                                 reinterpret_cast<uint8_t *>(s_run) + p.run_bytes - 2048) + team * TILE_M + quad * 32 + lane;
-                            if (p.maxq) {
+                            if constexpr (MAXQ) {
 #pragma unroll
                                 for (int k = 0; k < MAXCH; ++k) {
                                     const int c0 = half * 16 + k * 4 * kEpiWarps;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                             // (ordered value bits << 32 | ~v), so equal values keep the smaller factor index
                             float *tile_out = s_out + (size_t)team * out_tile_floats;
                             named_bar(1 + team, 32 * kTeamWarps);  // the previous tile's rows have been reduced
-                            if (p.maxq && half == 0) {
+                            if (MAXQ && half == 0) {
                                 const unsigned long long o = *s_pq;
                                 const float m1 = __uint_as_float((uint32_t)(o >> 32));
                                 const int a1 = (int)(uint32_t)o;
@@ -766,6 +768,7 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
         kern<<<grid, kThreads, smem_bytes, st>>>(a);
         return cudaGetLastError();
     };
+    if (reduce && a.maxq) return pl.KB == 1 ? launch(align_gemm_kernel<1, 3>) : launch(align_gemm_kernel<2, 3>);
     if (reduce) return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
     if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, 1>) : launch(align_gemm_kernel<1, 0>);
     return a.bulk ? launch(align_gemm_kernel<2, 1>) : launch(align_gemm_kernel<2, 0>);
