@@ -45,6 +45,7 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--func", required=True, help="substring of the mangled kernel name (template arguments)")
     ap.add_argument("--kernel", default=None, help="ncu -k filter (regex:...)")
+    ap.add_argument("--skip", type=int, default=0, help="index of the launch inside the report (ncu --launch-skip)")
     ap.add_argument("--src", default="vlgae_b200/csrc/dmv_gather.cu")
     ap.add_argument("--lib", default=os.path.join(ROOT, "vlgae_b200", "libvlgae_b200.so"))
     ap.add_argument("--top", type=int, default=40)
@@ -53,6 +54,8 @@ def main():
     cmd = ["ncu", "-i", args.report, "--page", "source", "--csv"]
     if args.kernel:
         cmd += ["-k", args.kernel]
+    if args.skip:
+        cmd += ["--launch-skip", str(args.skip), "--launch-count", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)

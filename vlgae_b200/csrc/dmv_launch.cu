@@ -256,6 +256,8 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     a.nb_lo = 0; a.nb_hi = a.N;
     static const int env_no_off = env_int("VLGAE_DMV_NO_OFFSETS", 0);
     a.no_offsets = env_no_off;
+    static const int env_retry = env_int("VLGAE_DMV_RETRY_ABOVE", 0);
+    a.retry_above = (float)env_retry;
     static const int env_sched = [] {
         const char *v = getenv("VLGAE_DMV_KERNEL");
         return !v ? 0 : (v[0] == 'f' ? 1 : (v[0] == 'g' ? 2 : 0));
