@@ -503,6 +503,59 @@ def neighbour_legs(dev, iters=10):
         "torch_formula_same_gpu_ms_forward": ms_rf, "torch_formula_same_gpu_ms_forward_backward": ms_rfb,
         "parity": {"max_abs_vs_oracle": a_err, "grad_max_rel_vs_torch_autograd": ab_err},
     }
+    del vis, txt, mid, go, out, ga, gr
+    torch.cuda.empty_cache()
+    # ---- f4: visual factor features, relation MLP collapsed (box_rel.py:42-52 + joint.py:140-179)
+    from vlgae_b200.vis_factors import vis_feat_unprune_collapsed
+
+    nb, F = 36, 2048
+
+    class MLP(torch.nn.Module):  # attribute layout of the reference's MLP (nn/common.py:23-51), dropout 0 as in vlgae.yaml:31
+        def __init__(self, n_in, n_hidden):
+            super().__init__()
+            self.linear = torch.nn.Linear(n_in, n_hidden)
+            self.activation = torch.nn.LeakyReLU()
+            self.dropout = torch.nn.Identity()
+
+        def forward(self, x):
+            return self.dropout(self.activation(self.linear(x)))
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.img_feat, self.use_attr = True, True
+            self.box_fc, self.rel_fc, self.attr_fc = MLP(2 * F, H), MLP(2 * F, H), MLP(2 * F, H)
+
+    torch.manual_seed(5)
+    enc = Enc().to(dev)
+    pre = torch.nn.Linear(H, 128, bias=False).to(dev)
+    feat = torch.randn(B, nb, F, generator=g, device=dev)
+    bmask = torch.rand(B, nb, generator=g, device=dev) > 0.1
+
+    def ref_vis():  # box_rel.py:35-52 + joint.py:144-177 with the reference's torch calls (pair tensor materialised)
+        inputs = torch.cat([feat, feat.mean(1, keepdim=True).expand(-1, nb, -1)], dim=-1)
+        rel = enc.rel_fc((inputs.unsqueeze(1) + inputs.unsqueeze(2)) / 2).view(B, -1, H)
+        box, attr = enc.box_fc(inputs), enc.attr_fc(inputs)
+        mid_ = torch.cat([box, rel, attr, box.mean(1, keepdim=True)], dim=1)
+        return pre(mid_), mid_
+
+    with torch.no_grad():
+        v_mine, m_mine, _split, mid_mine = vis_feat_unprune_collapsed(enc, pre, feat, bmask, return_mid=True)
+        v_ref, mid_ref = ref_vis()
+        v_err = float((v_mine.rename(None) - v_ref).abs().max())
+        m_err = float((mid_mine - mid_ref).abs().max())
+        if not (v_err <= 1e-3 and m_err <= 1e-3):
+            raise SystemExit(f"bench.py: parity gate failed on leg vis_factors: vis {v_err} mid {m_err}")
+        del v_ref, mid_ref
+        ms_mine = timed_launches(lambda: vis_feat_unprune_collapsed(enc, pre, feat, bmask), iters)
+        ms_ref = timed_launches(lambda: ref_vis(), 3)
+    res["vis_factors"] = {
+        "workload": f"visual factor features B={B} boxes={nb} F={2 * F} H={H} -> vis [B,{nb + nb * nb + nb + 1},128] "
+                    "(box_rel.py:42-52 + joint.py:140-179): three per-box library GEMMs + vlgae_vis_factors + the 256->128 Linear",
+        "ms_forward": ms_mine, "torch_formula_same_gpu_ms_forward": ms_ref,
+        "pair_tensor_bytes_not_formed": B * nb * nb * 2 * F * 4,
+        "parity": {"vis_max_abs_vs_torch_formula": v_err, "mid_max_abs_vs_torch_formula": m_err},
+    }
     return res
 
 

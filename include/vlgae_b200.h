@@ -273,6 +273,24 @@ int vlgae_word_attention_backward(const float *vis_feat, const float *txt_feat, 
                                   const float *lse, const float *grad_out, int B, int V, int n, int D, int H,
                                   float *grad_vis, float *grad_txt, float *grad_mid, void *stream);
 
+/*
+ * Visual factor features with the relation MLP collapsed.  Reference:
+ * VisBoxRelSimpleEncoder.forward (src/model/vis_encoder/box_rel.py:42-52) runs rel_fc = LeakyReLU(Linear(.)) on the n^2
+ * pairwise means (x_i + x_j) / 2 of the box inputs, and vis_feat_unprune (src/model/joint.py:140-179) concatenates
+ * [box | rel | attr | img] along the factor axis and builds the factor mask.  The Linear is affine, so
+ * W ((x_i + x_j) / 2) + b = (u_i + u_j) / 2 with u = rel_fc.linear(inputs) computed once per box by the caller.
+ *   u_box, u_rel [B][n][H]: pre-activations box_fc.linear(inputs), rel_fc.linear(inputs);  u_attr [B][n][H] or NULL (use_attr)
+ *   box_mask [B][n] bytes;  has_img: append encoded["box"].mean(1) as the last factor (cfg.add_image);  slope: LeakyReLU
+ *   mid  [B][V][H], V = n + n^2 (+ n) (+ 1):  box: lrelu(u_box[i]);  rel (i, j) at n + i n + j: lrelu((u_rel[i] + u_rel[j]) / 2);
+ *        attr: lrelu(u_attr[i]);  img: mean_i lrelu(u_box[i])
+ *   mask [B][V] bytes: box_mask | box_mask[i] & box_mask[j] & j > i | box_mask | 1        (joint.py:147-172)
+ * vlgae_vis_factors_backward: grad_mid [B][V][H] -> gradients of the per-box pre-activations (grad_attr NULL iff u_attr NULL).
+ */
+int vlgae_vis_factors(const float *u_box, const float *u_rel, const float *u_attr, const unsigned char *box_mask, int B, int n,
+                      int H, int has_img, float slope, float *mid, unsigned char *mask, void *stream);
+int vlgae_vis_factors_backward(const float *u_box, const float *u_rel, const float *u_attr, const float *grad_mid, int B, int n,
+                               int H, int has_img, float slope, float *grad_box, float *grad_rel, float *grad_attr, void *stream);
+
 /* out[b][...] = g[b] * in[b][...]  (inner = elements per sentence): backward of partition / max. */
 int vlgae_scale_rows(const float *in, const float *g, int B, size_t inner, float *out, void *stream);
 

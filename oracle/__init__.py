@@ -261,3 +261,29 @@ def dmv_scores(x1, x2, token, dec_score, root_score, head_mask=None, one=0.0, ze
     root = lsm(root_score, -1)[token]                                                    # :206-207
     md, ma = merge(dec, attach, root, one, zero)                                         # :209
     return attach.astype(np.float32), dec.astype(np.float32), root.astype(np.float32), md, ma
+
+
+def vis_factors(inputs, w_box, b_box, w_rel, b_rel, w_attr, b_attr, box_mask, add_image=True, slope=0.01):
+    """``VisBoxRelSimpleEncoder.forward`` (/root/reference/src/model/vis_encoder/box_rel.py:42-52) followed by the
+    concatenation and mask of ``vis_feat_unprune`` (/root/reference/src/model/joint.py:140-172), LITERALLY: the relation
+    MLP is applied to the n^2 pairwise means of the inputs (no collapse -- this is the checker).
+    inputs [B, n, F]; w_* [H, F], b_* [H]; returns (mid [B, V, H] float32, mask [B, V] bool)."""
+    x = _f32(inputs)
+    B, n, _ = x.shape
+
+    def mlp(t, w, b):
+        y = (t.astype(np.float64) @ np.asarray(w, dtype=np.float64).T + np.asarray(b, dtype=np.float64))
+        return np.where(y > 0, y, y * slope)
+
+    pair = (x[:, None, :, :].astype(np.float64) + x[:, :, None, :]) / 2          # box_rel.py:45
+    rel = mlp(pair, w_rel, b_rel).reshape(B, n * n, -1)                           # :46-48
+    box = mlp(x, w_box, b_box)                                                    # :50
+    feats, masks = [box, rel], []
+    bm = np.asarray(box_mask, dtype=bool)
+    rel_mask = np.triu(bm[:, None, :] & bm[:, :, None], 1).reshape(B, -1)         # joint.py:151-155
+    masks = [bm, rel_mask]
+    if w_attr is not None:
+        feats.append(mlp(x, w_attr, b_attr)); masks.append(bm)                    # :161-164
+    if add_image:
+        feats.append(box.mean(1, keepdims=True)); masks.append(np.ones((B, 1), dtype=bool))  # :165-176
+    return np.concatenate(feats, 1).astype(np.float32), np.concatenate(masks, 1)

@@ -59,6 +59,10 @@ PROTOTYPES = {
                                      c_void_p]),
     "vlgae_word_attention_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                               c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vlgae_vis_factors": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                  c_void_p]),
+    "vlgae_vis_factors_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]),
     "vlgae_scale_rows": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "vlgae_microbench_mufu": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     "vlgae_microbench_fp32": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),

@@ -69,5 +69,10 @@ cudaError_t launch_word_attention(const float *vis, const float *txt, const floa
 cudaError_t launch_word_attention_backward(const float *vis, const float *txt, const float *mid, const float *out,
                                            const float *lse, const float *gout, int B, int V, int n, int D, int H, float *gvis,
                                            float *gtxt, float *gmid, cudaStream_t st);
+// visual factor features with the relation MLP collapsed (vis_factors.cu; vis_encoder/box_rel.py:42-52, joint.py:140-179)
+cudaError_t launch_vis_factors(const float *u_box, const float *u_rel, const float *u_attr, const uint8_t *box_mask, int B, int n,
+                               int H, int has_img, float slope, float *mid, uint8_t *mask, cudaStream_t st);
+cudaError_t launch_vis_factors_backward(const float *u_box, const float *u_rel, const float *u_attr, const float *g_mid, int B, int n,
+                                        int H, int has_img, float slope, float *g_box, float *g_rel, float *g_attr, cudaStream_t st);
 
 }  // namespace vlgae

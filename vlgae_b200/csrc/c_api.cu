@@ -488,6 +488,26 @@ int vlgae_word_attention_backward(const float *vis_feat, const float *txt_feat, 
     return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "word attention backward launch");
 }
 
+int vlgae_vis_factors(const float *u_box, const float *u_rel, const float *u_attr, const unsigned char *box_mask, int B, int n,
+                      int H, int has_img, float slope, float *mid, unsigned char *mask, void *stream) {
+    if (!u_box || !u_rel || !box_mask || !mid || !mask) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if (B < 0 || n < 1 || n > 1024 || H < 1) return fail(VLGAE_E_INVALID, "%s", "B >= 0, 1 <= n <= 1024, H >= 1 expected");
+    if (B == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_vis_factors(u_box, u_rel, u_attr, box_mask, B, n, H, has_img, slope, mid, mask, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "vis factors launch");
+}
+
+int vlgae_vis_factors_backward(const float *u_box, const float *u_rel, const float *u_attr, const float *grad_mid, int B, int n,
+                               int H, int has_img, float slope, float *grad_box, float *grad_rel, float *grad_attr, void *stream) {
+    if (!u_box || !u_rel || !grad_mid || !grad_box || !grad_rel) return fail(VLGAE_E_INVALID, "%s", "null pointer");
+    if ((u_attr == nullptr) != (grad_attr == nullptr)) return fail(VLGAE_E_INVALID, "%s", "grad_attr must be given exactly when u_attr is");
+    if (B < 0 || n < 1 || n > 1024 || H < 1) return fail(VLGAE_E_INVALID, "%s", "B >= 0, 1 <= n <= 1024, H >= 1 expected");
+    if (B == 0) return VLGAE_OK;
+    cudaError_t e = vlgae::launch_vis_factors_backward(u_box, u_rel, u_attr, grad_mid, B, n, H, has_img, slope, grad_box, grad_rel,
+                                                       grad_attr, (cudaStream_t)stream);
+    return e == cudaSuccess ? VLGAE_OK : cuda_fail(e, "vis factors backward launch");
+}
+
 static int microbench(int which, int iters, float *ms_host, double *ops_host, void *stream) {
     if (!ms_host || !ops_host || iters < 1) return fail(VLGAE_E_INVALID, "%s", "bad microbench arguments");
     cudaStream_t st = (cudaStream_t)stream;
