@@ -333,6 +333,18 @@ def alignment_leg(dev, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    # the reference's own layout: dense rows of V = 1369 floats (odd: rows are only 4-byte aligned, no bulk stores)
+    for _ in range(2):
+        dense = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        dense = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dense = e0.elapsed_time(e1) / iters
+    dense_equal = bool(dense.is_contiguous() and torch.equal(dense, out))
+    del dense
     # parity on a corner block against the oracle (numpy fp32 restatement of joint.py:406-419)
     nb, na = 2, 3
     want = oracle.gather_logit_simple(vis[:na].cpu().numpy(), vm[:na].cpu().numpy(), txt[:nb].cpu().numpy(),
@@ -403,6 +415,8 @@ def alignment_leg(dev, iters=10):
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu capture, profiles/r1_align_kernel.txt)
                      "traffic": 7.61e9, "peak_source": src, "algorithmic_bytes_per_launch": out_bytes,
                      "kernel": "align_gemm_kernel (+ align_pack_kernel x2)"},
+        "dense_layout": {"what": "pad_rows=False: the reference's contiguous [B,A,Q,V] layout (rows of 1369 floats, 4-byte aligned)",
+                         "ms": ms_dense, "frac": out_bytes / (ms_dense * 1e-3) / 1e9 / peak, "equal_to_padded_result": dense_equal},
         "tensor_tflops_issued": 3 * 2.0 * A * B * Q * V * D / (ms * 1e-3) / 1e12,
         "parity": {"mask_pattern_equal": bool(((got == -1e20) == masked).all()), "max_abs_err_vs_fp32_oracle": err},
         "gpu_launches_per_call": 3,

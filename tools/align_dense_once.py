@@ -1,0 +1,18 @@
+"""tools/align_dense_once.py -- a few launches of the alignment logits on the reference's dense layout (for ncu captures)."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vlgae_b200.alignment import gather_logit_simple
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(99)
+A = B = 128
+Q, V, D = 82, 1369, 128
+vis = torch.randn(A, V, D, generator=g, device=dev)
+txt = torch.randn(B, Q, D, generator=g, device=dev)
+vm = torch.rand(A, V, generator=g, device=dev) > 0.1
+tm = torch.rand(B, Q, generator=g, device=dev) > 0.1
+pad = len(sys.argv) > 1 and sys.argv[1] == "pad"
+for _ in range(3):
+    out = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=pad)
+torch.cuda.synchronize()

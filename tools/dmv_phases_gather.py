@@ -13,8 +13,15 @@ from vlgae_b200._lib import check, lib  # noqa: E402
 
 dev = torch.device("cuda:0")
 check(lib().vlgae_dmv_set_schedule(2), "schedule")
-for B, n, ragged in [(1, 40, None), (128, 40, "cfg2"), (4096, 40, None), (512, 32, None), (512, 20, None)]:
+# default shapes, or "B,n,len" triples on the command line (all sentences of length len inside tensors padded to n words)
+cases = [(1, 40, None, None), (128, 40, "cfg2", None), (4096, 40, None, None), (512, 32, None, None), (512, 20, None, None)]
+if len(sys.argv) > 1:
+    cases = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
+    cases = [(B, n, None, ln) for B, n, ln in cases]
+for B, n, ragged, fixed_len in cases:
     md, ma, L = synth(B, n, 7, ragged)
+    if fixed_len is not None:
+        L[:] = fixed_len
     tmd, tma, tL = [torch.from_numpy(x).to(dev) for x in (md, ma, L)]
     out = ops.ParseBuffers(B, n + 1, dev)
     buf = torch.zeros(16, dtype=torch.int64, device=dev)

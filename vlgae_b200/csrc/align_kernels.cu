@@ -224,7 +224,7 @@ struct AlignSmem {
 // MODE 0: direct stores (rows not 16-byte aligned)   1: staged tile + bulk TMA stores   2: no [B,A,Q,V] output at all --
 // the epilogue reduces every query row to its maximum over the factors (and the arg-max) and merges the v-tiles with a
 // 64-bit atomicMax (gather_logit_reduced, joint.py:421-432: the 7.4 GB tensor is never materialised)
-template <int KB, int MODE>
+template <int KB, int MODE, bool SHIFT = false>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     constexpr bool BULK = MODE >= 1;      // a staged [query][128 factors] tile per epilogue team
     constexpr bool REDUCE = MODE >= 2;
@@ -240,11 +240,20 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     constexpr uint32_t A_COLS = 64u * KB;  // tensor-memory columns of one image tile (hi + lo, 32 per 64-wide k-block)
     uint8_t *s_ring = smem;
     float *s_out = reinterpret_cast<float *>(smem + (size_t)S * slot_bytes);
-    const size_t out_tile_floats = (size_t)p.out_rows * TILE_M;  // rows = min(nq, Q): the queries a tile can hold
+    // rows = min(nq, Q): the queries a tile can hold.  TS = row stride of a staged tile: 128 floats, or 132 in the SHIFTED
+    // layout used when the rows of `out` are not 16-byte aligned (odd V, no padding): row r is staged k_r floats to the
+    // right, k_r = word offset of its global destination modulo 4, so that shared and global addresses agree modulo 16 and
+    // all but <= 3 leading / trailing floats of the row still leave through one bulk copy
+    // (SHIFT is a template parameter: with a run-time stride the 16 staging stores per chunk lose their immediate offsets
+    // and the aligned layout went from 1.76 to 3.2 ms)
+    static_assert(!SHIFT || MODE == 1, "the shifted staging belongs to the materialising bulk-store mode");
+    constexpr int TS = SHIFT ? TILE_M + 4 : TILE_M;
+    constexpr bool shifted = SHIFT;
+    const size_t out_tile_floats = (size_t)p.out_rows * TS;
     float *s_neg = s_out + (size_t)NB * out_tile_floats;  // BULK: one row of -INF, the source of masked query rows
     // REDUCE: running (ordered max bits << 32 | ~arg-max) per (team, caption of the chunk, query); 0 = nothing seen yet
     unsigned long long *s_run = reinterpret_cast<unsigned long long *>(s_neg + TILE_M);
-    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + (size_t)S * slot_bytes + (BULK ? (size_t)NB * p.out_rows * 512 + 512 : 0) +
+    AlignSmem *sb = reinterpret_cast<AlignSmem *>(smem + (size_t)S * slot_bytes + (BULK ? (size_t)NB * p.out_rows * TS * 4 + 512 : 0) +
                                                   (REDUCE ? (size_t)p.run_bytes : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -578,19 +587,24 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                             // the warps spend 1 instruction per 4 B on shared memory only. NB tiles alternate, so the
                             // engine drains one while the next is staged.
                             float *tile_out = s_out + (size_t)team * out_tile_floats;
+                            float *tile_row0 = orow - (quad * 32 + lane);  // global address of (query 0, first factor of the tile)
+                            // word offset modulo 4 of query row r's destination: (k0 + r * vm) & 3
+                            const uint32_t k0 = shifted ? (uint32_t)(reinterpret_cast<uintptr_t>(tile_row0) >> 2) & 3u : 0u;
+                            const uint32_t vm = shifted ? (V & 3u) : 0u;
                             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                             named_bar(1 + team, 32 * kTeamWarps);  // every issuer's copies out of this tile have been read
 #pragma unroll
                             for (int k = 0; k < MAXCH; ++k) {
                                 const int c0 = half * 16 + k * 4 * kEpiWarps;
-                                float *slot = tile_out + (size_t)c0 * TILE_M + quad * 32 + lane;
+                                float *slot = tile_out + (size_t)c0 * TS + quad * 32 + lane;
+                                const uint32_t kc = k0 + (uint32_t)c0 * vm;
                                 if (c0 + 16 <= q_lim) {
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                                    for (int j = 0; j < 16; ++j) slot[j * TS + ((kc + j * vm) & 3u)] = __uint_as_float(r[k][j]);
                                 } else {
 #pragma unroll
                                     for (int j = 0; j < 16; ++j)
-                                        if (c0 + j < q_lim) slot[j * TILE_M] = __uint_as_float(r[k][j]);
+                                        if (c0 + j < q_lim) slot[j * TS + ((kc + j * vm) & 3u)] = __uint_as_float(r[k][j]);
                                 }
                             }
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -601,8 +615,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                             if (row < q_lim && !(p.debug & 1)) {
                                 const uint32_t w32 = row < 32 ? mb_cur.x : (row < 64 ? mb_cur.y : (row < 96 ? mb_cur.z : mb_cur.w));
                                 const bool keep = (w32 >> (row & 31)) & 1u;
-                                bulk_s2g(orow - (quad * 32 + lane) + (size_t)row * V, keep ? tile_out + (size_t)row * TILE_M : s_neg,
-                                         min(TILE_M, p.ldv - (vt0 + t) * TILE_M) * 4);
+                                const int len = min(TILE_M, p.ldv - (vt0 + t) * TILE_M);
+                                float *dst = tile_row0 + (size_t)row * V;
+                                if (!shifted) {
+                                    bulk_s2g(dst, keep ? tile_out + (size_t)row * TS : s_neg, len * 4);
+                                } else {
+                                    const int kr = (int)((k0 + (uint32_t)row * vm) & 3u), h = (4 - kr) & 3;  // h floats up to alignment
+                                    const float *src = tile_out + (size_t)row * TS + kr;                     // element e at src[e]
+                                    const int nb = len > h ? ((len - h) & ~3) : 0;
+                                    if (nb > 0) bulk_s2g(dst + h, keep ? src + h : s_neg, nb * 4);
+                                    for (int e = 0; e < min(h, len); ++e) __stcs(dst + e, keep ? src[e] : neg);
+                                    for (int e = h + nb; e < len; ++e) __stcs(dst + e, keep ? src[e] : neg);
+                                }
                             }
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
@@ -727,7 +751,10 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     a.maxv = maxv; a.argv = argv; a.maxq = maxq; a.argq = argq;
     if (maxq && pl.QT != 1) return cudaErrorInvalidValue;  // the max over the queries lives inside one query tile
     // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
-    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || ((bk ? atoi(bk) : 1) && (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0)); }
+    // (rows that are not 16-byte aligned -- odd V without padding, the reference's own layout -- use the shifted staging)
+    const bool aligned_rows = (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || (bk ? atoi(bk) != 0 : true); }
+    a.tile_stride = (reduce || aligned_rows) ? TILE_M : TILE_M + 4;
     // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
     size_t slot_bytes = (size_t)2 * pl.KB * pl.nq * 128;
     if (slot_bytes < (size_t)CHUNK_A) slot_bytes = CHUNK_A;
@@ -743,7 +770,7 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
         b_per = (B + bch - 1) / bch;
         run_bytes = (((size_t)2 * b_per * Q * 8 + 15) & ~(size_t)15) + 2048;  // + exchange slots of the max over the queries
     }
-    const size_t out_tile_bytes = (size_t)out_rows * 512, fixed = sizeof(AlignSmem) + 64 + 512 + run_bytes;
+    const size_t out_tile_bytes = (size_t)out_rows * a.tile_stride * 4, fixed = sizeof(AlignSmem) + 64 + 512 + run_bytes;
     int out_bufs = a.bulk ? 2 : 0;
     if (out_bufs == 2 && ((size_t)g_align_smem - fixed - 2 * out_tile_bytes) / slot_bytes < 2) out_bufs = 1;
     int stages = (int)(((size_t)g_align_smem - fixed - out_bufs * out_tile_bytes) / slot_bytes);
@@ -770,6 +797,7 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     };
     if (reduce && a.maxq) return pl.KB == 1 ? launch(align_gemm_kernel<1, 3>) : launch(align_gemm_kernel<2, 3>);
     if (reduce) return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
+    if (a.bulk && a.tile_stride != TILE_M) return pl.KB == 1 ? launch(align_gemm_kernel<1, 1, true>) : launch(align_gemm_kernel<2, 1, true>);
     if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, 1>) : launch(align_gemm_kernel<1, 0>);
     return a.bulk ? launch(align_gemm_kernel<2, 1>) : launch(align_gemm_kernel<2, 0>);
 }

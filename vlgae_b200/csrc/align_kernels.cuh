@@ -17,6 +17,7 @@ struct AlignArgs {
     int KB, VT, QT, nq;  // k-blocks of 64, v-tiles, q-tiles, padded queries per tile (multiple of 16, <= 128)
     int BCH, stages, out_bufs, out_rows, teams, split, debug, bulk;
     uint32_t slot_bytes;
+    int tile_stride;  // floats per row of a staged output tile: 128, or 132 when the rows of `out` are not 16-byte aligned
     float neg;
     float *maxv;  // MODE 2: [B][A][Q] max over the factors
     int *argv;    // MODE 2: [B][A][Q] first arg-max, or null

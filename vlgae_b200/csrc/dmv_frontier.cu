@@ -227,16 +227,22 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
 #pragma unroll
         for (int q = 0; q < 4; ++q) { ax[k][q] = (q & 1) ? 0.f : NEG_BIG; al[k][q] = ax[k][q]; ar[k][q] = ax[k][q]; }
     }
+    // ONE phase (one barrier) per width.  After phase s - 1 both the incomplete and the complete items of width s are final:
+    // the complete item of a span needs, as its last-arriving term, the incomplete item of the SAME span (split r = i for
+    // CL, r = j for CR), which the cell's owner has just produced itself -- so the owner folds that term in and finalises
+    // CL / CR right behind IL / IR, without a barrier in between.  Phase s then folds I(s) into the complete targets of
+    // width s + 1 .. 2 s - 1 and C(s) into the targets of width s + 1 .. 2 s + 1 (the two phases A(s), B(s) of the
+    // two-barrier schedule, minus the same-span terms), and finalises width s + 1.
 #pragma unroll 1
-    for (int s = 0; s <= len; ++s) {
+    for (int s = 0; s < len; ++s) {
         const int Ds = dbase(s, Nb);
-        if (s >= 1) {
-            // phase A(s): incomplete items of width s are final
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const int w = ow[k], i = oi[k];
-                if ((unsigned)(w - s) < (unsigned)s) {  // s <= w <= 2 s - 1
-                    const int Dd = dbase(w - s, Nb), j = i + w;
+        for (int k = 0; k < CPT; ++k) {
+            const int w = ow[k], i = oi[k];
+            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
+                const int j = i + w;
+                if (w <= 2 * s - 1) {  // terms whose later operand is an incomplete item of width s (s + 1 <= w <= 2 s - 1)
+                    const int Dd = dbase(w - s, Nb);
                     const float l3 = c.CL[Dd + i].y;          // CL[i, j-s].NO
                     const float2 i3 = c.IL[Ds + j - s];        // IL[j-s, j]
                     const float2 i4 = c.IR[Ds + i];            // IR[i, i+s]
@@ -245,24 +251,8 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     lse1(al[k][2], al[k][3], l3 + i3.y);
                     lse1(ar[k][0], ar[k][1], i4.x + r4);
                     lse1(ar[k][2], ar[k][3], i4.y + r4);
-                    if (w == s) {
-                        const int cc = Nb + tid + k * H;
-                        float2 vr = make_float2(lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
-                        if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);  // single-root mask, dmv.py:63
-                        c.CL[cc] = make_float2(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]));
-                        c.CR[cc] = vr;
-                    }
                 }
-            }
-            blk_sync<NT>();
-        }
-        if (s == len) break;
-        // phase B(s): complete items of width s are final
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            const int w = ow[k], i = oi[k];
-            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
-                const int De = dbase(w - 1 - s, Nb), j = i + w;
+                const int De = dbase(w - 1 - s, Nb);
                 // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
                 const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
                 if (w - 1 - s != s) {
@@ -272,14 +262,6 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                 } else {
                     lse1(ax[k][0], ax[k][1], la.y + ra.x);
                     lse1(ax[k][2], ax[k][3], la.x + ra.y);
-                }
-                if (w == s + 1) {
-                    const int cc = Nb + tid + k * H;
-                    const float xl = lse_fin(ax[k][0], ax[k][1]), xr = lse_fin(ax[k][2], ax[k][3]);
-                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
-                    c.IL[cc] = make_float2(xl + arcl.x, xl + arcl.y);
-                    c.IR[cc] = make_float2(xr + arcr.x, xr + arcr.y);
-                    c.X[cc] = make_float2(xl, xr);
                 }
                 if (w <= 2 * s) {
                     const int Dd = De + Nb - (w - 1 - s);   // dbase(w - s)
@@ -291,6 +273,23 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
                     lse1(al[k][2], al[k][3], l3 + i3.y);
                     lse1(ar[k][0], ar[k][1], i4.x + r4);
                     lse1(ar[k][2], ar[k][3], i4.y + r4);
+                }
+                if (w == s + 1) {  // this span's items are complete now: IL / IR, then CL / CR through the same-span terms
+                    const int cc = Nb + tid + k * H;
+                    const float xl = lse_fin(ax[k][0], ax[k][1]), xr = lse_fin(ax[k][2], ax[k][3]);
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                    const float2 il = make_float2(xl + arcl.x, xl + arcl.y), ir = make_float2(xr + arcr.x, xr + arcr.y);
+                    const float l3 = c.CL[i].y, r4 = c.CR[j].y;  // CL[i, i].NO, CR[j, j].NO (width-0 cells)
+                    lse1(al[k][0], al[k][1], l3 + il.x);
+                    lse1(al[k][2], al[k][3], l3 + il.y);
+                    lse1(ar[k][0], ar[k][1], ir.x + r4);
+                    lse1(ar[k][2], ar[k][3], ir.y + r4);
+                    float2 vr = make_float2(lse_fin(ar[k][0], ar[k][1]), lse_fin(ar[k][2], ar[k][3]));
+                    if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);  // single-root mask, dmv.py:63
+                    c.IL[cc] = il; c.IR[cc] = ir;
+                    c.X[cc] = make_float2(xl, xr);
+                    c.CL[cc] = make_float2(lse_fin(al[k][0], al[k][1]), lse_fin(al[k][2], al[k][3]));
+                    c.CR[cc] = vr;
                 }
             }
         }
@@ -314,15 +313,18 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
 #pragma unroll
         for (int q = 0; q < 4; ++q) { vc[k][q] = NEG_BIG; bc[k][q] = 255; }
     }
+    // one phase per width, as in inside_reg: the owner of a span finalises IL / IR and, through the same-span terms, CL / CR
+    // in the same visit (first-maximum ties are settled by the split index, so the order of arrival does not matter)
 #pragma unroll 1
-    for (int s = 0; s <= len; ++s) {
+    for (int s = 0; s < len; ++s) {
         const int Ds = dbase(s, Nb);
-        if (s >= 1) {
 #pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const int w = ow[k], i = oi[k];
-                if ((unsigned)(w - s) < (unsigned)s) {  // s <= w <= 2 s - 1
-                    const int Dd = dbase(w - s, Nb), j = i + w;
+        for (int k = 0; k < CPT; ++k) {
+            const int w = ow[k], i = oi[k];
+            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
+                const int j = i + w;
+                if (w <= 2 * s - 1) {  // later operand = an incomplete item of width s
+                    const int Dd = dbase(w - s, Nb);
                     const float l3 = c.CL[Dd + i].y;
                     const float2 i3 = c.IL[Ds + j - s];
                     const float2 i4 = c.IR[Ds + i];
@@ -331,25 +333,8 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), w - s);
                     amax1(vc[k][2], bc[k][2], __fadd_rn(i4.x, r4), s - 1);   // CR split r - i - 1, r = i + s
                     amax1(vc[k][3], bc[k][3], __fadd_rn(i4.y, r4), s - 1);
-                    if (w == s) {
-                        const int cc = Nb + tid + k * H;
-                        float2 vr = make_float2(vc[k][2], vc[k][3]);
-                        if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);
-                        c.CL[cc] = make_float2(vc[k][0], vc[k][1]);
-                        c.CR[cc] = vr;
-                        uint8_t *bp = c.bp + cc * 6;
-                        bp[2] = (uint8_t)bc[k][0]; bp[3] = (uint8_t)bc[k][1]; bp[4] = (uint8_t)bc[k][2]; bp[5] = (uint8_t)bc[k][3];
-                    }
                 }
-            }
-            blk_sync<NT>();
-        }
-        if (s == len) break;
-#pragma unroll
-        for (int k = 0; k < CPT; ++k) {
-            const int w = ow[k], i = oi[k];
-            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
-                const int De = dbase(w - 1 - s, Nb), j = i + w;
+                const int De = dbase(w - 1 - s, Nb);
                 const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
                 amax1(vx[k][0], bx[k][0], __fadd_rn(la.y, ra.x), s);
                 amax1(vx[k][1], bx[k][1], __fadd_rn(la.x, ra.y), s);
@@ -357,14 +342,6 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
                     amax1(vx[k][0], bx[k][0], __fadd_rn(lb.y, rb.x), w - 1 - s);
                     amax1(vx[k][1], bx[k][1], __fadd_rn(lb.x, rb.y), w - 1 - s);
-                }
-                if (w == s + 1) {
-                    const int cc = Nb + tid + k * H;
-                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
-                    c.IL[cc] = make_float2(__fadd_rn(vx[k][0], arcl.x), __fadd_rn(vx[k][0], arcl.y));
-                    c.IR[cc] = make_float2(__fadd_rn(vx[k][1], arcr.x), __fadd_rn(vx[k][1], arcr.y));
-                    uint8_t *bp = c.bp + cc * 6;
-                    bp[0] = (uint8_t)bx[k][0]; bp[1] = (uint8_t)bx[k][1];
                 }
                 if (w <= 2 * s) {
                     const int Dd = De + Nb - (w - 1 - s);   // dbase(w - s)
@@ -376,6 +353,25 @@ __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *c
                     amax1(vc[k][1], bc[k][1], __fadd_rn(l3, i3.y), s);
                     amax1(vc[k][2], bc[k][2], __fadd_rn(i4.x, r4), w - s - 1);
                     amax1(vc[k][3], bc[k][3], __fadd_rn(i4.y, r4), w - s - 1);
+                }
+                if (w == s + 1) {
+                    const int cc = Nb + tid + k * H;
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                    const float2 il = make_float2(__fadd_rn(vx[k][0], arcl.x), __fadd_rn(vx[k][0], arcl.y));
+                    const float2 ir = make_float2(__fadd_rn(vx[k][1], arcr.x), __fadd_rn(vx[k][1], arcr.y));
+                    const float l3 = c.CL[i].y, r4 = c.CR[j].y;  // CL[i, i].NO, CR[j, j].NO
+                    amax1(vc[k][0], bc[k][0], __fadd_rn(l3, il.x), 0);       // CL split 0 (r = i)
+                    amax1(vc[k][1], bc[k][1], __fadd_rn(l3, il.y), 0);
+                    amax1(vc[k][2], bc[k][2], __fadd_rn(ir.x, r4), w - 1);   // CR split w - 1 (r = j)
+                    amax1(vc[k][3], bc[k][3], __fadd_rn(ir.y, r4), w - 1);
+                    float2 vr = make_float2(vc[k][2], vc[k][3]);
+                    if (i == 0 && w != len) vr = make_float2(mask_zero, mask_zero);
+                    c.IL[cc] = il; c.IR[cc] = ir;
+                    c.CL[cc] = make_float2(vc[k][0], vc[k][1]);
+                    c.CR[cc] = vr;
+                    uint8_t *bp = c.bp + cc * 6;
+                    bp[0] = (uint8_t)bx[k][0]; bp[1] = (uint8_t)bx[k][1];
+                    bp[2] = (uint8_t)bc[k][0]; bp[3] = (uint8_t)bc[k][1]; bp[4] = (uint8_t)bc[k][2]; bp[5] = (uint8_t)bc[k][3];
                 }
             }
         }

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(WA_T, 2) word_attn_fwd_kernel(const float *__r
             float sum = pv;
             for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             s_p[q * WA_TV + lane] = pv;
+            __syncwarp();  // every lane has read s_m[q] before lane 0 replaces it
             if (lane == 0) {
                 const float al = __expf(mo - mx);
                 s_l[q] = s_l[q] * al + sum;

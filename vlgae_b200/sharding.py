@@ -52,19 +52,23 @@ def gather_heads(local_heads: torch.Tensor, num_sentences: int, rank: Optional[i
     if rank is None:
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     N = local_heads.shape[1]
-    out = local_heads.new_zeros((num_sentences, N))
     if world_size == 1:
-        out[shard_indices(num_sentences, 0, 1).to(out.device)] = local_heads
-        return out
+        return local_heads[:num_sentences].clone()
+    # Heads are positions < N: they travel as int16 (4x fewer bytes than the int64 the API returns), in ONE collective
+    # into a [W, per, N] buffer.  The round-robin deal puts sentence k W + r at (r, k), so the original order is a
+    # transpose of that buffer -- one strided copy, fused with the widening back to int64.
     per = (num_sentences + world_size - 1) // world_size
-    padded = local_heads.new_zeros((per, N))
+    wire = torch.int16 if N <= 32767 else local_heads.dtype
+    padded = torch.zeros((per, N), dtype=wire, device=local_heads.device)
     padded[: local_heads.shape[0]] = local_heads
-    parts = [torch.empty_like(padded) for _ in range(world_size)]
-    dist.all_gather(parts, padded, group=group)
-    for r, part in enumerate(parts):
-        idx = shard_indices(num_sentences, r, world_size).to(out.device)
-        out[idx] = part[: idx.numel()]
-    return out
+    parts = torch.empty((world_size, per, N), dtype=wire, device=local_heads.device)
+    # (on the wire as raw bytes: neither NCCL nor gloo has an int16 type, and a gather needs none)
+    src, dst = padded.view(torch.uint8), parts.view(torch.uint8)
+    try:
+        dist.all_gather_into_tensor(dst.view(world_size * per, -1), src, group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the tensor form
+        dist.all_gather(list(dst.unbind(0)), src, group=group)
+    return parts.permute(1, 0, 2).reshape(per * world_size, N)[:num_sentences].to(local_heads.dtype)
 
 
 def imbalance(lengths: torch.Tensor, world_size: int) -> float:
