@@ -971,7 +971,7 @@ def run_b200_arm(args):
                         "sorted desc, dealt round-robin (vlgae_b200.sharding.shard_indices), inside+outside+Viterbi per rank, "
                         "heads gathered on every rank in the original order (NCCL all_gather, mirrors pipeline.py:234-240)",
             "sentences": total, "per_rank": int(len(idx5)), "scaling": "strong",
-            "collective": f"nccl all_gather of heads ({total * N * 8 / 1e6:.1f} MB int64)" if dist is not None else "none (1 GPU)",
+            "collective": f"nccl all_gather_into_tensor of heads ({total * N * 2 / 1e6:.1f} MB on an int16 wire; int64 [{total}, {N}] returned)" if dist is not None else "none (1 GPU)",
             "ms_parse": ms5_parse, "ms_parse_plus_gather": ms5_all, "gather_ms": max(0.0, ms5_all - ms5_parse),
             "value": total / (ms5_all * 1e-3), "value_parse_only": total / (ms5_parse * 1e-3), "unit": "sentences/s",
             "roofline": {"bound": "sfu", "frac": wc5["mufu"] / world / (ms5_parse * 1e-3) / peaks["mufu"], "unit": "Gop/s",

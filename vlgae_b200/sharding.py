@@ -59,8 +59,11 @@ def gather_heads(local_heads: torch.Tensor, num_sentences: int, rank: Optional[i
     # transpose of that buffer -- one strided copy, fused with the widening back to int64.
     per = (num_sentences + world_size - 1) // world_size
     wire = torch.int16 if N <= 32767 else local_heads.dtype
-    padded = torch.zeros((per, N), dtype=wire, device=local_heads.device)
-    padded[: local_heads.shape[0]] = local_heads
+    if local_heads.shape[0] == per:
+        padded = local_heads.to(wire)  # one narrowing kernel
+    else:                              # the last ranks hold one sentence less: pad
+        padded = torch.zeros((per, N), dtype=wire, device=local_heads.device)
+        padded[: local_heads.shape[0]] = local_heads
     parts = torch.empty((world_size, per, N), dtype=wire, device=local_heads.device)
     # (on the wire as raw bytes: neither NCCL nor gloo has an int16 type, and a gather needs none)
     src, dst = padded.view(torch.uint8), parts.view(torch.uint8)
@@ -68,7 +71,9 @@ def gather_heads(local_heads: torch.Tensor, num_sentences: int, rank: Optional[i
         dist.all_gather_into_tensor(dst.view(world_size * per, -1), src, group=group)
     except (RuntimeError, NotImplementedError):  # a backend without the tensor form
         dist.all_gather(list(dst.unbind(0)), src, group=group)
-    return parts.permute(1, 0, 2).reshape(per * world_size, N)[:num_sentences].to(local_heads.dtype)
+    out = torch.empty((per, world_size, N), dtype=local_heads.dtype, device=local_heads.device)
+    out.copy_(parts.permute(1, 0, 2))  # transpose + widen in one kernel
+    return out.view(per * world_size, N)[:num_sentences]
 
 
 def imbalance(lengths: torch.Tensor, world_size: int) -> float:
