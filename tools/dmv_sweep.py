@@ -38,7 +38,7 @@ def synth(B, n, seed, ragged):
 
 
 CONFIGS = {
-    "cfg2": (128, 40, "cfg2"), "cfg2x8": (1024, 40, "cfg2"), "bulk": (16384, 40, "coco"),
+    "cfg2": (128, 40, "cfg2"), "cfg2x8": (1024, 40, "cfg2"), "bulk": (16384, 40, "coco"), "bulk100k": (100000, 40, "coco"),
     "bulk40": (8192, 40, "cfg2"), "n8": (512, 8, None), "n16": (512, 16, None), "n32": (512, 32, None),
     "n20": (512, 20, None), "n24": (512, 24, None), "n28": (512, 28, None), "n36": (512, 36, None), "n40": (512, 40, None),
     "n64": (512, 64, None), "n128": (512, 128, None), "full40": (4096, 40, None),

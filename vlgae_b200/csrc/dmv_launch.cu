@@ -273,8 +273,9 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     static const int env_gather_lo = env_int("VLGAE_GATHER_MIN_POSITIONS", 28);
     // in a bulk launch (length buckets, tens of waves) the gather schedule already wins from 18 positions on
     // (COCO-shaped 16384 sentences: 585 us with the buckets >= 18 on the gather schedule, 661 us with those >= 28)
-    // (r2c, lanes + length split: 528 us from 12 positions on, 604 us from 18)
-    static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 12);
+    // (r2c, lanes + length split: 528 us from 12 positions on, 604 us from 18; re-tuned on 100 k COCO-shaped captions after
+    // the one-phase forward sweeps of the frontier kernel: 12 / 14 / 16 / 18 / 20 -> 3156 / 3008 / 3206 / 3392 / 3142 us)
+    static const int env_gather_bulk_lo = env_int("VLGAE_GATHER_BULK_MIN_POSITIONS", 14);
     static const int env_lanes = env_int("VLGAE_DMV_LANES", 1);
     static const int env_split = env_int("VLGAE_GATHER_SPLIT", 1);
     static const int env_dynamic = env_int("VLGAE_GATHER_DYNAMIC", 1);
