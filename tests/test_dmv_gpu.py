@@ -309,6 +309,40 @@ def test_cfg3_n128_full_batch_properties(dev):
     np.testing.assert_array_equal(heads[:4], oheads)
 
 
+def test_cuda_graph_capture_of_a_multi_launch_call(dev):
+    """A call beyond one wave forks its launches (log / max semiring, length ranges) onto internal side streams and joins
+    them (csrc/dmv_launch.cu: Lanes); the fork / join is event-based, so the whole call can be captured into a CUDA graph
+    on the caller's stream and replayed: same results as the eager call, bit for bit."""
+    from vlgae_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    B, n = 1024, 40
+    L = torch.randint(4, n + 1, (B,), generator=g).sort(descending=True).values
+    md, ma, L = synth(B, n, 21, lengths=L)
+    tmd, tma, tL = _t(md, dev), _t(ma, dev), _t(L, dev)
+    eager = ops.dmv_parse(tmd, tma, tL, want_arcs=True)
+    torch.cuda.synchronize()
+    want = [x.clone() for x in (eager.Z, eager.gattach, eager.gdec, eager.best, eager.heads)]
+    out = ops.ParseBuffers(B, n + 1, dev)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for _ in range(2):  # warm-up on the capture stream: attributes, occupancy queries, side streams, workspace
+            ops.dmv_parse(tmd, tma, tL, out=out, prepared=True)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        ops.dmv_parse(tmd, tma, tL, out=out, prepared=True)
+    for buf in (out.Z, out.gattach, out.gdec, out.best):
+        buf.fill_(float("nan"))
+    out.heads.fill_(-1)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    got = [out.Z, out.gattach, out.gdec, out.best, out.heads]
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
 def test_upstream_gradient_scaling(dev):
     from vlgae_b200 import ops
 
