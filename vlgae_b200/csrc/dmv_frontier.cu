@@ -870,7 +870,7 @@ __device__ void max_pass(const DmvArgs &p, int b, int len, unsigned char *small,
 // kernel: persistent CTAs stride over (sentence, semiring) work items 
 // ---------------------------------------------------------------------------------------------
 template <int NT, int CPT, bool GC = false>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : (NT == 256 ? 3 : (NT == 128 ? 8 : (NT == 64 ? 16 : 1)))) dmv_frontier_kernel(DmvArgs p) {
+__global__ void __launch_bounds__(NT, NT == 512 ? (CPT >= 4 ? 1 : 2) : (NT == 256 ? 3 : (NT == 128 ? 8 : (NT == 64 ? 16 : 1)))) dmv_frontier_kernel(DmvArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.B * p.npass;
     const int nsm = p.nsm;
@@ -1002,7 +1002,9 @@ cudaError_t launch_dmv_frontier(DmvArgs a, int passes, int cap, int threads, boo
     }
     if (threads <= 512) {
         if (cells <= 512) return go(dmv_frontier_kernel<512, 1>, 512, true);
-        return cells <= 1024 ? go(dmv_frontier_kernel<512, 2>, 512, true) : go(dmv_frontier_kernel<512, 0>, 512, false);
+        if (cells <= 1024) return go(dmv_frontier_kernel<512, 2>, 512, true);
+        // charts of 46 .. 72 positions: five cells per thread in registers (one CTA per SM either way)
+        return cells <= 2560 ? go(dmv_frontier_kernel<512, 5>, 512, true) : go(dmv_frontier_kernel<512, 0>, 512, false);
     }
     return cells <= 1024 ? go(dmv_frontier_kernel<1024, 1>, 1024, true) : go(dmv_frontier_kernel<1024, 0>, 1024, false);
 }

@@ -145,7 +145,8 @@ static cudaError_t launch_frontier_cap(const DmvArgs &a, int passes, int cap, cu
         { ft = env_int("VLGAE_FRONTIER_WARP", 1) ? 32 : (cap <= 12 ? 64 : 128); reg_state = false; }
     else if (cap <= 33) { ft = 128; reg_state = false; }
     else if (cap <= 45) { ft = 256; reg_state = true; }   // <= 1024 cells: 4 per thread in registers
-    else { ft = 512; reg_state = false; }                 // one CTA per SM: more threads (n = 64: 907 vs 1039 us)
+    else { ft = 512; reg_state = env_int("VLGAE_FRONTIER_REG5", 1) != 0; }  // one CTA per SM: more threads (n = 64: 907 vs 1039 us);
+                                                          // <= 2560 cells: five per thread in registers
     if (env_ft > 0) ft = env_ft;
     if (fits) { f.workspace = nullptr; f.ws_stride = 0; }
     else f.ws_stride = dmv_ws_slice_bytes(a.N, 3);
