@@ -476,89 +476,72 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     if (reg_state) {
         inside_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
     } else {
+        // one phase per width, as in inside_reg (the span's owner finalises IL / IR and, through the same-span terms,
+        // CL / CR in one visit): a visit loads and stores the running state of its cell once for all three kinds of terms
 #pragma unroll 1
-        for (int s = 0; s <= len; ++s) {
+        for (int s = 0; s < len; ++s) {
             const int Ds = dbase(s, Nb);
-            if (s >= 1) {
-                // phase A(s): incomplete items of width s are final
-                const int whi = min(2 * s - 1, len);
-                const int c1 = dbase(whi + 1, Nb);
+            const int c0 = dbase(s + 1, Nb), c1 = dbase(min(2 * s + 1, len) + 1, Nb);  // targets of width s + 1 .. 2 s + 1
 #pragma unroll 1
-                for (int cc = Ds + tid; cc < c1; cc += NT) {
-                    const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+            for (int cc = c0 + tid; cc < c1; cc += NT) {
+                const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
+                const int De = dbase(w - 1 - s, Nb);
+                float4 a0 = c.A0[cc], a1, a2;
+                const bool ctarget = w <= 2 * s || w == s + 1;  // complete-item terms arrive, or the span is finalised
+                if (ctarget) { a1 = c.A1[cc]; a2 = c.A2[cc]; }
+                if (w <= 2 * s - 1) {  // later operand = an incomplete item of width s
                     const int Dd = dbase(w - s, Nb);
-                    // step 3 (dmv.py:58-59): CL[i,j][v] (+)= CL[i,r].NO + IL[r,j][v], r = j - s
-                    const float l3 = c.CL[Dd + i].y;
-                    const float2 i3 = c.IL[Ds + j - s];
-                    // step 4 (dmv.py:61-62): CR[i,j][v] (+)= IR[i,r][v] + CR[r,j].NO, r = i + s
-                    const float2 i4 = c.IR[Ds + i];
-                    const float r4 = c.CR[Dd + i + s].y;
-                    float4 a1 = c.A1[cc], a2 = c.A2[cc];
+                    const float l3 = c.CL[Dd + i].y;          // CL[i, j-s].NO
+                    const float2 i3 = c.IL[Ds + j - s];        // IL[j-s, j]
+                    const float2 i4 = c.IR[Ds + i];            // IR[i, i+s]
+                    const float r4 = c.CR[Dd + i + s].y;       // CR[i+s, j].NO
                     lse1(a1.x, a1.y, l3 + i3.x);
                     lse1(a1.z, a1.w, l3 + i3.y);
                     lse1(a2.x, a2.y, i4.x + r4);
                     lse1(a2.z, a2.w, i4.y + r4);
-                    if (w == s) {
-                        float2 vr = make_float2(lse_fin(a2.x, a2.y), lse_fin(a2.z, a2.w));
-                        if (i == 0 && w != len) vr = make_float2(p.mask_zero, p.mask_zero);  // single-root mask, dmv.py:63
-                        c.CL[cc] = make_float2(lse_fin(a1.x, a1.y), lse_fin(a1.z, a1.w));
-                        c.CR[cc] = vr;
-                    } else {
-                        c.A1[cc] = a1; c.A2[cc] = a2;
-                    }
                 }
-                blk_sync<NT>();
-            }
-            if (s == len) break;
-            // phase B(s): complete items of width s are final
-            {
-                const int ihi = min(2 * s + 1, len), chi = min(2 * s, len);
-                const int i0 = dbase(s + 1, Nb), nI = dbase(ihi + 1, Nb) - i0;
-                const int nC = chi >= s + 1 ? dbase(chi + 1, Nb) - i0 : 0;
-#pragma unroll 1
-                for (int t = tid; t < nI + nC; t += NT) {
-                    if (t < nI) {
-                        const int cc = i0 + t;
-                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                        const int De = dbase(w - 1 - s, Nb);
-                        // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
-                        const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
-                        float4 a0 = c.A0[cc];
-                        if (w - 1 - s != s) {
-                            const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
-                            lse2(a0.x, a0.y, la.y + ra.x, lb.y + rb.x);
-                            lse2(a0.z, a0.w, la.x + ra.y, lb.x + rb.y);
-                        } else {
-                            lse1(a0.x, a0.y, la.y + ra.x);
-                            lse1(a0.z, a0.w, la.x + ra.y);
-                        }
-                        if (w == s + 1) {
-                            const float xl = lse_fin(a0.x, a0.y), xr = lse_fin(a0.z, a0.w);
-                            const float2 arcl = c.IL[cc], arcr = c.IR[cc];
-                            c.IL[cc] = make_float2(xl + arcl.x, xl + arcl.y);
-                            c.IR[cc] = make_float2(xr + arcr.x, xr + arcr.y);
-                            c.X[cc] = make_float2(xl, xr);
-                        } else {
-                            c.A0[cc] = a0;
-                        }
-                    } else {
-                        const int cc = i0 + (t - nI);
-                        const int w = cw[cc] >> 8, i = cw[cc] & 255, j = i + w;
-                        const int Dd = dbase(w - s, Nb);
-                        const float l3 = c.CL[Ds + i].y;        // CL[i, i+s].NO
-                        const float2 i3 = c.IL[Dd + i + s];     // IL[i+s, j]
-                        const float2 i4 = c.IR[Dd + i];         // IR[i, j-s]
-                        const float r4 = c.CR[Ds + j - s].y;    // CR[j-s, j].NO
-                        float4 a1 = c.A1[cc], a2 = c.A2[cc];
-                        lse1(a1.x, a1.y, l3 + i3.x);
-                        lse1(a1.z, a1.w, l3 + i3.y);
-                        lse1(a2.x, a2.y, i4.x + r4);
-                        lse1(a2.z, a2.w, i4.y + r4);
-                        c.A1[cc] = a1; c.A2[cc] = a2;
-                    }
+                // steps 1, 2 (dmv.py:50-56): XL (+)= CR[i,r].NO + CL[r+1,j].HAS, XR (+)= CR[i,r].HAS + CL[r+1,j].NO
+                const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
+                if (w - 1 - s != s) {
+                    const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                    lse2(a0.x, a0.y, la.y + ra.x, lb.y + rb.x);
+                    lse2(a0.z, a0.w, la.x + ra.y, lb.x + rb.y);
+                } else {
+                    lse1(a0.x, a0.y, la.y + ra.x);
+                    lse1(a0.z, a0.w, la.x + ra.y);
                 }
-                blk_sync<NT>();
+                if (w <= 2 * s) {
+                    const int Dd = De + Nb - (w - 1 - s);   // dbase(w - s)
+                    const float l3 = c.CL[Ds + i].y;        // CL[i, i+s].NO
+                    const float2 i3 = c.IL[Dd + i + s];     // IL[i+s, j]
+                    const float2 i4 = c.IR[Dd + i];         // IR[i, j-s]
+                    const float r4 = c.CR[Ds + j - s].y;    // CR[j-s, j].NO
+                    lse1(a1.x, a1.y, l3 + i3.x);
+                    lse1(a1.z, a1.w, l3 + i3.y);
+                    lse1(a2.x, a2.y, i4.x + r4);
+                    lse1(a2.z, a2.w, i4.y + r4);
+                }
+                if (w == s + 1) {
+                    const float xl = lse_fin(a0.x, a0.y), xr = lse_fin(a0.z, a0.w);
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];
+                    const float2 il = make_float2(xl + arcl.x, xl + arcl.y), ir = make_float2(xr + arcr.x, xr + arcr.y);
+                    const float l3 = c.CL[i].y, r4 = c.CR[j].y;  // CL[i, i].NO, CR[j, j].NO (width-0 cells)
+                    lse1(a1.x, a1.y, l3 + il.x);
+                    lse1(a1.z, a1.w, l3 + il.y);
+                    lse1(a2.x, a2.y, ir.x + r4);
+                    lse1(a2.z, a2.w, ir.y + r4);
+                    float2 vr = make_float2(lse_fin(a2.x, a2.y), lse_fin(a2.z, a2.w));
+                    if (i == 0 && w != len) vr = make_float2(p.mask_zero, p.mask_zero);  // single-root mask, dmv.py:63
+                    c.IL[cc] = il; c.IR[cc] = ir;
+                    c.X[cc] = make_float2(xl, xr);
+                    c.CL[cc] = make_float2(lse_fin(a1.x, a1.y), lse_fin(a1.z, a1.w));
+                    c.CR[cc] = vr;
+                } else {
+                    c.A0[cc] = a0;
+                    if (ctarget) { c.A1[cc] = a1; c.A2[cc] = a2; }
+                }
             }
+            blk_sync<NT>();
         }
     }
     zres = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65, minus the offsets
