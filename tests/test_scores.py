@@ -90,3 +90,66 @@ def test_cuda_matches_oracle_at_cfg2_shape_and_feeds_the_chart():
     # a head beyond the end of its sentence takes part in no tree: its rows of the merged tensors get zero marginals
     pad = torch.arange(n, device=dev)[None, :] >= lengths.to(dev)[:, None]
     assert float(g1[pad].abs().max()) == 0.0, "heads beyond the sentence receive no gradient"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,T,r", [(1, 1, 1, 4), (2, 3, 65, 8), (3, 5, 130, 32), (2, 40, 1000, 16), (5, 2, 7, 4)])
+def test_cuda_edge_shapes_against_oracle(B, n, T, r):
+    """Single word, single token, vocabulary sizes around the 64-token tile, every supported rank; forward against the
+    numpy restatement, backward against autograd through the reference's torch formula in fp64."""
+    from vlgae_b200.scores import dmv_scores
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(100 + B + n + T)
+    x1 = torch.randn(B, n, 2, 2, r, generator=g)
+    x2 = torch.randn(T, 2, 2, r, generator=g)
+    token = torch.randint(0, T, (B, n), generator=g)
+    ds = torch.randn(B, n, 2, 2, 2, generator=g)
+    rs = torch.randn(T, generator=g)
+    hm = torch.rand(B, n, generator=g) > 0.7
+    t = [v.to(dev).requires_grad_() for v in (x1, x2, ds, rs)]
+    md, ma = dmv_scores(t[0], t[1], token.to(dev), t[2], t[3], hm.to(dev))
+    _, _, _, omd, oma = oracle.dmv_scores(x1.numpy(), x2.numpy(), token.numpy(), ds.numpy(), rs.numpy(), hm.numpy())
+    np.testing.assert_allclose(md.detach().cpu().numpy(), omd, rtol=0, atol=5e-6)
+    got = ma.detach().cpu().numpy()
+    big = oma <= -1e11
+    assert np.array_equal(got <= -1e11, big) and np.array_equal(got[big], oma[big])
+    np.testing.assert_allclose(got[~big], oma[~big], rtol=0, atol=2e-5)
+    gmd = torch.randn(md.shape, generator=g).to(dev)
+    gma = torch.randn(ma.shape, generator=g).to(dev)
+    mine = torch.autograd.grad([md, ma], t, [gmd, gma])
+    # the reference's formula (ldndmv.py:185-209) in fp64
+    d = [v.double().requires_grad_() for v in (x1, x2, ds, rs)]
+    rule = torch.einsum("bhdve,cdve->bhcdv", d[0], d[1]).log_softmax(2)
+    prob = rule.gather(2, token.reshape(B, 1, n, 1, 1).expand(B, n, n, 2, 2))
+    lm = torch.tril(torch.ones(n, n, dtype=torch.float64), -1)[None, :, :, None]
+    rm = torch.triu(torch.ones(n, n, dtype=torch.float64), 1)[None, :, :, None]
+    att = (prob[..., 0, :] * lm + prob[..., 1, :] * rm).masked_fill(hm[:, :, None, None], -1e20)
+    dec = d[2].permute(0, 1, 3, 4, 2).log_softmax(-1)
+    root = d[3].log_softmax(-1)[token]
+    rmd = torch.full((B, n + 1, 2, 2, 2), -1e12, dtype=torch.float64)
+    rma = torch.full((B, n + 1, n + 1, 2), -1e12, dtype=torch.float64)
+    rma[:, 0, 1:, 1] = root
+    rma[:, 1:, 1:, :] = att
+    rmd[:, 0, 1, :, :] = 0
+    rmd[:, 1:] = dec
+    theirs = torch.autograd.grad([rmd, rma], d, [gmd.double().cpu(), gma.double().cpu()])
+    for a, b_, name in zip(mine, theirs, ("x1", "x2", "dec_score", "root_score")):
+        scale = max(1.0, float(b_.abs().max()))
+        np.testing.assert_allclose(a.cpu().numpy(), b_.numpy(), rtol=0, atol=5e-5 * scale, err_msg=name)
+
+
+@pytest.mark.gpu
+def test_cuda_rejects_what_it_does_not_provide():
+    from vlgae_b200._lib import VlgaeError
+    from vlgae_b200.scores import dmv_scores
+
+    dev = torch.device("cuda:0")
+    x1, x2 = torch.zeros(1, 2, 2, 2, 16, device=dev), torch.zeros(5, 2, 2, 16, device=dev)
+    tok, ds, rs = torch.zeros(1, 2, dtype=torch.long, device=dev), torch.zeros(1, 2, 2, 2, 2, device=dev), torch.zeros(5, device=dev)
+    with pytest.raises(VlgaeError):
+        dmv_scores(x1, x2, tok, ds, rs, extended_valence=False)
+    with pytest.raises(VlgaeError):
+        dmv_scores(x1[..., :5], x2[..., :5], tok, ds, rs)  # rank 5 is not one of 4 / 8 / 16 / 32
+    with pytest.raises(VlgaeError):
+        dmv_scores(x1.cpu(), x2.cpu(), tok.cpu(), ds.cpu(), rs.cpu())

@@ -107,3 +107,35 @@ def test_cuda_matches_literal_oracle_at_cfg2_shape():
                                      bm[:nb].numpy())
     np.testing.assert_allclose(mid[:nb].cpu().numpy(), omid, rtol=1e-4, atol=2e-5)
     assert np.array_equal(mask[:nb].cpu().numpy(), omask)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,H,attr,img", [(1, 1, 5, True, True), (2, 3, 7, False, True), (3, 4, 130, True, False), (2, 2, 64, False, False)])
+def test_cuda_edge_shapes_against_torch_formula(B, n, H, attr, img):
+    """One box, channel counts that are not multiples of 4 (scalar path), every combination of the optional factor groups;
+    forward and backward against the pair formula in torch fp64."""
+    from vlgae_b200.vis_factors import pairwise_factors
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7 + B + n + H)
+    u = [torch.randn(B, n, H, generator=g) for _ in range(3)]
+    bm = torch.rand(B, n, generator=g) > 0.3
+    t = [v.to(dev).requires_grad_() for v in u]
+    mid, mask, split = pairwise_factors(t[0], t[1], t[2] if attr else None, bm.to(dev), add_image=img)
+    d = [v.double().requires_grad_() for v in u]
+    act = torch.nn.functional.leaky_relu
+    box = act(d[0], 0.01)
+    rel = act((d[1].unsqueeze(1) + d[1].unsqueeze(2)) / 2, 0.01).reshape(B, n * n, H)
+    feats = [box, rel] + ([act(d[2], 0.01)] if attr else []) + ([box.mean(1, keepdim=True)] if img else [])
+    ref = torch.cat(feats, 1)
+    rmask = torch.cat([bm, (bm.unsqueeze(1) & bm.unsqueeze(2)).triu(1).reshape(B, -1)] + ([bm] if attr else [])
+                      + ([torch.ones(B, 1, dtype=torch.bool)] if img else []), 1)
+    assert split == [n, n * n] + ([n] if attr else []) + ([1] if img else [])
+    np.testing.assert_allclose(mid.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(mask.cpu(), rmask)
+    go = torch.randn(ref.shape, generator=g)
+    ins = t if attr else t[:2]
+    mine = torch.autograd.grad(mid, ins, go.to(dev))
+    theirs = torch.autograd.grad(ref, d if attr else d[:2], go.double())
+    for a, b_ in zip(mine, theirs):
+        np.testing.assert_allclose(a.cpu().numpy(), b_.numpy(), rtol=1e-5, atol=1e-5)
