@@ -397,12 +397,35 @@ def alignment_leg(dev, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms_bwd = e0.elapsed_time(e1) / iters
+    # the gradient autograd hands over after the default (padded-row) forward: row stride ceil(V / 8) * 8
+    ldp = (V + 7) // 8 * 8
+    gpad = torch.ones((B, A, Q, ldp), dtype=torch.float32, device=dev)
+    gvis2, gtxt2 = torch.empty_like(vis), torch.empty_like(txt)
+
+    def bwd_pad():
+        _check(_lib().vlgae_align_logits_backward(gpad.data_ptr(), ldp, vis.data_ptr(), vmu.data_ptr(), txt.data_ptr(), tmu.data_ptr(),
+                                                  A, V, B, Q, D, 3, gvis2.data_ptr(), gtxt2.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  torch.cuda.current_stream(dev).cuda_stream), "vlgae_align_logits_backward")
+    bwd_pad()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        bwd_pad()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_bwd_pad = e0.elapsed_time(e1) / iters
+    pad_vs_dense = max(float((gvis2 - gvis).abs().max() / gvis.abs().max().clamp_min(1e-9)),
+                       float((gtxt2 - gtxt).abs().max() / gtxt.abs().max().clamp_min(1e-9)))
+    del gpad, gvis2, gtxt2
     want_t = ((vis * vm.unsqueeze(-1)).sum((0, 1)).unsqueeze(0).unsqueeze(0) * tm.unsqueeze(-1)).cpu()  # g = 1: sum of kept vis rows
     bwd_err = float((gtxt.cpu() - want_t).abs().max() / want_t.abs().max())
     del gup
     backward = {"workload": "vlgae_align_logits_backward (d vis and d txt, gradient streamed once each), same shape",
                 "ms": ms_bwd, "gradient_gb_per_s": 2 * out_bytes / (ms_bwd * 1e-3) / 1e9,
-                "rel_err_d_txt_vs_closed_form": bwd_err}
+                "rel_err_d_txt_vs_closed_form": bwd_err,
+                "padded_rows": {"what": f"gradient with the row stride of the default forward result ({ldp} floats)",
+                                "ms": ms_bwd_pad, "gradient_gb_per_s": 2 * out_bytes / (ms_bwd_pad * 1e-3) / 1e9,
+                                "max_rel_diff_vs_dense_gradient_result": pad_vs_dense}}
     reduced = {"workload": "vlgae_align_max_over_factors (max over V in the epilogue; joint.py:421-428), same shape",
                "ms": ms_red, "bit_identical_to_max_of_materialised": bool(torch.equal(maxv, ref_max)),
                "roofline": {"bound": "tensor", "achieved": flops / (ms_red * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
