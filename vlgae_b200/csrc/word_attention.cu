@@ -89,7 +89,7 @@ __device__ __forceinline__ void score_tile(const float *s_txt, const float *s_vi
 // grid (B, query splits): a CTA takes queries [blockIdx.y * nq_cta, ...) of caption blockIdx.x -- several CTAs per SM, so that
 // one CTA's tile loads hide behind another's products
 template <int WA_QG>
-__global__ void __launch_bounds__(WA_T, 2) word_attn_fwd_kernel(const float *__restrict__ vis, const float *__restrict__ txt,
+__global__ void __launch_bounds__(WA_T, WA_QG <= 2 ? 3 : 2) word_attn_fwd_kernel(const float *__restrict__ vis, const float *__restrict__ txt,
                                                                 const float *__restrict__ mid, int V, int n_all, int nq_cta, int D, int H,
                                                                 float *__restrict__ out, float *__restrict__ lse) {
     extern __shared__ __align__(16) float sm[];
@@ -329,8 +329,10 @@ __global__ void __launch_bounds__(WA_T) word_attn_bwd_kernel(const float *__rest
 cudaError_t launch_word_attention(const float *vis, const float *txt, const float *mid, int B, int V, int n, int D, int H,
                                   float *out, float *lse, cudaStream_t st) {
     if (n > WA_NQ || H > WA_T || n < 1 || D < 1 || H < 1) return cudaErrorInvalidValue;
-    // query splits: as many as still fit ONE wave of two CTAs per SM (148 SMs), at least 8 queries each
-    int ns = (2 * 148) / (B > 0 ? B : 1);
+    // query splits: as many as still fit ONE wave of three CTAs per SM (148 SMs; <= 16 queries per CTA keep the registers
+    // under the three-CTA bound), at least 8 queries each
+    static const int env_slots = [] { const char *v = getenv("VLGAE_WA_SLOTS"); return v && *v ? atoi(v) : 3; }();
+    int ns = (env_slots * 148) / (B > 0 ? B : 1);
     if (ns > (n + 7) / 8) ns = (n + 7) / 8;
     if (ns < 1) ns = 1;
     const int nq_cta = (n + ns - 1) / ns;
