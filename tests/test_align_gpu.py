@@ -357,3 +357,25 @@ def test_max_over_factors_backward_kernel(dev):
     (ref * w.double()).sum().backward()
     assert float((vis.grad.double() - vis2.grad).abs().max()) < 1e-4
     assert float((txt.grad.double() - txt2.grad).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("V", [121, 127, 129, 135, 241, 247, 249, 255, 361, 369, 1369])
+def test_dense_layout_sector_tiles_equal_padded(dev, V):
+    """The reference's dense layout (rows of odd length) is written by overlapping tiles 120 factors apart, every tile storing
+    whole 32-byte sectors of a row (align_gemm_kernel VSTEP): bit-identical to the padded result at every tile-boundary case."""
+    from vlgae_b200.alignment import gather_logit_simple
+
+    g_ = torch.Generator(device=dev).manual_seed(V)
+    A, B, Q, D = 3, 5, 19, 64
+    vis = torch.randn(A, V, D, generator=g_, device=dev)
+    txt = torch.randn(B, Q, D, generator=g_, device=dev)
+    vm = torch.rand(A, V, generator=g_, device=dev) > 0.2
+    tm = torch.rand(B, Q, generator=g_, device=dev) > 0.2
+    dense = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=False)
+    padded = gather_logit_simple(vis, vm, txt, tm, named=False, pad_rows=True)
+    torch.cuda.synchronize()
+    assert dense.is_contiguous() and dense.shape == (B, A, Q, V)
+    assert torch.equal(dense, padded)
+    ref = torch.einsum("avd,bqd->baqv", vis.double(), txt.double())
+    keep = (vm[None, :, None, :] & tm[:, None, :, None]).expand(B, A, Q, V)
+    assert float((dense.double() - ref)[keep].abs().max()) < 2e-3 and bool((dense[~keep] == -1e20).all())

@@ -163,7 +163,9 @@ __device__ __forceinline__ void bulk_s2g(float *dst, const float *src, int bytes
 // ---------------------------------------------------------------------------------------------
 __global__ void align_pack_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, int G, int R, int D,
                                   int KB, int rows_per_chunk, size_t tile_stride_bytes, int tiles, uint8_t *out,
-                                  uint32_t *maskbits) {
+                                  uint32_t *maskbits, int tile_step) {
+    // tile_step = first row of tile t is t * tile_step: 128, or 120 for the overlapping tiles of the sector-owning dense
+    // layout (align_gemm_kernel, VSTEP)
     // one thread per (g, tile, row, 8-element group): writes one 16-byte unit of hi and of lo
     const int groups = KB * 8;
     const size_t total = (size_t)G * tiles * rows_per_chunk * groups;
@@ -173,7 +175,7 @@ __global__ void align_pack_kernel(const float *__restrict__ x, const uint8_t *__
         const int r = (int)(u % rows_per_chunk); u /= rows_per_chunk;
         const int tile = (int)(u % tiles);
         const int g = (int)(u / tiles);
-        const int row = tile * TILE_M + r;
+        const int row = tile * tile_step + r;
         const int k0 = grp * 8;
         float v[8];
 #pragma unroll
@@ -224,7 +226,7 @@ struct AlignSmem {
 // MODE 0: direct stores (rows not 16-byte aligned)   1: staged tile + bulk TMA stores   2: no [B,A,Q,V] output at all --
 // the epilogue reduces every query row to its maximum over the factors (and the arg-max) and merges the v-tiles with a
 // 64-bit atomicMax (gather_logit_reduced, joint.py:421-432: the 7.4 GB tensor is never materialised)
-template <int KB, int MODE, bool SHIFT = false>
+template <int KB, int MODE, int VSTEP = 0>
 __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     constexpr bool BULK = MODE >= 1;      // a staged [query][128 factors] tile per epilogue team
     constexpr bool REDUCE = MODE >= 2;
@@ -246,9 +248,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     // all but <= 3 leading / trailing floats of the row still leave through one bulk copy
     // (SHIFT is a template parameter: with a run-time stride the 16 staging stores per chunk lose their immediate offsets
     // and the aligned layout went from 1.76 to 3.2 ms)
+    // VSTEP != 0 selects the shifted layout and is the distance between the first factors of consecutive tiles: 128
+    // (disjoint tiles: every 512-byte row segment starts and ends inside a 32-byte sector that a neighbouring tile -- another
+    // CTA, or this one later -- completes: 560 M L2 write-sector operations instead of 386 M, 3.1-3.3 ms) or 120: tiles
+    // OVERLAP by 8 factors and tile t > 0 stores, of row r, the 120 floats [120 t + e_r, 120 (t + 1) + e_r), e_r < 8 chosen so
+    // that the segment starts on a sector boundary of the global row -- every sector of a row except its first and its
+    // last is then written whole, by one bulk copy.  1369 factors are 12 tiles either way it is counted in pairs (6).
+    constexpr bool SHIFT = VSTEP != 0;
     static_assert(!SHIFT || MODE == 1, "the shifted staging belongs to the materialising bulk-store mode");
+    static_assert(VSTEP == 0 || VSTEP == TILE_M || VSTEP == TILE_M - 8, "tile step: 128 or 120");
     constexpr int TS = SHIFT ? TILE_M + 4 : TILE_M;
     constexpr bool shifted = SHIFT;
+    constexpr int VS = SHIFT ? VSTEP : TILE_M;  // factor step between tiles
     const size_t out_tile_floats = (size_t)p.out_rows * TS;
     float *s_neg = s_out + (size_t)NB * out_tile_floats;  // BULK: one row of -INF, the source of masked query rows
     // REDUCE: running (ordered max bits << 32 | ~arg-max) per (team, caption of the chunk, query); 0 = nothing seen yet
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
             bool v_ok_t[PAIR], v_keep_t[PAIR];
 #pragma unroll
             for (int t = 0; t < PAIR; ++t) {
-                const int vv = (vt0 + t) * TILE_M + quad * 32 + lane;
+                const int vv = (vt0 + t) * VS + quad * 32 + lane;
                 v_ok_t[t] = t < ntv && vv < p.V;
                 v_keep_t[t] = v_ok_t[t] && p.vis_mask[(size_t)a * p.V + vv] != 0;
             }
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
             const uint4 *mbp = reinterpret_cast<const uint4 *>(p.txt_maskbits) + (size_t)b0 * QT;
             uint4 mb = mbp[0];  // caption mask bits of the next tile are fetched while the current one is stored
             const size_t tile_rows = (size_t)TILE_M * V, cap_stride = (size_t)p.A * p.Q * V;
-            float *ob = p.out + ((size_t)b0 * p.A + a) * p.Q * V + vt0 * TILE_M + quad * 32 + lane;  // (b0, a, q = 0, v)
+            float *ob = p.out + ((size_t)b0 * p.A + a) * p.Q * V + vt0 * VS + quad * 32 + lane;  // (b0, a, q = 0, v)
             for (int b = b0; b < b1; ++b, ob += cap_stride) {
                 float *orow0 = ob;
                 for (int qt = 0; qt < QT; ++qt, orow0 += tile_rows) {
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                         ++gcount;
                         if (T == 2 && acc != (uint32_t)team) continue;
                         const bool v_ok = v_ok_t[t], v_keep = v_keep_t[t];
-                        float *orow = orow0 + t * TILE_M;
+                        float *orow = orow0 + t * VS;
                         mbar_wait(&sb->acc_full[acc], acc_phase);
                         tc_fence_after();
                         const uint32_t taddr = tmem_base + ACC_COL0 + acc * acc_stride + ((uint32_t)(quad * 32) << 16);
@@ -598,13 +609,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                 const int c0 = half * 16 + k * 4 * kEpiWarps;
                                 float *slot = tile_out + (size_t)c0 * TS + quad * 32 + lane;
                                 const uint32_t kc = k0 + (uint32_t)c0 * vm;
+                                // the shift of row c0 + j, (kc + j vm) & 3, has period 4 in j: four base pointers, and the 16
+                                // stores keep their immediate offsets
+                                float *sl[4];
+#pragma unroll
+                                for (int m = 0; m < 4; ++m) sl[m] = slot + ((kc + (uint32_t)m * vm) & 3u);
                                 if (c0 + 16 <= q_lim) {
 #pragma unroll
-                                    for (int j = 0; j < 16; ++j) slot[j * TS + ((kc + j * vm) & 3u)] = __uint_as_float(r[k][j]);
+                                    for (int j = 0; j < 16; ++j) sl[j & 3][j * TS] = __uint_as_float(r[k][j]);
                                 } else {
 #pragma unroll
                                     for (int j = 0; j < 16; ++j)
-                                        if (c0 + j < q_lim) slot[j * TS + ((kc + j * vm) & 3u)] = __uint_as_float(r[k][j]);
+                                        if (c0 + j < q_lim) sl[j & 3][j * TS] = __uint_as_float(r[k][j]);
                                 }
                             }
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -615,13 +631,24 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                             if (row < q_lim && !(p.debug & 1)) {
                                 const uint32_t w32 = row < 32 ? mb_cur.x : (row < 64 ? mb_cur.y : (row < 96 ? mb_cur.z : mb_cur.w));
                                 const bool keep = (w32 >> (row & 31)) & 1u;
-                                const int len = min(TILE_M, p.ldv - (vt0 + t) * TILE_M);
-                                float *dst = tile_row0 + (size_t)row * V;
                                 if (!shifted) {
-                                    bulk_s2g(dst, keep ? tile_out + (size_t)row * TS : s_neg, len * 4);
+                                    const int len = min(TILE_M, p.ldv - (vt0 + t) * TILE_M);
+                                    bulk_s2g(tile_row0 + (size_t)row * V, keep ? tile_out + (size_t)row * TS : s_neg, len * 4);
                                 } else {
-                                    const int kr = (int)((k0 + (uint32_t)row * vm) & 3u), h = (4 - kr) & 3;  // h floats up to alignment
-                                    const float *src = tile_out + (size_t)row * TS + kr;                     // element e at src[e]
+                                    // factors [x0, x1) of the tile belong to this tile in row `row` (see VSTEP above)
+                                    const int tg = vt0 + t;
+                                    int x0 = 0, x1 = min(TILE_M, p.ldv - tg * VS);
+                                    if (VS != TILE_M) {
+                                        const uint32_t k8 = (uint32_t)(reinterpret_cast<uintptr_t>(tile_row0) >> 2) & 7u;  // VS % 8 == 0
+                                        const int er = (int)((8u - ((k8 + (uint32_t)row * (V & 7u)) & 7u)) & 7u);
+                                        if (tg > 0) x0 = er;
+                                        if (tg < VT - 1) x1 = VS + er;
+                                    }
+                                    const int len = x1 - x0;
+                                    const int kr = (int)((k0 + (uint32_t)row * vm) & 3u);
+                                    const int h = (4 - ((kr + x0) & 3)) & 3;                                       // floats up to alignment
+                                    float *dst = tile_row0 + (size_t)row * V + x0;
+                                    const float *src = tile_out + (size_t)row * TS + kr + x0;                      // element e at src[e]
                                     const int nb = len > h ? ((len - h) & ~3) : 0;
                                     if (nb > 0) bulk_s2g(dst + h, keep ? src + h : s_neg, nb * 4);
                                     for (int e = 0; e < min(h, len); ++e) __stcs(dst + e, keep ? src[e] : neg);
@@ -685,10 +712,11 @@ cudaError_t align_device_info() {
 
 }  // namespace
 
-AlignPlan align_plan(int A, int V, int B, int Q, int D) {
+AlignPlan align_plan(int A, int V, int B, int Q, int D, int vstep) {
     AlignPlan pl{};
     pl.KB = (D + 63) / 64;
-    pl.VT = (V + TILE_M - 1) / TILE_M;
+    // tiles of 128 factors whose first factors are vstep apart (128: disjoint; 120: overlapping, align_gemm_kernel VSTEP)
+    pl.VT = V <= TILE_M ? 1 : (V - (TILE_M - vstep) + vstep - 1) / vstep;
     pl.QT = (Q + TILE_M - 1) / TILE_M;
     const int qmax = Q < TILE_M ? Q : TILE_M;
     pl.nq = (qmax + 15) & ~15;
@@ -700,17 +728,18 @@ AlignPlan align_plan(int A, int V, int B, int Q, int D) {
 }
 
 size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
-    const AlignPlan pl = align_plan(A, V, B, Q, D);
-    return pl.vis_packed_bytes + pl.txt_packed_bytes + ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
+    const AlignPlan pl = align_plan(A, V, B, Q, D), pd = align_plan(A, V, B, Q, D, TILE_M - 8);  // room for either tiling
+    return (pl.vis_packed_bytes > pd.vis_packed_bytes ? pl.vis_packed_bytes : pd.vis_packed_bytes) + pl.txt_packed_bytes +
+           ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
 }
 
 // pack both operands (bf16 hi / lo, swizzled tile images) + the caption mask bits into the workspace:
 //   [vis tiles][caption tiles][mask bits]   (shared by the forward and the backward kernels)
 cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
-                                void *workspace, cudaStream_t st) {
+                                void *workspace, cudaStream_t st, int vstep) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
-    const AlignPlan pl = align_plan(A, V, B, Q, D);
+    const AlignPlan pl = align_plan(A, V, B, Q, D, vstep);
     uint8_t *ws = reinterpret_cast<uint8_t *>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     uint8_t *vis_packed = ws;
     uint8_t *txt_packed = vis_packed + pl.vis_packed_bytes;
@@ -720,8 +749,8 @@ cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_
     const int cap = g_align_sm * 16;
     if (gv > cap) gv = cap;
     if (gt > cap) gt = cap;
-    align_pack_kernel<<<gv, 256, 0, st>>>(vis, nullptr, A, V, D, pl.KB, TILE_M, pl.tile_bytes, pl.VT, vis_packed, nullptr);
-    align_pack_kernel<<<gt, 256, 0, st>>>(txt, txt_mask, B, Q, D, pl.KB, TILE_M, pl.tile_bytes, pl.QT, txt_packed, maskbits);
+    align_pack_kernel<<<gv, 256, 0, st>>>(vis, nullptr, A, V, D, pl.KB, TILE_M, pl.tile_bytes, pl.VT, vis_packed, nullptr, vstep);
+    align_pack_kernel<<<gt, 256, 0, st>>>(txt, txt_mask, B, Q, D, pl.KB, TILE_M, pl.tile_bytes, pl.QT, txt_packed, maskbits, TILE_M);
     return cudaGetLastError();
 }
 
@@ -732,13 +761,23 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
                                      int *argq = nullptr) {
     cudaError_t e = align_device_info();
     if (e != cudaSuccess) return e;
-    const AlignPlan pl = align_plan(A, V, B, Q, D);
+    const bool reduce = maxv != nullptr;
+    // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
+    // (rows that are not 16-byte aligned -- odd V without padding, the reference's own layout -- use the shifted staging,
+    // with overlapping tiles 120 factors apart so that whole 32-byte sectors are written; VLGAE_ALIGN_VSTEP=128 for A/B runs)
+    const bool aligned_rows = (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    bool bulk;
+    { const char *bk = getenv("VLGAE_ALIGN_BULK"); bulk = reduce || (bk ? atoi(bk) != 0 : true); }
+    const bool shift = bulk && !(reduce || aligned_rows);
+    int vstep = TILE_M;
+    if (shift) { const char *vs = getenv("VLGAE_ALIGN_VSTEP"); vstep = (vs && atoi(vs) == TILE_M) ? TILE_M : TILE_M - 8; }
+    const AlignPlan pl = align_plan(A, V, B, Q, D, vstep);
     uint8_t *ws = reinterpret_cast<uint8_t *>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     uint8_t *vis_packed = ws;
     uint8_t *txt_packed = vis_packed + pl.vis_packed_bytes;
     uint32_t *maskbits = reinterpret_cast<uint32_t *>(txt_packed + pl.txt_packed_bytes);
 
-    e = align_pack_operands(vis, txt, txt_mask, A, V, B, Q, D, workspace, st);
+    e = align_pack_operands(vis, txt, txt_mask, A, V, B, Q, D, workspace, st, vstep);
     if (e != cudaSuccess) return e;
 
     AlignArgs a{};
@@ -747,13 +786,9 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     a.neg = neg; a.split = split == 1 ? 1 : 3;
     { const char *dbg = getenv("VLGAE_ALIGN_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }  // measurement aids, see the kernel
     a.prof = dmv_profile_buffer();
-    const bool reduce = maxv != nullptr;
     a.maxv = maxv; a.argv = argv; a.maxq = maxq; a.argq = argq;
     if (maxq && pl.QT != 1) return cudaErrorInvalidValue;  // the max over the queries lives inside one query tile
-    // bulk (TMA) stores need 16-byte aligned row segments; otherwise the warps store directly
-    // (rows that are not 16-byte aligned -- odd V without padding, the reference's own layout -- use the shifted staging)
-    const bool aligned_rows = (ldv % 4 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
-    { const char *bk = getenv("VLGAE_ALIGN_BULK"); a.bulk = reduce || (bk ? atoi(bk) != 0 : true); }
+    a.bulk = bulk;
     a.tile_stride = (reduce || aligned_rows) ? TILE_M : TILE_M + 4;
     // shared memory: ring slots (a caption tile, or chunks of an image tile) + staged output tiles
     size_t slot_bytes = (size_t)2 * pl.KB * pl.nq * 128;
@@ -797,7 +832,8 @@ static cudaError_t launch_align_mode(const float *vis, const uint8_t *vis_mask, 
     };
     if (reduce && a.maxq) return pl.KB == 1 ? launch(align_gemm_kernel<1, 3>) : launch(align_gemm_kernel<2, 3>);
     if (reduce) return pl.KB == 1 ? launch(align_gemm_kernel<1, 2>) : launch(align_gemm_kernel<2, 2>);
-    if (a.bulk && a.tile_stride != TILE_M) return pl.KB == 1 ? launch(align_gemm_kernel<1, 1, true>) : launch(align_gemm_kernel<2, 1, true>);
+    if (shift && vstep == TILE_M) return pl.KB == 1 ? launch(align_gemm_kernel<1, 1, TILE_M>) : launch(align_gemm_kernel<2, 1, TILE_M>);
+    if (shift) return pl.KB == 1 ? launch(align_gemm_kernel<1, 1, TILE_M - 8>) : launch(align_gemm_kernel<2, 1, TILE_M - 8>);
     if (pl.KB == 1) return a.bulk ? launch(align_gemm_kernel<1, 1>) : launch(align_gemm_kernel<1, 0>);
     return a.bulk ? launch(align_gemm_kernel<2, 1>) : launch(align_gemm_kernel<2, 0>);
 }

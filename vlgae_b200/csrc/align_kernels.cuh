@@ -32,7 +32,7 @@ struct AlignPlan {
     size_t tile_bytes, vis_packed_bytes, txt_packed_bytes, maskbits_bytes;
 };
 
-AlignPlan align_plan(int A, int V, int B, int Q, int D);
+AlignPlan align_plan(int A, int V, int B, int Q, int D, int vstep = 128);  // vstep: factors between consecutive image tiles
 size_t align_workspace_bytes(int A, int V, int B, int Q, int D);
 // split = 3: bf16 hi/lo split, three MMAs per product (fp32-class); split = 1: single bf16 MMA
 cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float *txt, const uint8_t *txt_mask, int A,
@@ -42,7 +42,7 @@ cudaError_t launch_align(const float *vis, const uint8_t *vis_mask, const float 
 // masked queries: neg / 0).  Workspace: align_workspace_bytes + align_reduce_bytes.
 size_t align_reduce_bytes(int A, int B, int Q);
 cudaError_t align_pack_operands(const float *vis, const float *txt, const uint8_t *txt_mask, int A, int V, int B, int Q, int D,
-                                void *workspace, cudaStream_t st);
+                                void *workspace, cudaStream_t st, int vstep = 128);
 // backward of the logits (align_bwd_kernels.cu): g [B][A][Q][ldg]; grad_vis [A][V][D] and / or grad_txt [B][Q][D] (null = skip);
 // workspace: align_workspace_bytes
 cudaError_t launch_align_backward(const float *g, int ldg, const float *vis, const uint8_t *vis_mask, const float *txt,

@@ -297,6 +297,77 @@ __device__ __forceinline__ void inside_reg(const LogChart &c, const uint16_t *cw
     }
 }
 
+// The same sweep in the LINEAR domain (sums of products on exp(offset scores), as csrc/dmv_gather.cu): the running state of
+// a target is one float per item, a term one FMA -- no exp, no max, no log on the phase's chain, and a third of the
+// instructions per visit, which is what a phase costs at 2-4 active warps per SM sub-partition.  The caller checks the
+// range of the result and falls back to the log-domain sweep above.  X keeps 1 / X for the reverse sweep.
+template <int NT, int CPT>
+__device__ __forceinline__ void inside_lin_reg(const LogChart &c, const uint16_t *cw, int Nb, int len) {
+    const int tid = blk_tid<NT>(), nc = ncells(Nb);
+    const int H = (nc - Nb + CPT - 1) / CPT;
+    int ow[CPT], oi[CPT];
+    float2 ax[CPT], al[CPT], ar[CPT];  // (XL, XR), CL (HAS, NO), CR (HAS, NO)
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int cc = Nb + tid + k * H;
+        const int e = (tid < H && cc < nc) ? (int)cw[cc] : 0;
+        ow[k] = e >> 8; oi[k] = e & 255;
+        ax[k] = al[k] = ar[k] = make_float2(0.f, 0.f);
+    }
+#pragma unroll 1
+    for (int s = 0; s < len; ++s) {
+        const int Ds = dbase(s, Nb);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int w = ow[k], i = oi[k];
+            if ((unsigned)(w - 1 - s) <= (unsigned)s) {  // s + 1 <= w <= 2 s + 1
+                const int j = i + w;
+                if (w <= 2 * s - 1) {
+                    const int Dd = dbase(w - s, Nb);
+                    const float l3 = c.CL[Dd + i].y;
+                    const float2 i3 = c.IL[Ds + j - s];
+                    const float2 i4 = c.IR[Ds + i];
+                    const float r4 = c.CR[Dd + i + s].y;
+                    al[k].x = fmaf(l3, i3.x, al[k].x); al[k].y = fmaf(l3, i3.y, al[k].y);
+                    ar[k].x = fmaf(i4.x, r4, ar[k].x); ar[k].y = fmaf(i4.y, r4, ar[k].y);
+                }
+                const int De = dbase(w - 1 - s, Nb);
+                const float2 la = c.CR[Ds + i], ra = c.CL[De + i + s + 1];
+                ax[k].x = fmaf(la.y, ra.x, ax[k].x);   // XL: CR.NO * CL.HAS
+                ax[k].y = fmaf(la.x, ra.y, ax[k].y);   // XR: CR.HAS * CL.NO
+                if (w - 1 - s != s) {
+                    const float2 lb = c.CR[De + i], rb = c.CL[Ds + j - s];
+                    ax[k].x = fmaf(lb.y, rb.x, ax[k].x);
+                    ax[k].y = fmaf(lb.x, rb.y, ax[k].y);
+                }
+                if (w <= 2 * s) {
+                    const int Dd = De + Nb - (w - 1 - s);
+                    const float l3 = c.CL[Ds + i].y;
+                    const float2 i3 = c.IL[Dd + i + s];
+                    const float2 i4 = c.IR[Dd + i];
+                    const float r4 = c.CR[Ds + j - s].y;
+                    al[k].x = fmaf(l3, i3.x, al[k].x); al[k].y = fmaf(l3, i3.y, al[k].y);
+                    ar[k].x = fmaf(i4.x, r4, ar[k].x); ar[k].y = fmaf(i4.y, r4, ar[k].y);
+                }
+                if (w == s + 1) {
+                    const int cc = Nb + tid + k * H;
+                    const float2 arcl = c.IL[cc], arcr = c.IR[cc];  // linear arc factors
+                    const float2 il = make_float2(ax[k].x * arcl.x, ax[k].x * arcl.y), ir = make_float2(ax[k].y * arcr.x, ax[k].y * arcr.y);
+                    const float l3 = c.CL[i].y, r4 = c.CR[j].y;
+                    float2 vl = make_float2(fmaf(l3, il.x, al[k].x), fmaf(l3, il.y, al[k].y));
+                    float2 vr = make_float2(fmaf(ir.x, r4, ar[k].x), fmaf(ir.y, r4, ar[k].y));
+                    if (i == 0 && w != len) vr = make_float2(0.f, 0.f);  // single-root mask, dmv.py:63 (exp(-1e12))
+                    c.IL[cc] = il; c.IR[cc] = ir;
+                    c.X[cc] = make_float2(ax[k].x > 0.f ? __fdividef(1.f, ax[k].x) : 0.f, ax[k].y > 0.f ? __fdividef(1.f, ax[k].y) : 0.f);
+                    c.CL[cc] = vl;
+                    c.CR[cc] = vr;
+                }
+            }
+        }
+        blk_sync<NT>();
+    }
+}
+
 template <int NT, int CPT>
 __device__ __forceinline__ void viterbi_reg(const MaxChart &c, const uint16_t *cw, int Nb, int len, float mask_zero) {
     const int tid = blk_tid<NT>(), nc = ncells(Nb);
@@ -397,8 +468,11 @@ __device__ __forceinline__ unsigned char *chart_base(unsigned char *small, unsig
     return small + small_bytes(Nb);
 }
 
-template <int NT, int CPT, bool GC>
-__device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
+// LIN: the linear-domain variant (register-state variants with the chart in shared memory only).  It returns false -- having
+// written nothing that the log-domain pass does not overwrite -- when the result left the safe fp32 range or failed its
+// self-check; the caller then runs the log-domain pass.
+template <int NT, int CPT, bool GC, bool LIN>
+__device__ bool log_pass_impl(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
     const int tid = blk_tid<NT>(), N = p.N;
     const int Nb = len + 1, nc = ncells(Nb);
     float *sdec = reinterpret_cast<float *>(small);
@@ -424,7 +498,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     constexpr bool reg_state = CPT > 0;  // the launcher picks CPT so that the sentence's cells fit (cap - 1 words)
 
     float *mu = reinterpret_cast<float *>(small + (((size_t)Nb * 8 * 4 + 15) & ~(size_t)15) + (((size_t)nc * 2 + 15) & ~(size_t)15));
-    float zres = 0.f;
+    float zres = 0.f, ztop = 1.f;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
     int *mukey = attempt == 0 ? reinterpret_cast<int *>(mu) : nullptr;
@@ -461,8 +535,21 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         const int d = cw[cc] >> 8, lo = cw[cc] & 255;
         const float ml = mu[lo], mr = mu[lo + d];
         const float2 vl = c.IL[cc], vr = c.IR[cc];
-        c.IL[cc] = make_float2(__fadd_rn(vl.x, -ml), __fadd_rn(vl.y, -ml));
-        c.IR[cc] = make_float2(__fadd_rn(vr.x, -mr), __fadd_rn(vr.y, -mr));
+        if (LIN) {  // linear arc factors (a score of -1e12 / -1e20 becomes an exact 0)
+            c.IL[cc] = make_float2(fexp(__fadd_rn(vl.x, -ml)), fexp(__fadd_rn(vl.y, -ml)));
+            c.IR[cc] = make_float2(fexp(__fadd_rn(vr.x, -mr)), fexp(__fadd_rn(vr.y, -mr)));
+        } else {
+            c.IL[cc] = make_float2(__fadd_rn(vl.x, -ml), __fadd_rn(vl.y, -ml));
+            c.IR[cc] = make_float2(__fadd_rn(vr.x, -mr), __fadd_rn(vr.y, -mr));
+        }
+    }
+    if (LIN) {
+#pragma unroll 1
+        for (int i = tid; i < Nb; i += NT) {  // STOP factors of the width-0 items
+            const float2 l = c.CL[i], r = c.CR[i];
+            c.CL[i] = make_float2(fexp(l.x), fexp(l.y));
+            c.CR[i] = make_float2(fexp(r.x), fexp(r.y));
+        }
     }
     if (!reg_state) {
         const float4 init = make_float4(NEG_BIG, 0.f, NEG_BIG, 0.f);
@@ -473,7 +560,9 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     if (prof) p.prof[0] = clock64() - t0c;
 
     // ---------------- inside ----------------
-    if (reg_state) {
+    if (LIN) {
+        inside_lin_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len);
+    } else if (reg_state) {
         inside_reg<NT, (CPT > 0 ? CPT : 1)>(c, cw, Nb, len, p.mask_zero);
     } else {
         // one phase per width, as in inside_reg (the span's owner finalises IL / IR and, through the same-span terms,
@@ -544,6 +633,17 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
             blk_sync<NT>();
         }
     }
+    if (LIN) {
+        ztop = c.CR[cidx(0, len, Nb)].y;          // linear domain
+        if (!(ztop > 1e-30f && ztop < 1e30f)) {   // out of the safe range (also NaN): the log-domain pass takes over
+            blk_sync<NT>();
+            return false;
+        }
+        zres = __logf(ztop);
+        if (fabsf(zres) <= 16.f || len == 0) break;
+        blk_sync<NT>();
+        continue;
+    }
     zres = c.CR[cidx(0, len, Nb)].y;  // dmv.py:65, minus the offsets
     // (chart values of magnitude <= max(48, len) keep one fp32 ulp <= 8e-6; n = 128 without the second sweep: |gpu - fp64|
     // 5.5e-6 instead of 1.8e-6, 6.9 instead of 8.9 ms at B = 512)
@@ -551,8 +651,11 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     blk_sync<NT>();
     }
     if (prof) p.prof[1] = clock64() - t0c;
-    if (tid == 0) p.Z[b] = zres + mu[Nb];
-    if (!want_grad) { blk_sync<NT>(); return; }
+    if (LIN && !(fabsf(zres) <= 40.f)) { blk_sync<NT>(); return false; }  // the corrected offsets did not bring Z' near 1
+    if (!LIN || !want_grad) {
+        if (tid == 0) p.Z[b] = zres + mu[Nb];
+    }
+    if (!want_grad) { blk_sync<NT>(); return true; }
 
     // ---------------- outside (explicit reverse sweep) ----------------
     {
@@ -561,7 +664,7 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
 #pragma unroll 1
         for (int t = tid; t < 2 * nc; t += NT) g4[t] = z;
         blk_sync<NT>();
-        if (tid == 0) c.gCR[cidx(0, len, Nb)].y = p.gZ ? p.gZ[b] : 1.f;
+        if (tid == 0) c.gCR[cidx(0, len, Nb)].y = LIN ? __fdividef(p.gZ ? p.gZ[b] : 1.f, ztop) : (p.gZ ? p.gZ[b] : 1.f);
         blk_sync<NT>();
     }
     unsigned rw_next = __float2uint_rz(__fdividef(1048576.0f, (float)(Nb - len))) + 2u;
@@ -578,6 +681,44 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
         const unsigned rw = rw_next;
         rw_next = __float2uint_rz(__fdividef(1048576.0f, (float)(np + 1))) + 2u;
         const int pb = dbase(w, Nb);
+        if (LIN) {
+            // linear adjoints (alpha_P += alpha_L alpha_R  =>  beta_L += beta_P alpha_R, beta_R += beta_P alpha_L): the same
+            // tasks and the same single writer per accumulator word, one FMA per term instead of an exponential
+#pragma unroll 1
+            for (int t = tid; t < ntask; t += NT) {
+                const int a = (int)(((unsigned)t * rw) >> 20), i = t - a * np;
+                const float2 bl = c.gCL[pb + i];
+                float2 br = c.gCR[pb + i];
+                if (i == 0 && w != len) br = make_float2(0.f, 0.f);  // the mask overwrote CR[0][w]: nothing passes
+                const int cl3 = cidx(i, a, Nb), cr3 = cidx(i + a, w - a, Nb);
+                const int cl4 = cl3 + Nb - a, cr4 = cr3 - Nb + w - a;
+                const float lv3 = c.CL[cl3].y;
+                const float2 rv3 = c.IL[cr3];
+                const float2 lv4 = c.IR[cl4];
+                const float rv4 = c.CR[cr4].y;
+                const float o1 = c.gCL[cl3].y, o4 = c.gCR[cr4].y;
+                const float2 o2 = c.gIL[cr3], o3 = c.gIR[cl4];
+                c.gCL[cl3].y = fmaf(bl.x, rv3.x, fmaf(bl.y, rv3.y, o1));
+                c.gIL[cr3] = make_float2(fmaf(bl.x, lv3, o2.x), fmaf(bl.y, lv3, o2.y));
+                c.gIR[cl4] = make_float2(fmaf(br.x, rv4, o3.x), fmaf(br.y, rv4, o3.y));
+                c.gCR[cr4].y = fmaf(br.x, lv4.x, fmaf(br.y, lv4.y, o4));
+            }
+            blk_sync<NT>();
+#pragma unroll 1
+            for (int t = tid; t < ntask; t += NT) {
+                const int a = (int)(((unsigned)t * rw) >> 20), i = t - a * np;
+                const float2 gil = c.gIL[pb + i], gir = c.gIR[pb + i], il = c.IL[pb + i], ir = c.IR[pb + i], ix = c.X[pb + i];
+                // beta X = sum_v beta I[v] * arc[v],  arc[v] = I[v] / X
+                const float bxl = fmaf(gil.x, il.x, gil.y * il.y) * ix.x, bxr = fmaf(gir.x, ir.x, gir.y * ir.y) * ix.y;
+                const int cl = cidx(i, a, Nb), cr = cidx(i + a + 1, w - 1 - a, Nb);
+                const float2 lv = c.CR[cl], rv = c.CL[cr];
+                const float2 ol = c.gCR[cl], orr = c.gCL[cr];
+                c.gCR[cl] = make_float2(fmaf(bxr, rv.y, ol.x), fmaf(bxl, rv.x, ol.y));    // CR.HAS from XR (x CL.NO), CR.NO from XL (x CL.HAS)
+                c.gCL[cr] = make_float2(fmaf(bxl, lv.y, orr.x), fmaf(bxr, lv.x, orr.y));  // CL.HAS from XL (x CR.NO), CL.NO from XR (x CR.HAS)
+            }
+            blk_sync<NT>();
+            continue;
+        }
         // phase A'(w): complete parents of width w (steps 3, 4 transposed)
 #pragma unroll 1
         for (int t = tid; t < ntask; t += NT) {
@@ -622,6 +763,36 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     if (prof) p.prof[2] = clock64() - t0c;
 
     // ---------------- outputs ----------------
+    if (LIN) {
+        // alpha * beta = d (gZ log Z) / d (log potential), in place; then the self-check: every word has exactly one head, so
+        // its arc marginals sum to gZ
+#pragma unroll 1
+        for (int cc = tid; cc < nc; cc += NT) {
+            if (cc < Nb) {
+                const float2 a = c.CL[cc], g = c.gCL[cc], a2 = c.CR[cc], g2 = c.gCR[cc];
+                c.gCL[cc] = make_float2(a.x == 0.f ? 0.f : a.x * g.x, a.y == 0.f ? 0.f : a.y * g.y);
+                c.gCR[cc] = make_float2(a2.x == 0.f ? 0.f : a2.x * g2.x, a2.y == 0.f ? 0.f : a2.y * g2.y);
+            } else {
+                const float2 a = c.IL[cc], g = c.gIL[cc], a2 = c.IR[cc], g2 = c.gIR[cc];
+                c.gIL[cc] = make_float2(a.x == 0.f ? 0.f : a.x * g.x, a.y == 0.f ? 0.f : a.y * g.y);
+                c.gIR[cc] = make_float2(a2.x == 0.f ? 0.f : a2.x * g2.x, a2.y == 0.f ? 0.f : a2.y * g2.y);
+            }
+        }
+        blk_sync<NT>();
+        const float gz = p.gZ ? p.gZ[b] : 1.f;
+        bool good = true;
+#pragma unroll 1
+        for (int k = 1 + tid; k < Nb; k += NT) {
+            float t0 = 0.f;
+            for (int h = 0; h < k; ++h) { const float2 v = c.gIR[cidx(h, k - h, Nb)]; t0 += v.x + v.y; }       // heads to the left
+            for (int h = k + 1; h < Nb; ++h) { const float2 v = c.gIL[cidx(k, h - k, Nb)]; t0 += v.x + v.y; }  // heads to the right
+            if (!(fabsf(t0 - gz) <= 1e-3f * fabsf(gz) + 1e-30f)) good = false;
+        }
+        if (NT == 32) good = __all_sync(0xffffffffu, good);
+        else good = __syncthreads_and(good);
+        if (!good) return false;
+        if (tid == 0) p.Z[b] = zres + mu[Nb];
+    }
     if (p.gattach) {
         float2 *ga = reinterpret_cast<float2 *>(p.gattach + (size_t)b * N * N * 2);
 #pragma unroll 1
@@ -652,6 +823,15 @@ __device__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small,
     }
     blk_sync<NT>();
     if (prof) p.prof[3] = clock64() - t0c;
+    return true;
+}
+
+template <int NT, int CPT, bool GC>
+__device__ __forceinline__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
+    if constexpr (CPT > 0 && !GC) {
+        if (!p.no_linear && log_pass_impl<NT, CPT, GC, true>(p, b, len, small, chart)) return;
+    }
+    log_pass_impl<NT, CPT, GC, false>(p, b, len, small, chart);
 }
 
 // ---------------------------------------------------------------------------------------------
