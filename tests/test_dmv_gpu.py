@@ -441,3 +441,20 @@ def test_dependency_crf_golden(golden, dev, name):
         np.testing.assert_array_equal(predicted.cpu().numpy(), oheads[:, 1:])
     finally:
         ts.semirings.semirings.NEGINF = old
+
+
+@pytest.mark.parametrize("lin", ["0", "1"])
+def test_frontier_linear_variant_off_and_at_every_length(dev, lin):
+    """The linear-domain frontier sweeps are length-bound by default (<= 24 words, csrc/dmv_launch.cu).  The switch is read
+    once per process, so the golden-vector and boundary tests of the frontier schedule are re-run in a child process with the
+    variant off (0) and forced on for every length (1): all three settings must meet the same parity bar."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VLGAE_FRONTIER_LINEAR=lin)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_dmv_gpu.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "(golden_reference_vectors or launch_variant_boundaries or tie_stress or full_length) and frontier"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -33,7 +33,8 @@ struct DmvArgs {
     int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
     int no_offsets;    // debug: log-semiring sweeps on the raw scores (no per-word offsets)
-    int no_linear;     // frontier schedule: keep the register-state log-semiring sweeps in the log domain (debug / A-B runs)
+    int lin_max_len;   // frontier schedule: sentences of at most this many words run the register-state log-semiring sweeps in the
+                       // LINEAR domain (0 = never; see launch_dmv for the default and why it is length-bound)
     float retry_above; // log-semiring sweeps: repeat once with corrected offsets when |log Z'| exceeds this (0 = default)
     // gather schedule (linear-domain log semiring): redo[b] = 1 when sentence b failed the sweep's self-check; the
     // follow-up frontier launch handles exactly the sentences with only[b] != 0 (null = all)

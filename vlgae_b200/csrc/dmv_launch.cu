@@ -257,11 +257,17 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     a.nb_lo = 0; a.nb_hi = a.N;
     static const int env_no_off = env_int("VLGAE_DMV_NO_OFFSETS", 0);
     a.no_offsets = env_no_off;
-    // opt-in: 53.3 -> 49.4 us on the cfg2 batch and marginals 5x closer to the exact ones (2.5e-7 vs 1.3e-6 from fp64) -- but the
-    // reference's own fp32 sweep is 1.0012e-5 from fp64 on that batch, so the closer result lands 1.0014e-5 from the
-    // REFERENCE, a hair outside the plain 1e-5 gate that the log-domain sweep passes (9.78e-6).  Parity first: off by default.
-    static const int env_lin = env_int("VLGAE_FRONTIER_LINEAR", 0);
-    a.no_linear = !env_lin;
+    // Linear-domain frontier sweeps (dmv_frontier.cu, LIN) for sentences of <= 24 words by default.  The variant is faster
+    // (512 x 8 words: 19.0 -> 27.0 M sentences/s, cfg1 +9 %, 100k captions +4 %; 40 words: 53.3 -> 49.4 us) and closer to the
+    // exact marginals everywhere (2.5e-7 instead of 1.3e-6 from fp64 on the cfg2 batch) -- and exactly that breaks the plain
+    // 1e-5 gate on LONG sentences: the reference's own fp32 sweep is 1.0012e-5 from fp64 on the cfg2 batch (its error grows
+    // with |log Z| ~ 4 len: one ulp is 1.5e-5 from 128 on), so the closer result lands 1.0014e-5 from the REFERENCE where the
+    // log-domain sweep happens to land at 9.78e-6.  Up to 24 words |log Z| < 128 keeps the reference within ~5e-6 of fp64 and
+    // both arithmetics within the tolerance; beyond, parity with the reference comes first.  Charts of 46..72 positions are
+    // slower in the linear variant anyway (five cells per thread: n = 64 x 512 711k -> 650k sentences/s).
+    // VLGAE_FRONTIER_LINEAR = 0: never, 1: every length, n > 1: up to n words.
+    static const int env_lin = env_int("VLGAE_FRONTIER_LINEAR", 24);
+    a.lin_max_len = env_lin == 1 ? 1 << 20 : env_lin;
     static const int env_retry = env_int("VLGAE_DMV_RETRY_ABOVE", 0);
     a.retry_above = (float)env_retry;
     static const int env_sched = [] {
