@@ -181,6 +181,13 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             a.share_flag = (unsigned *)(share + (((size_t)B * stride * 4 + 15) & ~(size_t)15));
             a.share_epoch = ++epoch;
             a.share_stride = stride;
+            if (B <= (int)sizeof(a.len_inline)) {  // the lengths are host-readable: hand them over by value
+                for (int b = 0; b < B; ++b) {
+                    const int64_t l = lengths_host[b];
+                    a.len_inline[b] = (unsigned char)(l < 0 ? 0 : (l > 255 ? 255 : l));
+                }
+                a.n_len_inline = B;
+            }
             static const bool trace = getenv("VLGAE_E2E_TRACE") != nullptr;  // host-side breakdown of the call (debug)
             const auto t_launch = std::chrono::steady_clock::now();
             rc = run_dmv(a, 3, nullptr, 0, stream);

@@ -100,7 +100,7 @@ template <int NT>
 __device__ __forceinline__ int blk_tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
 
 __device__ __forceinline__ int clamp_len(const DmvArgs &p, int b) {
-    int len = (int)p.lengths[b];
+    int len = b < p.n_len_inline ? (int)p.len_inline[b] : (int)p.lengths[b];
     return len < 0 ? 0 : (len > p.N - 1 ? p.N - 1 : len);
 }
 

@@ -50,6 +50,10 @@ struct DmvArgs {
     unsigned *share_flag;    // [B]
     unsigned share_epoch;
     int share_stride;        // floats per sentence: N * 8 + 4 * ncells(N)
+    // host entry point: the lengths are in HOST memory, and reading one from there is a PCIe round trip in front of a CTA's
+    // first score load; the host side has them for free, so up to 256 travel in the kernel parameters instead
+    int n_len_inline;               // sentences b < n_len_inline take their length from len_inline[b]
+    unsigned char len_inline[256];  // clamped to [0, 255] (charts of that path have <= 72 positions)
 };
 
 // passes bitmask: 1 = log semiring, 2 = max semiring
