@@ -1049,8 +1049,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? (CPT >= 4 ? 1 : 2) : (NT == 25
         const int len = clamp_len(p, b);  // read once: the lengths may live in host memory (one PCIe round trip)
         if (len + 1 < p.nb_lo || len + 1 > p.nb_hi) continue;
         unsigned char *chart = GC ? reinterpret_cast<unsigned char *>(p.workspace) + (size_t)blockIdx.x * p.ws_stride : nullptr;
+#ifdef VLGAE_TIMELINE  // debug build (nvcc -DVLGAE_TIMELINE): the pointer kept live across the sweeps costs the 64-register
+                       // variants 2 us on the cfg2 batch, so the default build does not carry it
+        long long *tl = (p.prof && p.prof_all && threadIdx.x == 0) ? p.prof + 8 + ((size_t)which * p.B + b) * 2 : nullptr;
+        if (tl) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl[0]));
+#endif
         if (which == 0) log_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
         else max_pass<NT, CPT, GC>(p, b, len, smem_raw, chart);
+#ifdef VLGAE_TIMELINE
+        if (tl) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl[1]));
+#endif
     }
 }
 

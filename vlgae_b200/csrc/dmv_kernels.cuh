@@ -32,6 +32,8 @@ struct DmvArgs {
     int nb_lo, nb_hi;  // this launch handles sentences with nb_lo <= len + 1 <= nb_hi (length buckets)
     int smem_n;        // chart positions the shared-memory layout is sized for (>= nb_hi)
     long long *prof;   // optional [8] cycle counters written by the CTA of sentence 0 (debug)
+    int prof_all;      // debug (build with -DVLGAE_TIMELINE, run with VLGAE_PROF_ALL=1): prof holds 8 + 4 B more words,
+                       // %globaltimer at the start / end of every work item of the frontier kernel
     int no_offsets;    // debug: log-semiring sweeps on the raw scores (no per-word offsets)
     int lin_max_len;   // frontier schedule: sentences of at most this many words run the register-state log-semiring sweeps in the
                        // LINEAR domain (0 = never; see launch_dmv for the default and why it is length-bound)

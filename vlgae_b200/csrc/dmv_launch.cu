@@ -272,6 +272,8 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     // VLGAE_FRONTIER_LINEAR = 0: never, 1: every length, n > 1: up to n words.
     static const int env_lin = env_int("VLGAE_FRONTIER_LINEAR", 24);
     a.lin_max_len = env_lin == 1 ? 1 << 20 : env_lin;
+    static const int env_prof_all = env_int("VLGAE_PROF_ALL", 0);
+    a.prof_all = env_prof_all;
     static const int env_retry = env_int("VLGAE_DMV_RETRY_ABOVE", 0);
     a.retry_above = (float)env_retry;
     static const int env_sched = [] {
