@@ -254,9 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
     // OVERLAP by 8 factors and tile t > 0 stores, of row r, the 120 floats [120 t + e_r, 120 (t + 1) + e_r), e_r < 8 chosen so
     // that the segment starts on a sector boundary of the global row -- every sector of a row except its first and its
     // last is then written whole, by one bulk copy.  1369 factors are 12 tiles either way it is counted in pairs (6).
+    // (Owning whole 128-byte lines instead -- tiles 96 factors apart, the same code with U = 32 -- was measured too: 14 tiles =
+    // 7 pairs, 2.43 ms against 2.25 ms; not instantiated.)
     constexpr bool SHIFT = VSTEP != 0;
     static_assert(!SHIFT || MODE == 1, "the shifted staging belongs to the materialising bulk-store mode");
-    static_assert(VSTEP == 0 || VSTEP == TILE_M || VSTEP == TILE_M - 8, "tile step: 128 or 120");
+    static_assert(VSTEP == 0 || VSTEP == TILE_M || VSTEP == TILE_M - 8 || VSTEP == TILE_M - 32, "tile step: 128, 120 or 96");
     constexpr int TS = SHIFT ? TILE_M + 4 : TILE_M;
     constexpr bool shifted = SHIFT;
     constexpr int VS = SHIFT ? VSTEP : TILE_M;  // factor step between tiles
@@ -639,8 +641,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_gemm_kernel(AlignArgs p) {
                                     const int tg = vt0 + t;
                                     int x0 = 0, x1 = min(TILE_M, p.ldv - tg * VS);
                                     if (VS != TILE_M) {
-                                        const uint32_t k8 = (uint32_t)(reinterpret_cast<uintptr_t>(tile_row0) >> 2) & 7u;  // VS % 8 == 0
-                                        const int er = (int)((8u - ((k8 + (uint32_t)row * (V & 7u)) & 7u)) & 7u);
+                                        constexpr uint32_t U = TILE_M - VS;  // floats per owned unit: a 32-byte sector (8) or a 128-byte line (32)
+                                        const uint32_t k8 = (uint32_t)(reinterpret_cast<uintptr_t>(tile_row0) >> 2) & (U - 1);  // VS % U == 0
+                                        const int er = (int)((U - ((k8 + (uint32_t)row * (V & (U - 1))) & (U - 1))) & (U - 1));
                                         if (tg > 0) x0 = er;
                                         if (tg < VT - 1) x1 = VS + er;
                                     }
@@ -728,7 +731,7 @@ AlignPlan align_plan(int A, int V, int B, int Q, int D, int vstep) {
 }
 
 size_t align_workspace_bytes(int A, int V, int B, int Q, int D) {
-    const AlignPlan pl = align_plan(A, V, B, Q, D), pd = align_plan(A, V, B, Q, D, TILE_M - 8);  // room for either tiling
+    const AlignPlan pl = align_plan(A, V, B, Q, D), pd = align_plan(A, V, B, Q, D, TILE_M - 32);  // room for any tiling
     return (pl.vis_packed_bytes > pd.vis_packed_bytes ? pl.vis_packed_bytes : pd.vis_packed_bytes) + pl.txt_packed_bytes +
            ((pl.maskbits_bytes + 255) & ~(size_t)255) + 1024;
 }
