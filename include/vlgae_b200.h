@@ -132,6 +132,20 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
                          int64_t *heads_host, void *stream);
 
 /*
+ * The same call without the final synchronisation: it returns once the work is enqueued on `stream`
+ * (the stream semantics every torch operator of the reference has -- torch_struct/dmv.py runs
+ * asynchronously on the current stream and the caller synchronises when it reads a result).  The
+ * host buffers must stay valid and untouched until `stream` has drained; the results are in host
+ * memory from then on.  Calls on different streams may be in flight together (bulk decoding with
+ * two batches double-buffered: the PCIe traffic of one overlaps the sweeps of the other).
+ * Zero-copy only: every buffer must be pinned, Z_host and best_host non-null and N within the
+ * shared-memory charts (N <= 72), otherwise VLGAE_E_INVALID; B > 256 is fine.
+ */
+int vlgae_dmv_parse_host_async(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                               float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                               int64_t *heads_host, void *stream);
+
+/*
  * DMV1o.merge  (distributions.py:253-265): prepend ROOT.
  *   dec [B][n][2][2][2], attach [B][n][n][2], root [B][n]  ->  dec_w [B][n+1][2][2][2], attach_w [B][n+1][n+1][2]
  */

@@ -458,3 +458,45 @@ def test_frontier_linear_variant_off_and_at_every_length(dev, lin):
                         "-k", "(golden_reference_vectors or launch_variant_boundaries or tie_stress or full_length) and frontier"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_host_entry_point_async_two_streams(dev):
+    """vlgae_dmv_parse_host_async: two different batches in flight on two streams (each stream owns its hand-off buffer), then
+    a third call re-using the first stream; after the streams have drained every result equals the synchronous call's bit
+    for bit.  Pageable buffers are refused (the asynchronous call is zero-copy only)."""
+    from vlgae_b200._lib import check, lib
+
+    L_ = lib()
+    batches = []
+    for seed, (B, n) in enumerate([(128, 40), (96, 33), (128, 40)]):
+        md, ma, L = synth(B, n, 40 + seed)
+        rng = np.random.default_rng(seed)
+        L = np.sort(rng.integers(1, n + 1, size=B))[::-1].astype(np.int64).copy()
+        N = md.shape[1]
+        h = {k: torch.from_numpy(v).pin_memory() for k, v in (("md", md), ("ma", ma), ("L", L))}
+
+        def outs():
+            return {"Z": torch.full((B,), -7.0).pin_memory(), "best": torch.full((B,), -7.0).pin_memory(),
+                    "gdec": torch.full(md.shape, -7.0).pin_memory(), "gatt": torch.full(ma.shape, -7.0).pin_memory(),
+                    "heads": torch.full((B, N), -7, dtype=torch.int64).pin_memory()}
+
+        batches.append((B, N, h, outs(), outs()))
+
+    def args(B, N, h, o):
+        return (h["md"].data_ptr(), h["ma"].data_ptr(), h["L"].data_ptr(), B, N, -1e12, o["Z"].data_ptr(), o["gdec"].data_ptr(),
+                o["gatt"].data_ptr(), o["best"].data_ptr(), o["heads"].data_ptr())
+
+    for B, N, h, want, _ in batches:
+        check(L_.vlgae_dmv_parse_host(*args(B, N, h, want), None), "parse_host")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for (B, N, h, _, got), st in zip(batches, (s1, s2, s1)):
+        check(L_.vlgae_dmv_parse_host_async(*args(B, N, h, got), st.cuda_stream), "parse_host_async")
+    s1.synchronize()
+    s2.synchronize()
+    for B, N, h, want, got in batches:
+        for k in want:
+            np.testing.assert_array_equal(got[k].numpy(), want[k].numpy(), err_msg=k)
+    B, N, h, want, got = batches[0]
+    pageable = torch.from_numpy(h["md"].numpy().copy())
+    rc = L_.vlgae_dmv_parse_host_async(pageable.data_ptr(), *args(B, N, h, got)[1:], s1.cuda_stream)
+    assert rc != 0 and b"pinned" in L_.vlgae_last_error()

@@ -28,6 +28,8 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlgae_dmv_parse_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vlgae_dmv_parse_host_async": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlgae_dmv_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                                 c_void_p]),
     "vlgae_deptree_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -116,9 +116,10 @@ int vlgae_dmv_parse(const float *dec, const float *attach, const int64_t *length
     return run_dmv(a, 3, workspace, workspace_bytes, stream);
 }
 
-int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
-                         float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
-                         int64_t *heads_host, void *stream) {
+// async_only: vlgae_dmv_parse_host_async -- zero-copy or nothing, and no synchronisation
+static int parse_host_impl(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                           float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                           int64_t *heads_host, void *stream, bool async_only) {
     int rc = check_dmv(dec_host, attach_host, lengths_host, B, N);
     if (rc) return rc;
     if (B == 0) return VLGAE_OK;
@@ -152,16 +153,32 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             const bool want_grad = gdec_host || gattach_host;
             // device scratch through which the log CTA of a sentence hands the staged inputs to the max CTA
             // (DmvArgs::share): every input byte crosses PCIe once instead of twice
-            static thread_local unsigned char *share = nullptr;
-            static thread_local size_t share_bytes = 0;
-            static thread_local unsigned epoch = 0;
-            static thread_local int share_dev = -1;
-            const int stride = N * 8 + 4 * (N * (N + 1) / 2);
-            const size_t need = (size_t)B * stride * 4 + (size_t)B * 4 + 64;
+            // one buffer per (device, stream): calls in flight on different streams (vlgae_dmv_parse_host_async) must not
+            // share it; calls on one stream are serialised by the stream
+            struct Share { unsigned char *buf; size_t bytes; unsigned epoch; int dev; cudaStream_t st; };
+            static thread_local Share shares[4] = {};
+            static thread_local int share_next = 0;
             int cur_dev = 0;
             cudaGetDevice(&cur_dev);
-            if (share && share_dev != cur_dev) { share = nullptr; share_bytes = 0; }  // another device: its own buffer (the old one stays with its device)
-            share_dev = cur_dev;
+            Share *sh = nullptr;
+            for (Share &c : shares)
+                if (c.buf && c.dev == cur_dev && c.st == st) sh = &c;
+            if (!sh) {
+                for (Share &c : shares)
+                    if (!c.buf) { sh = &c; break; }
+                if (!sh) {  // every slot taken: recycle one (its owner's work is drained first)
+                    sh = &shares[share_next];
+                    share_next = (share_next + 1) % 4;
+                    if (sh->dev == cur_dev) { cudaStreamSynchronize(sh->st); cudaFree(sh->buf); }
+                    *sh = Share{};
+                }
+                sh->dev = cur_dev; sh->st = st;
+            }
+            unsigned char *&share = sh->buf;
+            size_t &share_bytes = sh->bytes;
+            unsigned &epoch = sh->epoch;
+            const int stride = N * 8 + 4 * (N * (N + 1) / 2);
+            const size_t need = (size_t)B * stride * 4 + (size_t)B * 4 + 64;
             if (share_bytes < need) {
                 if (share) { cudaStreamSynchronize(st); cudaFree(share); share = nullptr; share_bytes = 0; }
                 cudaError_t ea = cudaMalloc((void **)&share, need);
@@ -192,6 +209,7 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             const auto t_launch = std::chrono::steady_clock::now();
             rc = run_dmv(a, 3, nullptr, 0, stream);
             if (rc) return rc;
+            if (async_only) return VLGAE_OK;  // results are in host memory once `stream` has drained
             const auto t_issued = std::chrono::steady_clock::now();
             cudaError_t es = cudaStreamSynchronize(st);
             if (trace) {
@@ -203,6 +221,8 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
             return es == cudaSuccess ? VLGAE_OK : cuda_fail(es, "sync");
         }
     }
+    if (async_only)
+        return fail(VLGAE_E_INVALID, "%s", "vlgae_dmv_parse_host_async needs pinned host buffers (Z and best included) and N within shared memory");
     // one device arena: dec | attach | gdec | gattach | Z | best | lengths | heads | workspace
     const size_t fl = nd + na + nd + na + 2 * (size_t)B;
     const size_t bytes = ((fl * 4 + 15) & ~(size_t)15) + (size_t)B * 8 + (size_t)B * N * 8 + 256 + ws;
@@ -245,6 +265,21 @@ int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const 
     CK(cudaStreamSynchronize(st), "sync");
 #undef CK
     return VLGAE_OK;
+}
+
+int vlgae_dmv_parse_host(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                         float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                         int64_t *heads_host, void *stream) {
+    return parse_host_impl(dec_host, attach_host, lengths_host, B, N, mask_zero, Z_host, gdec_host, gattach_host, best_host,
+                           heads_host, stream, false);
+}
+
+int vlgae_dmv_parse_host_async(const float *dec_host, const float *attach_host, const int64_t *lengths_host, int B, int N,
+                               float mask_zero, float *Z_host, float *gdec_host, float *gattach_host, float *best_host,
+                               int64_t *heads_host, void *stream) {
+    if (!Z_host || !best_host) return fail(VLGAE_E_INVALID, "%s", "Z_host and best_host must be non-null");
+    return parse_host_impl(dec_host, attach_host, lengths_host, B, N, mask_zero, Z_host, gdec_host, gattach_host, best_host,
+                           heads_host, stream, true);
 }
 
 int vlgae_dmv_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
