@@ -933,6 +933,46 @@ def run_b200_arm(args):
             in_flight[f"in_flight_{depth}"] = {"us_per_batch": ms_if / n_if * 1e3, "value": B * world * n_if / (ms_if * 1e-3),
                                                "unit": "sentences/s", "steps": n_if,
                                                "roofline_frac": mufu0 * n_if / (ms_if * 1e-3) / peaks["mufu"]}
+    # ---- the headline with the linear-domain sweeps at EVERY length (vlgae_dmv_set_linear_max_len; default: <= 24 words) ----
+    linear_leg = None
+    if not args.no_legs and rank == 0:
+        check(L_.vlgae_dmv_set_linear_max_len(1 << 20), "set_linear_max_len")
+        try:
+            for k in range(5):
+                step(k)
+            torch.cuda.synchronize()
+            n_lin = max(40, min(args.steps, 400))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(n_lin):
+                step(args.warmup + k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_lin = e0.elapsed_time(e1) / n_lin
+            step(0)
+            torch.cuda.synchronize()
+            g_lin = pool[0][3].gattach.cpu().numpy()
+            lin_par = {"heads_bit_exact": bool(np.array_equal(pool[0][3].heads.cpu().numpy(), oheads)),
+                       "marginal_max_abs_vs_f64": float(np.abs(g_lin - ogatt64).max())}
+            if golden is not None:
+                lin_par["marginal_max_abs_vs_reference"] = float(np.abs(g_lin - golden["grad_attach"]).max())
+                lin_par["reference_marginal_max_abs_vs_f64"] = float(np.abs(golden["grad_attach"] - ogatt64).max())
+                lin_par["Z_max_rel_vs_reference"] = float(np.abs((pool[0][3].Z.cpu().numpy() - golden["partition"][:, 0]) / golden["partition"][:, 0]).max())
+            lin_par["rule"] = ("three-way: where |gpu - reference| exceeds 1e-5 the GPU result must be at least as close to the fp64 "
+                               "evaluation as the reference is")
+            lin_ok = lin_par["heads_bit_exact"] and lin_par["marginal_max_abs_vs_f64"] <= 1e-5 and (
+                golden is None or lin_par["marginal_max_abs_vs_reference"] <= 1e-5
+                or lin_par["marginal_max_abs_vs_f64"] <= lin_par["reference_marginal_max_abs_vs_f64"])
+            lin_par["gate"] = "pass" if lin_ok else "FAIL"
+            if not lin_ok:
+                raise SystemExit(f"bench.py: parity gate failed on leg cfg2_linear_domain: {lin_par}")
+            linear_leg = {"workload": "the headline batches with the frontier sweeps in the linear domain at every length "
+                                      "(vlgae_dmv_set_linear_max_len; the default keeps sentences of > 24 words in the log domain so that "
+                                      "the headline stays within a plain 1e-5 of the reference's own fp32 result)",
+                          "us_per_launch": ms_lin * 1e3, "value": B / (ms_lin * 1e-3), "unit": "sentences/s", "steps": n_lin,
+                          "roofline_frac": work_counts(L0)["mufu"] / (ms_lin * 1e-3) / peaks["mufu"], "parity": lin_par}
+        finally:
+            check(L_.vlgae_dmv_set_linear_max_len(-1), "set_linear_max_len")
     del pool, pmd, pma
     torch.cuda.empty_cache()
 
@@ -941,6 +981,8 @@ def run_b200_arm(args):
         in_flight["workload"] = ("the headline batches (cfg2, device-resident, rotating through the same pool) issued round-robin on "
                                  "2 / 4 streams: independent batches in flight together, as in bulk decoding")
         legs["cfg2_in_flight"] = in_flight
+    if linear_leg:
+        legs["cfg2_linear_domain"] = linear_leg
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2: overwritten between launches
     quick = args.quick
     # ---- cfg1 and the cfg3 length sweep: single-GPU configurations, rank 0 at N = 1 ----

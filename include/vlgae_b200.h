@@ -60,6 +60,17 @@ const char *vlgae_last_error(void);
 int vlgae_dmv_set_schedule(int which);
 
 /*
+ * Frontier schedule: sentences of at most `words` words run their log-semiring sweeps in the LINEAR domain (sums of
+ * products on exp(offset scores), self-checked, log-domain fallback inside the CTA; csrc/dmv_frontier.cu, LIN).
+ * words < 0 restores the default (24, or VLGAE_FRONTIER_LINEAR); 0 = never; a large value = every length.
+ * The linear sweeps are faster (cfg2 batch 53 -> 45 us) and closer to the exact marginals (2.5e-7 instead of 1.1e-6
+ * from fp64); the default is length-bound because the reference's own fp32 sweep (torch_struct/dmv.py:47-63 +
+ * helpers.py:150-154) drifts to 1.0e-5 from the exact result at 40 words, and a result that is closer to the truth
+ * than that cannot also stay within 1e-5 of the reference.  Process-wide, like vlgae_dmv_set_schedule.
+ */
+int vlgae_dmv_set_linear_max_len(int words);
+
+/*
  * Debug aid: a device buffer of 8 int64; the CTAs of sentence 0 write cumulative SM cycle counts after each phase
  * ([0..3] log pass: staged, inside done, outside done, outputs written; [4..6] max pass: staged, chart done,
  * back-trace done).  NULL disables it (default).

@@ -500,3 +500,32 @@ def test_host_entry_point_async_two_streams(dev):
     pageable = torch.from_numpy(h["md"].numpy().copy())
     rc = L_.vlgae_dmv_parse_host_async(pageable.data_ptr(), *args(B, N, h, got)[1:], s1.cuda_stream)
     assert rc != 0 and b"pinned" in L_.vlgae_last_error()
+
+
+def test_linear_domain_at_every_length_setter(golden, dev):
+    """vlgae_dmv_set_linear_max_len: the frontier sweeps in the linear domain at every length on the full cfg2 batch -- heads
+    bit-exact, log Z within 1e-4, marginals closer to the fp64 evaluation than the reference's own (three-way rule), and
+    strictly more exact than the default; the default (log domain beyond 24 words) stays within the PLAIN 1e-5 of the reference."""
+    from vlgae_b200 import ops
+    from vlgae_b200._lib import check, lib
+
+    g = golden("dmv_cfg2_full")
+    hmd, hma = oracle.merge(g["dec"], g["attach"], g["root"])
+    md, ma, L = _t(hmd, dev), _t(hma, dev), _t(g["lengths"], dev)
+    _, _, gatt64 = oracle.dmv_log(hmd, hma, g["lengths"], trim=True, f64=True)
+    check(lib().vlgae_dmv_set_schedule(1), "set_schedule")
+    try:
+        dflt = ops.dmv_parse(md, ma, L)
+        d_att = dflt.gattach.cpu().numpy()
+        check(lib().vlgae_dmv_set_linear_max_len(1 << 20), "set_linear_max_len")
+        lin = ops.dmv_parse(md, ma, L)
+        l_att = lin.gattach.cpu().numpy()
+    finally:
+        check(lib().vlgae_dmv_set_linear_max_len(-1), "set_linear_max_len")
+        check(lib().vlgae_dmv_set_schedule(0), "set_schedule")
+    np.testing.assert_array_equal(lin.heads.cpu().numpy(), g["heads"])
+    np.testing.assert_array_equal(lin.best.cpu().numpy(), g["max"][:, 0])
+    np.testing.assert_allclose(lin.Z.cpu().numpy(), g["partition"][:, 0], rtol=Z_RTOL)
+    assert_three_way(l_att, g["grad_attach"], gatt64)
+    assert np.abs(l_att - gatt64).max() < np.abs(d_att - gatt64).max() < 3e-6
+    np.testing.assert_allclose(d_att, g["grad_attach"], rtol=0, atol=MARG_ATOL)  # the default: plain tolerance

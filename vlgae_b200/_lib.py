@@ -18,6 +18,7 @@ PROTOTYPES = {
     "vlgae_version": (c_int, []),
     "vlgae_last_error": (ctypes.c_char_p, []),
     "vlgae_dmv_set_schedule": (c_int, [c_int]),
+    "vlgae_dmv_set_linear_max_len": (c_int, [c_int]),
     "vlgae_dmv_set_profile_buffer": (c_int, [c_void_p]),
     "vlgae_dmv_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vlgae_dmv_inside_outside": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,

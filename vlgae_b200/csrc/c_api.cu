@@ -68,6 +68,10 @@ int vlgae_dmv_set_schedule(int which) {
     vlgae::dmv_set_schedule(which);
     return VLGAE_OK;
 }
+int vlgae_dmv_set_linear_max_len(int words) {
+    vlgae::dmv_set_linear_max_len(words);
+    return VLGAE_OK;
+}
 const char *vlgae_last_error(void) { return g_err; }
 
 size_t vlgae_dmv_workspace_bytes(int B, int N) {

@@ -76,6 +76,7 @@ constexpr int DMV_GATHER_COUNTERS = 16;  // ints reserved behind the redo flags
 bool dmv_gather_fits(int cap, int passes, int smem_optin);
 cudaError_t launch_dmv_gather(DmvArgs a, int passes, int cap, int threads, int sm_count, cudaStream_t st);
 void dmv_set_schedule(int which);  // 0 = automatic, 1 = frontier, 2 = gather
+void dmv_set_linear_max_len(int words);  // frontier schedule: linear-domain sweeps up to this many words; < 0 = the default
 size_t dmv_ws_slice_bytes(int N, int passes);  // what vlgae_dmv_workspace_bytes reserves per CTA (either schedule)
 cudaError_t launch_merge(const float *dec, const float *attach, const float *root, int B, int n, float one, float zero,
                          float *dec_w, float *attach_w, cudaStream_t st);

@@ -120,6 +120,8 @@ static int env_int(const char *name, int dflt) {
 }
 static int g_schedule = 0;  // 0 = automatic, 1 = frontier, 2 = gather
 void dmv_set_schedule(int which) { g_schedule = which; }
+static int g_lin_max_len = -1;  // < 0: the default (VLGAE_FRONTIER_LINEAR, else 24)
+void dmv_set_linear_max_len(int words) { g_lin_max_len = words; }
 static long long *g_prof = nullptr;
 void dmv_set_profile_buffer(long long *buf) { g_prof = buf; }
 long long *dmv_profile_buffer() { return g_prof; }
@@ -271,7 +273,7 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     // slower in the linear variant anyway (five cells per thread: n = 64 x 512 711k -> 650k sentences/s).
     // VLGAE_FRONTIER_LINEAR = 0: never, 1: every length, n > 1: up to n words.
     static const int env_lin = env_int("VLGAE_FRONTIER_LINEAR", 24);
-    a.lin_max_len = env_lin == 1 ? 1 << 20 : env_lin;
+    a.lin_max_len = g_lin_max_len >= 0 ? g_lin_max_len : (env_lin == 1 ? 1 << 20 : env_lin);
     static const int env_prof_all = env_int("VLGAE_PROF_ALL", 0);
     a.prof_all = env_prof_all;
     static const int env_retry = env_int("VLGAE_DMV_RETRY_ABOVE", 0);
