@@ -831,7 +831,8 @@ __device__ bool log_pass_impl(const DmvArgs &p, int b, int len, unsigned char *s
 template <int NT, int CPT, bool GC>
 __device__ __forceinline__ void log_pass(const DmvArgs &p, int b, int len, unsigned char *small, unsigned char *chart) {
     if constexpr (CPT > 0 && !GC) {
-        if (len <= p.lin_max_len && log_pass_impl<NT, CPT, GC, true>(p, b, len, small, chart)) return;
+        if ((len <= p.lin_max_len || (p.lin_long_from > 0 && len >= p.lin_long_from)) &&
+            log_pass_impl<NT, CPT, GC, true>(p, b, len, small, chart)) return;
     }
     log_pass_impl<NT, CPT, GC, false>(p, b, len, small, chart);
 }

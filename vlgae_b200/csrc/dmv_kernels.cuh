@@ -35,6 +35,8 @@ struct DmvArgs {
     int prof_all;      // debug (build with -DVLGAE_TIMELINE, run with VLGAE_PROF_ALL=1): prof holds 8 + 4 B more words,
                        // %globaltimer at the start / end of every work item of the frontier kernel
     int no_offsets;    // debug: log-semiring sweeps on the raw scores (no per-word offsets)
+    int lin_long_from; // ... and so do sentences of at least this many words (0 = none): from ~45 words on the reference's own
+                       // fp32 result is > 1e-5 from the exact one and parity is judged by the three-way rule anyway
     int lin_max_len;   // frontier schedule: sentences of at most this many words run the register-state log-semiring sweeps in the
                        // LINEAR domain (0 = never; see launch_dmv for the default and why it is length-bound)
     float retry_above; // log-semiring sweeps: repeat once with corrected offsets when |log Z'| exceeds this (0 = default)

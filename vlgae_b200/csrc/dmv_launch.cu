@@ -246,7 +246,7 @@ static cudaError_t launch_gather_redo(const DmvArgs &a, int passes, int lo, int 
     DmvArgs r = a;
     r.npass = 1; r.first_pass = 0; r.only = a.redo; r.redo = nullptr; r.workspace = nullptr; r.ws_stride = 0;
     r.nb_lo = lo; r.nb_hi = hi;
-    r.lin_max_len = 0;  // these sentences failed the linear-domain self-check once already: log domain straight away
+    r.lin_max_len = 0; r.lin_long_from = 0;  // these sentences failed the linear-domain self-check once already: log domain straight away
     return launch_frontier_cap(r, 1, hi, st);
 }
 
@@ -269,11 +269,14 @@ cudaError_t launch_dmv(const DmvArgs &a_in, int passes, cudaStream_t st) {
     // 1e-5 gate on LONG sentences: the reference's own fp32 sweep is 1.0012e-5 from fp64 on the cfg2 batch (its error grows
     // with |log Z| ~ 4 len: one ulp is 1.5e-5 from 128 on), so the closer result lands 1.0014e-5 from the REFERENCE where the
     // log-domain sweep happens to land at 9.78e-6.  Up to 24 words |log Z| < 128 keeps the reference within ~5e-6 of fp64 and
-    // both arithmetics within the tolerance; beyond, parity with the reference comes first.  Charts of 46..72 positions are
-    // slower in the linear variant anyway (five cells per thread: n = 64 x 512 711k -> 650k sentences/s).
+    // both arithmetics within the tolerance; beyond (25..44 words), parity with the reference comes first.
     // VLGAE_FRONTIER_LINEAR = 0: never, 1: every length, n > 1: up to n words.
     static const int env_lin = env_int("VLGAE_FRONTIER_LINEAR", 24);
     a.lin_max_len = g_lin_max_len >= 0 ? g_lin_max_len : (env_lin == 1 ? 1 << 20 : env_lin);
+    // ... and again from 45 words on (the five-cells-per-thread charts of 46..72 positions): there the reference's own fp32
+    // result is > 1e-5 from the exact one (1.4e-5 at n = 64), so parity is the three-way rule either way, which the more exact
+    // sweep always meets; n = 64 x 512: 711 k -> 804 k sentences/s.  Off together with the short range (0).
+    a.lin_long_from = a.lin_max_len > 0 ? 45 : 0;
     static const int env_prof_all = env_int("VLGAE_PROF_ALL", 0);
     a.prof_all = env_prof_all;
     static const int env_retry = env_int("VLGAE_DMV_RETRY_ABOVE", 0);
