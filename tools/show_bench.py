@@ -10,9 +10,9 @@ print("parity", {k: v for k, v in d["parity"].items() if "marginal" in k or k ==
 if "cpu_baseline" in d:
     print("cpu_baseline", d["cpu_baseline"])
 for k, v in d.get("legs", {}).items():
-    items = v.items() if k == "cfg3" else [(k, v)]
+    items = [(a, b) for a, b in v.items() if isinstance(b, dict)] if k in ("cfg3", "cfg2_in_flight") else [(k, v)]
     for kk, vv in items:
-        keep = ("us_per_launch", "ms_per_step", "ms_parse", "ms_parse_plus_gather", "value", "exposed_allreduce_us_per_step", "sentences_per_s")
+        keep = ("us_per_launch", "us_per_batch", "ms_per_step", "ms_parse", "ms_parse_plus_gather", "value", "exposed_allreduce_us_per_step", "sentences_per_s")
         print(k, kk, {a: b for a, b in vv.items() if a in keep}, "frac", vv.get("roofline", {}).get("frac"),
               "marg", vv.get("parity", {}).get("marginal_max_abs_vs_f64"))
 a = d.get("alignment")
