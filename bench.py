@@ -822,14 +822,32 @@ def run_b200_arm(args):
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
+    # The K timed steps are captured into ONE CUDA graph and replayed: the same K launches on the same rotating batches,
+    # without a host thread in the loop -- with 8 ranks on one host the python launch loops jitter, and the max over ranks of a
+    # 1 ms region picked that up (every rank's batch takes the same 53.3 us on one GPU, tools/seed_sweep.py).
+    # VLGAE_BENCH_NO_GRAPH=1 times plain stream launches instead.
+    graph, timed_as = None, "K stream launches"
+    if args.steps <= 5000 and not os.environ.get("VLGAE_BENCH_NO_GRAPH"):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for k in range(args.steps):
+                    step(args.warmup + k)
+            timed_as = "one CUDA graph of the K launches, replayed once"
+        except Exception as ex:  # capture refused: fall back to stream launches and say so
+            graph, timed_as = None, f"K stream launches (graph capture failed: {type(ex).__name__})"
+        torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.timed = True
     ev0.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
+    if graph is not None:
+        graph.replay()
+    else:
+        for k in range(args.steps):
+            step(args.warmup + k)
     ev1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -1150,6 +1168,7 @@ def run_b200_arm(args):
                        "parallelism": f"sentence-sharded x{world} (a length-sorted global batch of {world} x 128 captions dealt round-robin: "
                                       "every rank holds the cfg2 length profile, own scores), no collective on the headline path "
                                       "(legs.cfg4 / legs.cfg5 carry the NCCL collectives)",
+                       "timed_as": timed_as,
                        "l2": f"inputs rotate through a pool of {pool_n} distinct batches "
                              f"({pool_n * step_bytes / 2**20:.0f} MiB > L2), no flush needed; legs flush L2 between launches"},
             "e2e": {"value": B * world * e2e_steps / e2e_s, "unit": "sentences/s", "h2d_bytes_per_step": h2d,
