@@ -935,18 +935,43 @@ def run_b200_arm(args):
                     step(k)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(cur)
-            for s_ in ss:
-                s_.wait_event(e0)
-            for k in range(n_if):
-                with torch.cuda.stream(ss[k % depth]):
-                    step(args.warmup + k)
-            for s_ in ss:
-                done = torch.cuda.Event()
-                done.record(s_)
-                cur.wait_event(done)
-            e1.record(cur)
+            g_if = None
+            if graph is not None:  # as the headline: one graph (forked onto the streams inside), no python in the loop
+                try:
+                    g_if = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_if):
+                        cap = torch.cuda.current_stream()
+                        for s_ in ss:
+                            s_.wait_stream(cap)
+                        for k in range(n_if):
+                            with torch.cuda.stream(ss[k % depth]):
+                                step(args.warmup + k)
+                        for s_ in ss:
+                            cap.wait_stream(s_)
+                except Exception:
+                    g_if = None
+                torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
             torch.cuda.synchronize()
+            if g_if is not None:
+                e0.record(cur)
+                g_if.replay()
+                e1.record(cur)
+            else:
+                e0.record(cur)
+                for s_ in ss:
+                    s_.wait_event(e0)
+                for k in range(n_if):
+                    with torch.cuda.stream(ss[k % depth]):
+                        step(args.warmup + k)
+                for s_ in ss:
+                    done = torch.cuda.Event()
+                    done.record(s_)
+                    cur.wait_event(done)
+                e1.record(cur)
+            torch.cuda.synchronize()
+            del g_if
             ms_if, = max_over_ranks(e0.elapsed_time(e1))
             in_flight[f"in_flight_{depth}"] = {"us_per_batch": ms_if / n_if * 1e3, "value": B * world * n_if / (ms_if * 1e-3),
                                                "unit": "sentences/s", "steps": n_if,
